@@ -1,0 +1,206 @@
+"""Synthetic scenes for the rasterization hot path.
+
+The reference ships no scene other than ``ConstructSphere`` (projekt.cpp:4123-4289) and no
+camera, light or resolution constants, so the survey pins them; this module is that pin.
+Everything is generated on the host with numpy float32 and consumed *identically* by the
+CPU oracle and the CUDA path (both read the same camera-space float arrays).
+
+Vertex streams use the reference layout (projekt.h:2-15, projekt.cpp:3898-3934):
+non-indexed, three entries per triangle -- positions v3, colours v4 (r,g,b,a), normals v3,
+uvs v2.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+DRAWS_PER_TRIANGLE = 32  # fixed stride into the SplitMix64 stream, 25 used
+
+
+def splitmix64(seed: int, first: int, count: int) -> np.ndarray:
+    """Outputs ``first .. first+count-1`` of the SplitMix64 stream started at ``seed``.
+
+    Output i of the sequential generator is mix(seed + (i+1)*GOLDEN), so any slice of the
+    stream can be produced in parallel."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(first + 1, first + count + 1, dtype=np.uint64)
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + idx * _GOLDEN
+        z = (z ^ (z >> np.uint64(30))) * _M1
+        z = (z ^ (z >> np.uint64(27))) * _M2
+        return z ^ (z >> np.uint64(31))
+
+
+def u01(bits: np.ndarray) -> np.ndarray:
+    """(next() >> 40) * 2^-24 as float32."""
+    return ((bits >> np.uint64(40)).astype(np.float32)) * np.float32(2.0 ** -24)
+
+
+@dataclass
+class Transform:
+    """projective_transform (projekt.cpp:79-89)."""
+    meters_to_pixels: float
+    screen_center: tuple
+    focal_length: float = 1.0
+    distance_above_target: float = 10.0
+
+
+@dataclass
+class Light:
+    """light_info (projekt.cpp:4026-4027)."""
+    P: tuple = (5.0, 5.0, 8.0)
+    intensity: tuple = (0.8, 0.8, 0.8, 0.0)
+
+
+@dataclass
+class Scene:
+    name: str
+    width: int
+    height: int
+    transform: Transform
+    positions: np.ndarray      # [ntri*3, 3] float32 camera space
+    colors: np.ndarray         # [ntri*3, 4] float32 r,g,b,a
+    normals: np.ndarray        # [ntri*3, 3] float32
+    uvs: np.ndarray            # [ntri*3, 2] float32 (read unconditionally by the reference)
+    object_p: tuple = (0.0, 0.0, 0.0)
+    ambient: tuple = (0.2, 0.2, 0.2, 1.0)
+    lights: list = field(default_factory=lambda: [Light()])
+    clear_color: int = 0
+    clear_depth: float = -1e30
+
+    @property
+    def triangle_count(self) -> int:
+        return self.positions.shape[0] // 3
+
+
+def default_transform(width: int, height: int) -> Transform:
+    return Transform(meters_to_pixels=height / 2.0, screen_center=(width / 2.0, height / 2.0))
+
+
+def _soup_chunk(seed, first_tri, count, width, height, rmin, rmax, tr: Transform, jitter=0.5):
+    f32 = np.float32
+    bits = splitmix64(seed, first_tri * DRAWS_PER_TRIANGLE, count * DRAWS_PER_TRIANGLE)
+    u = u01(bits).reshape(count, DRAWS_PER_TRIANGLE)
+    r = f32(rmin) + u[:, 2] * f32(rmax - rmin)
+    # keep every vertex on screen: centre at least r+2 away from each border
+    cx = (r + f32(2.0)) + u[:, 0] * (f32(width) - f32(2.0) * (r + f32(2.0)))
+    cy = (r + f32(2.0)) + u[:, 1] * (f32(height) - f32(2.0) * (r + f32(2.0)))
+    theta0 = u[:, 3] * f32(2.0 * np.pi)
+    pos = np.empty((count, 3, 3), dtype=f32)
+    col = np.empty((count, 3, 4), dtype=f32)
+    nrm = np.empty((count, 3, 3), dtype=f32)
+    inv_m = f32(1.0) / f32(tr.meters_to_pixels)
+    for k in range(3):
+        d = u[:, 4 + 7 * k: 4 + 7 * (k + 1)]
+        # decreasing angle in screen space => the reference's back-face test passes
+        ang = theta0 - f32(k * 2.0 * np.pi / 3.0) + f32(jitter) * (d[:, 0] - f32(0.5))
+        sx = cx + r * np.cos(ang).astype(f32)
+        sy = cy + r * np.sin(ang).astype(f32)
+        z = f32(-4.0) + d[:, 1] * f32(8.0)
+        # UnprojectVertex (projekt.cpp:147-160): xy = ((D - z)/f) * ((screen - centre)*(1/m))
+        dist = (f32(tr.distance_above_target) - z) / f32(tr.focal_length)
+        pos[:, k, 0] = dist * ((sx - f32(tr.screen_center[0])) * inv_m)
+        pos[:, k, 1] = dist * ((sy - f32(tr.screen_center[1])) * inv_m)
+        pos[:, k, 2] = z
+        col[:, k, 0] = d[:, 2] ** 3
+        col[:, k, 1] = d[:, 3] ** 3
+        col[:, k, 2] = d[:, 4] ** 3
+        col[:, k, 3] = f32(1.0)
+        nx = d[:, 5] - f32(0.5)
+        ny = d[:, 6] - f32(0.5)
+        inv = f32(1.0) / np.sqrt(nx * nx + ny * ny + f32(1.0)).astype(f32)
+        nrm[:, k, 0] = nx * inv
+        nrm[:, k, 1] = ny * inv
+        nrm[:, k, 2] = inv
+    return pos, col, nrm
+
+
+def triangle_soup(name, seed, count, width, height, rmin, rmax, chunk=1 << 20, jitter=0.5) -> Scene:
+    """Random triangle soup in screen space mapped back to camera space."""
+    tr = default_transform(width, height)
+    pos = np.empty((count * 3, 3), dtype=np.float32)
+    col = np.empty((count * 3, 4), dtype=np.float32)
+    nrm = np.empty((count * 3, 3), dtype=np.float32)
+    for first in range(0, count, chunk):
+        n = min(chunk, count - first)
+        p, c, m = _soup_chunk(seed, first, n, width, height, rmin, rmax, tr, jitter)
+        pos[first * 3:(first + n) * 3] = p.reshape(-1, 3)
+        col[first * 3:(first + n) * 3] = c.reshape(-1, 4)
+        nrm[first * 3:(first + n) * 3] = m.reshape(-1, 3)
+    uvs = np.zeros((count * 3, 2), dtype=np.float32)
+    return Scene(name, width, height, tr, pos, col, nrm, uvs)
+
+
+def construct_sphere(step_count: int = 24, radius: float = 0.5):
+    """Host-side restatement of ConstructSphere (projekt.cpp:4123-4289) with a parametric
+    StepCount (the reference hard-codes 24, :4129).  4*S*S - 4*S triangles.  Used for the
+    C5 mesh; config C1 uses the verbatim sphere stored in tests/golden/."""
+    f32 = np.float32
+    S = step_count
+    inc_incl = f32(np.pi) / f32(S)
+    inc_azim = f32(2.0 * np.pi) / f32(S * 2)
+
+    def point(incl, azim):
+        si, ci = np.sin(incl).astype(f32), np.cos(incl).astype(f32)
+        return np.stack([si * np.cos(azim).astype(f32), ci, si * np.sin(azim).astype(f32)], -1)
+
+    ii, aa = np.meshgrid(np.arange(S, dtype=f32), np.arange(2 * S, dtype=f32), indexing="ij")
+    incl, nincl = ii * inc_incl, (ii + 1) * inc_incl
+    azim, nazim = aa * inc_azim, (aa + 1) * inc_azim
+    p1, p2 = point(incl, azim), point(nincl, azim)
+    p3, p4 = point(nincl, nazim), point(incl, nazim)
+    up = np.zeros_like(p1); up[..., 1] = 1.0
+    down = np.zeros_like(p1); down[..., 1] = -1.0
+    blue = ((f32(1.0) + np.cos(azim).astype(f32)) / f32(2.0))
+    nblue = ((f32(1.0) + np.cos(nazim).astype(f32)) / f32(2.0))
+    cur_r = f32(1.0) + ii * (f32(-1.0) / f32(S))      # red 1 -> 0, green 0 -> 1 (:4131-4141)
+    cur_g = ii * (f32(1.0) / f32(S))
+    nxt_r = cur_r + f32(-1.0) / f32(S)
+    nxt_g = cur_g + f32(1.0) / f32(S)
+
+    def colour(r, g, b):
+        return np.stack([r, g, b, np.ones_like(r)], -1).astype(f32)
+
+    c_cur_b, c_nxt_b = colour(cur_r, cur_g, blue), colour(nxt_r, nxt_g, blue)
+    c_nxt_nb, c_cur_nb = colour(nxt_r, nxt_g, nblue), colour(cur_r, cur_g, nblue)
+    top_p = np.stack([up[0], p2[0], p3[0]], 1)                       # [2S, 3, 3]   (:4156-4189)
+    top_c = np.stack([c_cur_b[0], c_nxt_b[0], c_nxt_nb[0]], 1)
+    bot_p = np.stack([p1[S - 1], down[S - 1], p4[S - 1]], 1)        # (:4190-4223)
+    bot_c = np.stack([c_cur_b[S - 1], c_nxt_b[S - 1], c_nxt_nb[S - 1]], 1)
+    m = slice(1, S - 1)                                              # (:4224-4281) two per cell
+    mid_p = np.stack([np.stack([p1[m], p2[m], p3[m]], 2), np.stack([p1[m], p3[m], p4[m]], 2)], 2)
+    mid_c = np.stack([np.stack([c_cur_b[m], c_nxt_b[m], c_nxt_nb[m]], 2),
+                      np.stack([c_cur_b[m], c_nxt_nb[m], c_cur_nb[m]], 2)], 2)
+    nrm = np.concatenate([top_p.reshape(-1, 3), mid_p.reshape(-1, 3), bot_p.reshape(-1, 3)]).astype(f32)
+    col = np.concatenate([top_c.reshape(-1, 4), mid_c.reshape(-1, 4), bot_c.reshape(-1, 4)]).astype(f32)
+    pos = (f32(radius) * nrm).astype(f32)
+    uvs = np.zeros((pos.shape[0], 2), dtype=f32)
+    return pos, col, nrm, uvs
+
+
+def sphere_scene(pos, col, nrm, uvs, width=1920, height=1080, meters_to_pixels=500.0,
+                 focal=2.0, dist=3.0, light_p=(2.0, 2.0, 2.0), name="c1_sphere", object_p=(0.0, 0.0, 0.0)) -> Scene:
+    """Config C1: the reference sphere as one object."""
+    tr = Transform(meters_to_pixels, (width / 2.0, height / 2.0), focal, dist)
+    return Scene(name, width, height, tr, np.ascontiguousarray(pos, np.float32),
+                 np.ascontiguousarray(col, np.float32), np.ascontiguousarray(nrm, np.float32),
+                 np.ascontiguousarray(uvs, np.float32), object_p=object_p,
+                 lights=[Light(P=light_p)])
+
+
+# The named configs of BASELINE.json (sizes, seeds and radii from SURVEY.md 8d).
+CONFIGS = {
+    "c2": dict(seed=0xB2000002, count=1_000_000, width=1920, height=1080, rmin=1.5, rmax=4.0),
+    "c3": dict(seed=0xB2000003, count=50_000, width=3840, height=2160, rmin=32.0, rmax=96.0),
+    "c4": dict(seed=0xB2000004, count=20_000_000, width=16384, height=16384, rmin=2.0, rmax=10.0),
+}
+
+
+def make_config(name: str, scale: float = 1.0) -> Scene:
+    """``scale`` < 1 shrinks the triangle count (parity tests); the bench uses scale 1."""
+    cfg = dict(CONFIGS[name])
+    cfg["count"] = max(1, int(round(cfg["count"] * scale)))
+    return triangle_soup(name, **cfg)

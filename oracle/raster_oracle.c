@@ -1,0 +1,437 @@
+/* TEST INFRASTRUCTURE ONLY -- see raster_oracle.h for scope, pinning and build flags.
+ * Plain C restatement of the reference's scalar Gouraud path; every function cites the
+ * reference lines it follows.  No code here is shared with the CUDA product. */
+#include "raster_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <xmmintrin.h>
+
+/* ---- math layer, pinned exactly as oracle/ref_shim.h pins it ---- */
+
+/* RoundR32ToS32: cvtss2si, round-half-even, NaN/overflow -> INT_MIN (projekt.cpp:402, 3988) */
+static int32_t round_s32(float V) { return _mm_cvtss_si32(_mm_set_ss(V)); }
+static uint32_t round_u32(float V) { return (uint32_t)round_s32(V); }            /* :520-523 */
+static float clamp01(float V) { if(V < 0.0f) V = 0.0f; else if(V > 1.0f) V = 1.0f; return V; }
+static float inner3(const float A[3], const float B[3])                          /* left to right */
+{
+    return A[0]*B[0] + A[1]*B[1] + A[2]*B[2];
+}
+/* Normalize(a) = a * (1/sqrt(a.a))   (projekt.cpp:3926, 4029) */
+static void normalize3(const float A[3], float Out[3])
+{
+    float S = 1.0f/sqrtf(inner3(A, A));
+    Out[0] = S*A[0]; Out[1] = S*A[1]; Out[2] = S*A[2];
+}
+
+/* projekt.cpp:74-93 */
+void orc_project_vertex(const float Cam[3], const orc_transform *T, float Out[3])
+{
+    float Dist = T->DistanceAboveTarget - Cam[2];                /* :81 */
+    Out[0] = 0.0f; Out[1] = 0.0f; Out[2] = 0.0f;                 /* :77 */
+    if(Dist > 0.2f)                                              /* :82, :86 */
+    {
+        float S = (1.0f/Dist)*T->FocalLength;                    /* :88, scalar*scalar first */
+        float Px = S*Cam[0];
+        float Py = S*Cam[1];
+        Out[0] = T->ScreenCenterX + T->MetersToPixels*Px;        /* :89 */
+        Out[1] = T->ScreenCenterY + T->MetersToPixels*Py;
+        Out[2] = Dist + T->MetersToPixels*0.0f;
+    }
+}
+
+/* Gouraud vertex colour, projekt.cpp:4022-4062 (non-bitmap branch).  The reference lights
+ * each edge end separately; the value depends only on the vertex, so it is computed once. */
+static void light_vertex(const float Cam[3], const float Nrm[3], const float Col[4],
+                         const orc_scene *Scene, float Out[4])
+{
+    float C[4] = {0, 0, 0, 0};
+    for(uint32_t L = 0; L < Scene->LightCount; ++L)
+    {
+        const orc_light *Light = Scene->Lights + L;
+        float ToLight[3] = { Light->P[0] - Cam[0], Light->P[1] - Cam[1], Light->P[2] - Cam[2] };
+        float Dir[3];
+        normalize3(ToLight, Dir);                                /* :4029 */
+        if(L == 0)                                               /* :4032-4044 */
+        {
+            for(int i = 0; i < 4; ++i) C[i] = Col[i]*Scene->Ambient[i];
+        }
+        float Dot = clamp01(inner3(Dir, Nrm));                   /* :4047 */
+        for(int i = 0; i < 4; ++i)                               /* :4058 */
+        {
+            C[i] = clamp01(C[i] + Dot*(Col[i]*Light->Intensity[i]));
+        }
+    }
+    for(int i = 0; i < 4; ++i) Out[i] = C[i];
+}
+
+/* projekt.cpp:2-72.  Count == 0 is undefined in the reference (infinite recursion guarded by
+ * Assert, :20-33); here it is a no-op. */
+void orc_merge_sort(uint32_t Count, orc_edge *First, orc_edge *Temp)
+{
+    if(Count <= 1) return;
+    if(Count == 2)                                               /* :9-19 */
+    {
+        if(First[0].YMin > First[1].YMin)
+        {
+            orc_edge T = First[0]; First[0] = First[1]; First[1] = T;
+        }
+        return;
+    }
+    uint32_t Half0 = Count/2, Half1 = Count - Half0;             /* :22-23 */
+    orc_merge_sort(Half0, First, Temp);
+    orc_merge_sort(Half1, First + Half0, Temp);
+    uint32_t A = 0, B = Half0;
+    for(uint32_t Out = 0; Out < Count; ++Out)                    /* :39-59 */
+    {
+        if(A == Half0) Temp[Out] = First[B++];
+        else if(B == Count) Temp[Out] = First[A++];
+        else if(First[A].YMin < First[B].YMin) Temp[Out] = First[A++];
+        else Temp[Out] = First[B++];                             /* ties: right half first */
+    }
+    memcpy(First, Temp, Count*sizeof(orc_edge));                 /* :65-70 */
+}
+
+/* projekt.cpp:3882-4121, PhongShading == 0, Object->Bitmap == 0. */
+int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm,
+                            uint32_t VertexCount, const float P[3], const orc_scene *Scene,
+                            orc_edge *Edges, orc_edge *Temp)
+{
+    static const uint32_t Indices[3][2] = { {0, 1}, {1, 2}, {2, 0} };   /* :3936-3941 */
+    if(Scene->LightCount == 0) return -1;
+    uint32_t TriangleCount = VertexCount/3;                      /* :3886 */
+    uint32_t Visible = 0;
+    for(uint32_t Tri = 0; Tri < TriangleCount; ++Tri)
+    {
+        float Cam[3][3], Proj[3][3], Lit[3][4];
+        for(int v = 0; v < 3; ++v)
+        {
+            for(int c = 0; c < 3; ++c) Cam[v][c] = Pos[9*(size_t)Tri + 3*v + c] + P[c];  /* :3900 */
+            orc_project_vertex(Cam[v], &Scene->Transform, Proj[v]);                    /* :3907 */
+        }
+        /* back-face test, :3926-3927, :3943 with Eye = (0,0,-1) (:3888) */
+        float D1[3] = { Proj[1][0] - Proj[0][0], Proj[1][1] - Proj[0][1], Proj[1][2] - Proj[0][2] };
+        float D2[3] = { Proj[2][0] - Proj[0][0], Proj[2][1] - Proj[0][1], Proj[2][2] - Proj[0][2] };
+        float N1[3], N2[3];
+        normalize3(D1, N1);
+        normalize3(D2, N2);
+        float Cx = N1[1]*N2[2] - N1[2]*N2[1];
+        float Cy = N1[2]*N2[0] - N1[0]*N2[2];
+        float Cz = N1[0]*N2[1] - N1[1]*N2[0];
+        float Facing = 0.0f*Cx + 0.0f*Cy + -1.0f*Cz;
+        if(!(Facing > 0.0f)) continue;
+
+        for(int v = 0; v < 3; ++v)
+        {
+            light_vertex(Cam[v], Nrm + 9*(size_t)Tri + 3*v, Col + 12*(size_t)Tri + 4*v, Scene, Lit[v]);
+        }
+
+        for(uint32_t e = 0; e < 3; ++e)                          /* :3947 */
+        {
+            uint32_t MinI = Indices[e][0], MaxI = Indices[e][1];
+            if(Proj[MinI][1] > Proj[MaxI][1]) { uint32_t T = MinI; MinI = MaxI; MaxI = T; }  /* :3957 */
+            const float *MinV = Proj[MinI], *MaxV = Proj[MaxI];
+            if(!(MaxV[1] > 0)) continue;                         /* :3968 */
+
+            orc_edge *E = Edges + Visible;
+            E->YMax = round_s32(MaxV[1]);                        /* :3988 */
+            float ClippedY = 0, T = 0.0f;
+            if(MinV[1] < 0.0f)                                   /* :3993-3997 */
+            {
+                ClippedY = -MinV[1];
+                T = (-MinV[1])/(MaxV[1] - MinV[1]);
+            }
+            float RoundedMin = (float)round_s32(MinV[1]);
+            E->YMin = (int32_t)((0.0f > RoundedMin) ? 0.0f : RoundedMin);   /* :3999 */
+            E->XMin = MinV[0];                                   /* :4000 */
+            E->ZMin = Cam[MinI][2];                              /* :4001 */
+            if(MinV[1] - MaxV[1] != 0)                           /* :4066 */
+            {
+                float YDiff = (float)E->YMax - (float)E->YMin;   /* :4070 */
+                E->ZGradient = (Cam[MaxI][2] - Cam[MinI][2])/YDiff;          /* :4072 */
+                E->Gradient = (MaxV[0] - MinV[0])/(MaxV[1] - MinV[1]);       /* :4073 */
+                E->XMin += ClippedY*E->Gradient;                 /* :4075 */
+                E->ZMin += ClippedY*E->ZGradient;                /* :4076 */
+                for(int i = 0; i < 4; ++i)                       /* :4091 */
+                {
+                    E->MinColor[i] = (1.0f - T)*Lit[MinI][i] + T*Lit[MaxI][i];
+                }
+                E->Left = (E->YMin == round_s32(Proj[Indices[e][0]][1])) ? 1 : 0;     /* :4093 */
+                for(int i = 0; i < 4; ++i)                       /* :4096-4102 */
+                {
+                    E->ColorGradient[i] = (Lit[MaxI][i] - E->MinColor[i])/YDiff;
+                }
+                E->Triangle = (int32_t)Tri;
+                ++Visible;                                       /* :4068 */
+            }
+        }
+    }
+    orc_merge_sort(Visible, Edges, Temp);                        /* :4117 */
+    return (int32_t)Visible;
+}
+
+/* Running state of one edge while it is in the active list. */
+typedef struct active_edge {
+    float X, Z, C[4];
+    const orc_edge *E;
+} active_edge;
+
+/* projekt.cpp:212-216 / 229-233: does New sort strictly before Old? */
+static int edge_before(const active_edge *New, const active_edge *Old)
+{
+    return New->X < Old->X ||
+           (New->X == Old->X &&
+            (New->E->Gradient < Old->E->Gradient ||
+             (New->E->Gradient == Old->E->Gradient && New->E->Left < Old->E->Left)));
+}
+
+/* projekt.cpp:306-425 (span set-up) and 510-538 (Gouraud pixel loop). */
+static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Row,
+                          int32_t PrimIndex, orc_target *T, orc_stats *Stats)
+{
+    float XDiff = roundf(R->X - L->X);                           /* :311-312 */
+    float CInc[4], ZInc;
+    if(XDiff != 0.0f)                                            /* :333-363 */
+    {
+        for(int i = 0; i < 4; ++i) CInc[i] = (R->C[i] - L->C[i])/XDiff;
+        ZInc = (R->Z - L->Z)/XDiff;
+    }
+    else
+    {
+        for(int i = 0; i < 4; ++i) CInc[i] = 0.0f;
+        ZInc = 0.0f;
+    }
+    float Z = L->Z;                                              /* :375 */
+    float C[4] = { L->C[0], L->C[1], L->C[2], L->C[3] };         /* :379 */
+    float XOffset = 0.0f;
+    float LeftX = L->X;                                          /* :381-390 */
+    if(LeftX < 0) { XOffset = -LeftX; LeftX = 0; }
+    else if(LeftX >= (float)T->Width) { LeftX = (float)T->Width - 1; }
+    float RightX = R->X;                                         /* :392-400 */
+    if(RightX < 0) { RightX = 0; }
+    else if(RightX >= (float)T->Width) { RightX = (float)T->Width - 1; }
+    int32_t MinX = (int32_t)(float)round_s32(LeftX);             /* :402-406 */
+    int32_t MaxX = (int32_t)(float)round_s32(RightX);
+    Z += XOffset*ZInc;                                           /* :408 */
+    for(int i = 0; i < 4; ++i) C[i] += XOffset*CInc[i];          /* :412 */
+
+    uint32_t *Pixel = (uint32_t *)((uint8_t *)T->Color + (size_t)MinX*4 + (size_t)Row*T->Pitch);  /* :414 */
+    float *ZPixel = T->Z + MinX + (size_t)Row*T->ZStride;        /* :418 */
+    int32_t *Prim = T->Prim ? T->Prim + MinX + (size_t)Row*T->ZStride : 0;
+    if(Stats) Stats->SpanRows += 1;
+    for(int32_t X = MinX; X <= MaxX; ++X)                        /* :423 */
+    {
+        /* colour is r,g,b,a = C[0..3]; packed A R G B (:520-523) */
+        uint32_t Color32 = (round_u32(C[3]*255.0f) << 24) | (round_u32(C[0]*255.0f) << 16) |
+                           (round_u32(C[1]*255.0f) << 8) | (round_u32(C[2]*255.0f) << 0);
+        if(Stats) Stats->Fragments += 1;
+        if(Z > *ZPixel)                                          /* :525 */
+        {
+            *ZPixel = Z;
+            *Pixel = Color32;
+            if(Prim) *Prim = PrimIndex;
+            if(Stats) Stats->DepthPasses += 1;
+        }
+        ++ZPixel; ++Pixel; if(Prim) ++Prim;
+        for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];        /* :534 */
+        Z += ZInc;                                               /* :535 */
+    }
+}
+
+/* Level-1 active-edge walk of one triangle (projekt.cpp:173-303 and 542-597 restated for a
+ * list of at most three edges with array storage instead of the intrusive linked list).
+ * Defined behaviour where the reference is undefined:
+ *   - a row whose list holds fewer than two edges draws nothing and steps nothing
+ *     (the reference reads ListHead->YMax / ->Next through a null pointer, :262, :301);
+ *   - after two edges cross, they are exchanged in the list (the reference exchanges them
+ *     but leaves ListHead/ListTail stale, :562-572, and walks off the list one row later,
+ *     :274-278): bit 2 of the result reports that case. */
+int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
+                          orc_target *T, orc_stats *Stats)
+{
+    if(EdgeCount == 0) return 0;
+    if(EdgeCount > 3) EdgeCount = 3;
+    int32_t FirstRow = Edges[0].YMin;                            /* :173 */
+    int32_t MaxRow = Edges[0].YMax;                              /* :176-185 */
+    for(uint32_t e = 1; e < EdgeCount; ++e) if(MaxRow < Edges[e].YMax) MaxRow = Edges[e].YMax;
+    int32_t MaxY = MaxRow;                                       /* :187-196 */
+    if(MaxY > T->Height) MaxY = T->Height;
+
+    active_edge List[3];
+    uint32_t Count = 0;
+    int32_t Result = 0;
+    for(int32_t Row = FirstRow; Row < MaxY; ++Row)               /* :198 */
+    {
+        for(uint32_t e = 0; e < EdgeCount; ++e)                  /* :202-260 insertion */
+        {
+            if(Edges[e].YMin != Row) continue;
+            active_edge New;
+            New.X = Edges[e].XMin; New.Z = Edges[e].ZMin; New.E = Edges + e;
+            for(int i = 0; i < 4; ++i) New.C[i] = Edges[e].MinColor[i];
+            uint32_t At = Count;
+            for(uint32_t k = 0; k < Count; ++k)
+            {
+                if(edge_before(&New, &List[k])) { At = k; break; }
+            }
+            for(uint32_t k = Count; k > At; --k) List[k] = List[k - 1];
+            List[At] = New;
+            ++Count;
+        }
+        uint32_t Kept = 0;                                       /* :262-296 expiry */
+        for(uint32_t k = 0; k < Count; ++k)
+        {
+            if(List[k].E->YMax <= Row) continue;
+            List[Kept++] = List[k];
+        }
+        Count = Kept;
+        if(Count < 2) continue;                                  /* defined: nothing happens */
+
+        active_edge *L = &List[0], *R = &List[1];                /* :300-303, first pair only */
+        orc_fill_span(L, R, Row, PrimIndex, T, Stats);           /* Row >= 0 always (:308) */
+        Result |= 1;
+        L->X += L->E->Gradient;      R->X += R->E->Gradient;     /* :542-543 */
+        L->Z += L->E->ZGradient;     R->Z += R->E->ZGradient;    /* :545-546 */
+        for(int i = 0; i < 4; ++i)                               /* :548-549 */
+        {
+            L->C[i] += L->E->ColorGradient[i];
+            R->C[i] += R->E->ColorGradient[i];
+        }
+        if(L->X > R->X)                                          /* :562-572 */
+        {
+            active_edge Tmp = *L; *L = *R; *R = Tmp;
+            if(Row + 1 < MaxY) Result |= 2;
+        }
+    }
+    return Result;
+}
+
+/* One triangle = one object: FillEdgeTable on the 3-vertex object, then the level-1 walk. */
+static int32_t render_one(const float *Pos, const float *Col, const float *Nrm, uint32_t Tri,
+                          const float P[3], const orc_scene *Scene, orc_target *T,
+                          int32_t PrimIndex, orc_stats *Stats)
+{
+    orc_edge Edges[3], Temp[3];
+    int32_t Count = orc_fill_edge_table(Pos + 9*(size_t)Tri, Col + 12*(size_t)Tri, Nrm + 9*(size_t)Tri,
+                                        3, P, Scene, Edges, Temp);
+    if(Count < 0) return Count;
+    if(Stats) { Stats->Triangles += 1; if(Count > 0) Stats->Visible += 1; }
+    int32_t R = orc_draw_triangle(Edges, (uint32_t)Count, PrimIndex, T, Stats);
+    if(Stats && (R & 2)) Stats->RefWouldCrash += 1;
+    return R;
+}
+
+int32_t orc_render_triangles(const float *Pos, const float *Col, const float *Nrm,
+                             uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
+                             orc_target *Target, int32_t PrimBase, uint8_t *WouldCrash,
+                             orc_stats *Stats)
+{
+    if(Scene->LightCount == 0) return -1;
+    for(uint32_t Tri = 0; Tri < TriangleCount; ++Tri)
+    {
+        int32_t R = render_one(Pos, Col, Nrm, Tri, P, Scene, Target, PrimBase + (int32_t)Tri, Stats);
+        if(WouldCrash) WouldCrash[Tri] = (uint8_t)((R & 2) ? 1 : 0);
+    }
+    return 0;
+}
+
+typedef struct worker_args {
+    const float *Pos, *Col, *Nrm;
+    uint32_t First, Last;
+    const float *P;
+    const orc_scene *Scene;
+    orc_target Target;
+    orc_stats Stats;
+} worker_args;
+
+static void *worker_main(void *Arg)
+{
+    worker_args *W = (worker_args *)Arg;
+    for(uint32_t Tri = W->First; Tri < W->Last; ++Tri)
+    {
+        render_one(W->Pos, W->Col, W->Nrm, Tri, W->P, W->Scene, &W->Target, (int32_t)Tri, &W->Stats);
+    }
+    return 0;
+}
+
+/* Worker t renders the contiguous range t into a private copy of the target; copies are
+ * folded in range order with the reference's depth rule (strict >, projekt.cpp:525), which
+ * reproduces the single-thread result exactly (first submitted wins equal depth). */
+int32_t orc_render_triangles_mt(const float *Pos, const float *Col, const float *Nrm,
+                                uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
+                                orc_target *Target, uint32_t Threads, orc_stats *Stats)
+{
+    if(Scene->LightCount == 0) return -1;
+    if(Threads < 1) Threads = 1;
+    worker_args *Args = (worker_args *)calloc(Threads, sizeof(worker_args));
+    pthread_t *Ids = (pthread_t *)calloc(Threads, sizeof(pthread_t));
+    size_t ZCount = (size_t)Target->ZStride*(size_t)Target->Height;
+    size_t CBytes = (size_t)Target->Pitch*(size_t)Target->Height;
+    for(uint32_t t = 0; t < Threads; ++t)
+    {
+        worker_args *W = Args + t;
+        W->Pos = Pos; W->Col = Col; W->Nrm = Nrm; W->P = P; W->Scene = Scene;
+        W->First = (uint32_t)(((uint64_t)TriangleCount*t)/Threads);
+        W->Last = (uint32_t)(((uint64_t)TriangleCount*(t + 1))/Threads);
+        W->Target = *Target;
+        if(t > 0)
+        {
+            W->Target.Color = (uint32_t *)malloc(CBytes);
+            W->Target.Z = (float *)malloc(ZCount*sizeof(float));
+            W->Target.Prim = Target->Prim ? (int32_t *)malloc(ZCount*sizeof(int32_t)) : 0;
+            memcpy(W->Target.Color, Target->Color, CBytes);
+            memcpy(W->Target.Z, Target->Z, ZCount*sizeof(float));
+            if(Target->Prim) memcpy(W->Target.Prim, Target->Prim, ZCount*sizeof(int32_t));
+        }
+        pthread_create(&Ids[t], 0, worker_main, W);
+    }
+    for(uint32_t t = 0; t < Threads; ++t) pthread_join(Ids[t], 0);
+    for(uint32_t t = 0; t < Threads; ++t)
+    {
+        worker_args *W = Args + t;
+        if(Stats)
+        {
+            Stats->Triangles += W->Stats.Triangles;     Stats->Visible += W->Stats.Visible;
+            Stats->SpanRows += W->Stats.SpanRows;       Stats->Fragments += W->Stats.Fragments;
+            Stats->DepthPasses += W->Stats.DepthPasses; Stats->RefWouldCrash += W->Stats.RefWouldCrash;
+        }
+        if(t == 0) continue;
+        for(int32_t Y = 0; Y < Target->Height; ++Y)
+        {
+            uint32_t *DstC = (uint32_t *)((uint8_t *)Target->Color + (size_t)Y*Target->Pitch);
+            uint32_t *SrcC = (uint32_t *)((uint8_t *)W->Target.Color + (size_t)Y*Target->Pitch);
+            float *DstZ = Target->Z + (size_t)Y*Target->ZStride;
+            float *SrcZ = W->Target.Z + (size_t)Y*Target->ZStride;
+            for(int32_t X = 0; X < Target->Width; ++X)
+            {
+                if(SrcZ[X] > DstZ[X])
+                {
+                    DstZ[X] = SrcZ[X]; DstC[X] = SrcC[X];
+                    if(Target->Prim) Target->Prim[(size_t)Y*Target->ZStride + X] =
+                        W->Target.Prim[(size_t)Y*Target->ZStride + X];
+                }
+            }
+        }
+        free(W->Target.Color); free(W->Target.Z); free(W->Target.Prim);
+    }
+    free(Args); free(Ids);
+    return 0;
+}
+
+/* Layout mirrors of the two reference structs the fallback receives (oracle/ref_shim.h). */
+typedef struct ref_loaded_bitmap { int32_t Width, Height, Pitch; void *Memory; } ref_loaded_bitmap;
+typedef struct ref_commands_head { uint32_t Width; float *ZBuffer; } ref_commands_head;
+
+void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
+                      void *RefGameRenderCommands)
+{
+    orc_fallback_ctx *Ctx = (orc_fallback_ctx *)User;
+    ref_loaded_bitmap *B = (ref_loaded_bitmap *)RefLoadedBitmap;
+    ref_commands_head *C = (ref_commands_head *)RefGameRenderCommands;
+    orc_target T;
+    T.Width = B->Width; T.Height = B->Height; T.Pitch = B->Pitch;
+    T.Color = (uint32_t *)B->Memory; T.Z = C->ZBuffer; T.ZStride = C->Width; T.Prim = 0;
+    render_one(Ctx->Pos, Ctx->Col, Ctx->Nrm, TriangleIndex, Ctx->P, Ctx->Scene, &T,
+               (int32_t)TriangleIndex, 0);
+}
