@@ -1,0 +1,544 @@
+// C ABI of libb200raster.so (include/b200_raster.h) and the host-side frame orchestration:
+//   setup_kernel -> tile_scan_kernel -> scatter_kernel -> raster_kernel
+// on one CUDA stream, no host synchronisation inside a frame.  The only host/device handshake
+// is the size of the (triangle, tile) pair list: it is copied back right after the scan and
+// looked at when the *next* call arrives (or at b200r_sync); if it exceeded the list's
+// capacity the scatter and raster kernels of that frame returned without touching the targets,
+// the list is grown and the frame is issued again.
+//
+// There is no CPU fallback anywhere in this file: without a compute-capability-10 device every
+// entry point returns B200R_E_NO_DEVICE.
+#include "../../include/b200_raster.h"
+#include "raster_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace b200r;
+
+namespace {
+
+struct DeviceBuffer
+{
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need)
+    {
+        if(need <= bytes) return cudaSuccess;
+        if(ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+        size_t want = need + need/4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if(e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if(ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+// control words that are zeroed once per frame with a single memset
+struct FrameWords
+{
+    unsigned pair_total;
+    unsigned work_counter;
+    unsigned long long counters[2];     // binned triangles, tile pairs
+};
+
+} // namespace
+
+struct b200r_context
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t total_ready = nullptr;
+    std::string error;
+    int tile_w = 64, tile_h = 32;
+
+    DeviceBuffer recs, rects, tiles, pairs, words;
+    FrameWords *h_words = nullptr;      // pinned
+
+    // the last issued frame, kept so it can be issued again after the pair list grew
+    bool pending = false;
+    ViewParams view;
+    std::vector<MeshParams> meshes;
+    b200r_device_target target;
+    unsigned total_tris = 0;
+    unsigned ntiles = 0;
+
+    b200r_frame_stats stats = {};
+
+    // host-pointer path mirrors
+    DeviceBuffer d_pos, d_col, d_nrm, d_color, d_depth;
+};
+
+static int fail(b200r_context *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if(c)
+    {
+        c->error = what;
+        if(e != cudaSuccess) { c->error += ": "; c->error += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(c, B200R_E_CUDA, #call, e_); } while(0)
+
+static int fill_view(b200r_context *c, const game_render_commands *cmd, const b200r_device_target *t, ViewParams &v)
+{
+    if(!cmd || !t) return fail(c, B200R_E_INVALID, "null Commands / Target");
+    const light_data &ld = cmd->LightData;
+    if(ld.LightCount == 0 || ld.LightCount > (u32)kMaxLights || !ld.Lights)
+        return fail(c, B200R_E_UNSUPPORTED, "LightCount must be 1..8 (0 lights leaves MinColor undefined in the reference, projekt.cpp:4022)");
+    if(t->Width <= 0 || t->Height <= 0 || t->BandRows <= 0 || t->BandFirstRow < 0 ||
+       t->BandFirstRow + t->BandRows > t->Height || !t->Color || !t->Depth)
+        return fail(c, B200R_E_INVALID, "bad target geometry");
+    if(t->ColorPitch < t->Width*4 || (t->ColorPitch & 3) || t->DepthStride < t->Width)
+        return fail(c, B200R_E_INVALID, "bad target pitch");
+    v.m2p = cmd->Transform.MetersToPixels;
+    v.cx = cmd->Transform.ScreenCenter.x; v.cy = cmd->Transform.ScreenCenter.y;
+    v.focal = cmd->Transform.FocalLength; v.dist = cmd->Transform.DistanceAboveTarget;
+    v.amb[0] = ld.AmbientIntensity.x; v.amb[1] = ld.AmbientIntensity.y;
+    v.amb[2] = ld.AmbientIntensity.z; v.amb[3] = ld.AmbientIntensity.w;
+    v.nlights = (int)ld.LightCount;
+    for(int i = 0; i < kMaxLights; ++i)
+    {
+        DevLight L = {0, 0, 0, 0, 0, 0, 0};
+        if(i < v.nlights)
+        {
+            const light_info &s = ld.Lights[i];
+            L.px = s.P.x; L.py = s.P.y; L.pz = s.P.z;
+            L.ir = s.Intensity.x; L.ig = s.Intensity.y; L.ib = s.Intensity.z; L.ia = s.Intensity.w;
+        }
+        v.lights[i] = L;
+    }
+    v.width = t->Width; v.height = t->Height;
+    v.band_y0 = t->BandFirstRow; v.band_y1 = t->BandFirstRow + t->BandRows;
+    v.tile_w = c->tile_w; v.tile_h = c->tile_h;
+    v.tiles_x = (t->Width + c->tile_w - 1)/c->tile_w;
+    v.tiles_y = (t->BandRows + c->tile_h - 1)/c->tile_h;
+    if(v.tiles_x > 65535 || v.tiles_y > 65535) return fail(c, B200R_E_UNSUPPORTED, "more than 65535 tiles per axis");
+    return B200R_OK;
+}
+
+// Enqueue every kernel of the frame described by c->view / c->meshes / c->target.
+static int issue_frame(b200r_context *c)
+{
+    const ViewParams &v = c->view;
+    const unsigned ntiles = c->ntiles;
+    unsigned *tile_count = (unsigned *)c->tiles.ptr;
+    unsigned *tile_fill = tile_count + ntiles;
+    unsigned *tile_offset = tile_fill + ntiles;
+    FrameWords *words = (FrameWords *)c->words.ptr;
+
+    CU(cudaMemsetAsync(tile_count, 0, (size_t)ntiles*2*sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
+
+    SetupOutputs so;
+    so.recs = (uint32_t *)c->recs.ptr;
+    so.rects = (uint2 *)c->rects.ptr;
+    so.tile_count = tile_count;
+    so.counters = words->counters;
+    for(const MeshParams &m : c->meshes)
+    {
+        launch_setup(v, m, so, c->stream);
+        if(m.ntri) c->stats.KernelLaunches += 1;
+    }
+    launch_tile_scan(tile_count, tile_offset, ntiles, &words->pair_total, c->stream);
+    c->stats.KernelLaunches += 1;
+    CU(cudaMemcpyAsync(c->h_words, words, sizeof(FrameWords), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->total_ready, c->stream));
+
+    const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
+    launch_scatter(so.rects, c->total_tris, v.tiles_x, tile_offset, tile_fill, (unsigned *)c->pairs.ptr,
+                   &words->pair_total, pair_cap, c->stream);
+    if(c->total_tris) c->stats.KernelLaunches += 1;
+
+    RasterParams rp;
+    rp.v = v;
+    rp.recs = so.recs;
+    rp.tile_count = tile_count;
+    rp.tile_offset = tile_offset;
+    rp.pair_list = (const unsigned *)c->pairs.ptr;
+    rp.pair_total = &words->pair_total;
+    rp.pair_capacity = pair_cap;
+    rp.work_counter = &words->work_counter;
+    rp.ntiles = ntiles;
+    rp.color = c->target.Color;
+    rp.depth = c->target.Depth;
+    rp.color_pitch_words = c->target.ColorPitch/4;
+    rp.depth_stride = c->target.DepthStride;
+    rp.bulk_ok = ((((uintptr_t)c->target.Color) & 15) == 0 && (((uintptr_t)c->target.Depth) & 15) == 0 &&
+                  (c->target.ColorPitch & 15) == 0 && ((c->target.DepthStride*4) & 15) == 0 &&
+                  (c->target.Width & 3) == 0) ? 1 : 0;
+    cudaError_t e = launch_raster(rp, c->sm_count, c->stream);
+    if(e != cudaSuccess) return fail(c, B200R_E_CUDA, "raster_kernel launch", e);
+    c->stats.KernelLaunches += 1;
+    CU(cudaGetLastError());
+    c->pending = true;
+    return B200R_OK;
+}
+
+// Look at the pair total of the last issued frame; grow the list and re-issue if it overflowed.
+static int settle_pending(b200r_context *c)
+{
+    while(c->pending)
+    {
+        CU(cudaEventSynchronize(c->total_ready));
+        const unsigned total = c->h_words->pair_total;
+        const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
+        c->stats.Binned = c->h_words->counters[0];
+        c->stats.TilePairs = c->h_words->counters[1];
+        c->pending = false;
+        if(total > pair_cap)
+        {
+            CU(cudaStreamSynchronize(c->stream));
+            CU(c->pairs.reserve((size_t)total*sizeof(unsigned)));
+            c->stats.Reruns += 1;
+            int rc = issue_frame(c);
+            if(rc != B200R_OK) return rc;
+        }
+    }
+    return B200R_OK;
+}
+
+extern "C" {
+
+int b200r_create(b200r_context **out, int device)
+{
+    if(!out) return B200R_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return B200R_E_NO_DEVICE;
+    if(device < 0) { if(cudaGetDevice(&device) != cudaSuccess) return B200R_E_NO_DEVICE; }
+    if(device >= count) return B200R_E_INVALID;
+    cudaDeviceProp prop;
+    if(cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B200R_E_NO_DEVICE;
+    if(prop.major != 10) return B200R_E_NO_DEVICE;          // kernels are built for sm_100a only
+    b200r_context *c = new (std::nothrow) b200r_context;
+    if(!c) return B200R_E_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if(cudaSetDevice(device) != cudaSuccess ||
+       cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaEventCreateWithFlags(&c->total_ready, cudaEventDisableTiming) != cudaSuccess ||
+       cudaMallocHost((void **)&c->h_words, sizeof(FrameWords)) != cudaSuccess ||
+       c->words.reserve(sizeof(FrameWords)) != cudaSuccess)
+    {
+        b200r_destroy(c);
+        return B200R_E_CUDA;
+    }
+    c->stream = c->own_stream;
+    memset(c->h_words, 0, sizeof(FrameWords));
+    *out = c;
+    return B200R_OK;
+}
+
+void b200r_destroy(b200r_context *c)
+{
+    if(!c) return;
+    cudaSetDevice(c->device);
+    if(c->stream) cudaStreamSynchronize(c->stream);
+    c->recs.release(); c->rects.release(); c->tiles.release(); c->pairs.release(); c->words.release();
+    c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_color.release(); c->d_depth.release();
+    if(c->h_words) cudaFreeHost(c->h_words);
+    if(c->total_ready) cudaEventDestroy(c->total_ready);
+    if(c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *b200r_last_error(const b200r_context *c) { return c ? c->error.c_str() : "null context"; }
+
+int b200r_set_stream(b200r_context *c, void *s)
+{
+    if(!c) return B200R_E_INVALID;
+    CU(cudaSetDevice(c->device));
+    int rc = settle_pending(c);
+    if(rc != B200R_OK) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return B200R_OK;
+}
+
+int b200r_sync(b200r_context *c)
+{
+    if(!c) return B200R_E_INVALID;
+    CU(cudaSetDevice(c->device));
+    int rc = settle_pending(c);
+    if(rc != B200R_OK) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return B200R_OK;
+}
+
+int b200r_set_tile(b200r_context *c, int w, int h)
+{
+    if(!c) return B200R_E_INVALID;
+    if(!((w == 64 && h == 32) || (w == 32 && h == 32) || (w == 128 && h == 16) || (w == 64 && h == 16)))
+        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16 or 64x16");
+    int rc = b200r_sync(c);
+    if(rc != B200R_OK) return rc;
+    c->tile_w = w; c->tile_h = h;
+    return B200R_OK;
+}
+
+int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 mesh_count,
+                        const game_render_commands *cmd, const b200r_device_target *target, u32 flags)
+{
+    if(!c) return B200R_E_INVALID;
+    if(flags & B200R_WHOLE_OBJECT_AEL) return fail(c, B200R_E_UNSUPPORTED, "whole-object AEL pairing is not implemented");
+    if(mesh_count && !meshes) return fail(c, B200R_E_INVALID, "null Meshes");
+    CU(cudaSetDevice(c->device));
+    int rc = settle_pending(c);                 // the previous frame must be complete in the stream
+    if(rc != B200R_OK) return rc;
+
+    ViewParams v;
+    rc = fill_view(c, cmd, target, v);
+    if(rc != B200R_OK) return rc;
+
+    uint64_t total = 0;
+    std::vector<MeshParams> ms;
+    ms.reserve(mesh_count);
+    for(u32 i = 0; i < mesh_count; ++i)
+    {
+        const b200r_device_mesh &m = meshes[i];
+        if(m.TriangleCount && (!m.Positions || !m.Colors || !m.Normals))
+            return fail(c, B200R_E_INVALID, "mesh with null attribute pointer");
+        MeshParams mp;
+        mp.pos = m.Positions; mp.col = m.Colors; mp.nrm = m.Normals;
+        mp.ntri = m.TriangleCount;
+        mp.px = m.P.x; mp.py = m.P.y; mp.pz = m.P.z;
+        mp.prim_base = (unsigned)total;
+        total += m.TriangleCount;
+        ms.push_back(mp);
+    }
+    if(total > 0x7fffffffull) return fail(c, B200R_E_UNSUPPORTED, "more than 2^31-1 triangles per call");
+
+    const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
+    CU(c->recs.reserve((size_t)std::max<uint64_t>(total, 1)*kRecWords*sizeof(uint32_t)));
+    CU(c->rects.reserve((size_t)std::max<uint64_t>(total, 1)*sizeof(uint2)));
+    CU(c->tiles.reserve((size_t)ntiles*3*sizeof(unsigned)));
+    if(c->pairs.bytes == 0)
+        CU(c->pairs.reserve((size_t)std::max<uint64_t>(total + total/2, 1u << 16)*sizeof(unsigned)));
+
+    c->view = v;
+    c->meshes.swap(ms);
+    c->target = *target;
+    c->total_tris = (unsigned)total;
+    c->ntiles = ntiles;
+    c->stats.Triangles = total;
+    c->stats.Tiles = ntiles;
+    return issue_frame(c);
+}
+
+int b200r_clear_device(b200r_context *c, const b200r_device_target *t, u32 color, r32 depth)
+{
+    if(!c || !t || !t->Color || !t->Depth || t->Width <= 0 || t->BandRows <= 0) return fail(c, B200R_E_INVALID, "bad clear target");
+    CU(cudaSetDevice(c->device));
+    int rc = settle_pending(c);
+    if(rc != B200R_OK) return rc;
+    launch_clear(t->Color, t->ColorPitch/4, t->Depth, t->DepthStride, t->Width, t->BandRows, color, depth, c->stream);
+    c->stats.KernelLaunches += 1;
+    CU(cudaGetLastError());
+    return B200R_OK;
+}
+
+int b200r_get_stats(b200r_context *c, b200r_frame_stats *s)
+{
+    if(!c || !s) return B200R_E_INVALID;
+    *s = c->stats;
+    return B200R_OK;
+}
+
+// ---------------------------------------------------------------------------- host-pointer path
+static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, u32 n,
+                          std::vector<b200r_device_mesh> &meshes)
+{
+    uint64_t verts = 0;
+    for(u32 i = 0; i < n; ++i)
+    {
+        const render_entry_3d_object &o = objs[i];
+        if(o.PhongShading || o.Bitmap) return fail(c, B200R_E_UNSUPPORTED, "Phong / textured objects are not implemented (SURVEY.md 8f rows 1-2)");
+        u32 tris = o.VertexCount/3;                          // projekt.cpp:3886
+        if(tris && (!o.VertexData || !o.ColorData || !o.NormalData)) return fail(c, B200R_E_INVALID, "object with null vertex stream");
+        verts += (uint64_t)tris*3;
+    }
+    CU(c->d_pos.reserve((size_t)std::max<uint64_t>(verts, 1)*12));
+    CU(c->d_col.reserve((size_t)std::max<uint64_t>(verts, 1)*16));
+    CU(c->d_nrm.reserve((size_t)std::max<uint64_t>(verts, 1)*12));
+    uint64_t at = 0;
+    for(u32 i = 0; i < n; ++i)
+    {
+        const render_entry_3d_object &o = objs[i];
+        u32 tris = o.VertexCount/3;
+        size_t nv = (size_t)tris*3;
+        b200r_device_mesh m;
+        m.Positions = (const r32 *)c->d_pos.ptr + at*3;
+        m.Colors = (const r32 *)c->d_col.ptr + at*4;
+        m.Normals = (const r32 *)c->d_nrm.ptr + at*3;
+        m.TriangleCount = tris;
+        m.P = o.P;
+        if(nv)
+        {
+            CU(cudaMemcpyAsync((void *)m.Positions, o.VertexData, nv*12, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync((void *)m.Colors, o.ColorData, nv*16, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync((void *)m.Normals, o.NormalData, nv*12, cudaMemcpyHostToDevice, c->stream));
+        }
+        at += nv;
+        meshes.push_back(m);
+    }
+    return B200R_OK;
+}
+
+int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u32 n,
+                         const game_render_commands *cmd, const loaded_bitmap *out, u32 flags)
+{
+    if(!c) return B200R_E_INVALID;
+    if(!cmd || !out || !out->Memory || !cmd->ZBuffer || (n && !objs)) return fail(c, B200R_E_INVALID, "null argument");
+    if(out->Width <= 0 || out->Height <= 0 || out->Pitch < out->Width*4 || cmd->Width < (u32)out->Width)
+        return fail(c, B200R_E_INVALID, "bad OutputTarget / Commands->Width");
+    if(flags & B200R_WHOLE_OBJECT_AEL) return fail(c, B200R_E_UNSUPPORTED, "whole-object AEL pairing is not implemented");
+    CU(cudaSetDevice(c->device));
+    int rc = settle_pending(c);
+    if(rc != B200R_OK) return rc;
+
+    std::vector<b200r_device_mesh> meshes;
+    rc = upload_objects(c, objs, n, meshes);
+    if(rc != B200R_OK) return rc;
+
+    // device mirrors of the targets: rows padded to 64 pixels so every tile row is a 16-byte
+    // aligned bulk copy
+    const int W = out->Width, H = out->Height;
+    const int wpad = (W + 63) & ~63;
+    CU(c->d_color.reserve((size_t)wpad*H*4));
+    CU(c->d_depth.reserve((size_t)wpad*H*4));
+    CU(cudaMemcpy2DAsync(c->d_color.ptr, (size_t)wpad*4, out->Memory, (size_t)out->Pitch, (size_t)W*4, H,
+                         cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->d_depth.ptr, (size_t)wpad*4, cmd->ZBuffer, (size_t)cmd->Width*4, (size_t)W*4, H,
+                         cudaMemcpyHostToDevice, c->stream));
+    b200r_device_target t;
+    t.Color = (u32 *)c->d_color.ptr; t.Depth = (r32 *)c->d_depth.ptr;
+    t.Width = W; t.Height = H; t.ColorPitch = wpad*4; t.DepthStride = wpad;
+    t.BandFirstRow = 0; t.BandRows = H;
+    rc = b200r_render_device(c, meshes.data(), (u32)meshes.size(), cmd, &t, flags);
+    if(rc != B200R_OK) return rc;
+    rc = settle_pending(c);                     // re-issue before the read-back if the list grew
+    if(rc != B200R_OK) return rc;
+    CU(cudaMemcpy2DAsync(out->Memory, (size_t)out->Pitch, c->d_color.ptr, (size_t)wpad*4, (size_t)W*4, H,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(cmd->ZBuffer, (size_t)cmd->Width*4, c->d_depth.ptr, (size_t)wpad*4, (size_t)W*4, H,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200R_OK;
+}
+
+// The reference's MergeSort (projekt.cpp:2-72) is not stable: on equal YMin the merge takes the
+// right half first (:51-58) while the two-element base case keeps the left one first (:13).  The
+// resulting order is a pure function of (YMin, position): walk the recursion from the root and
+// emit, per level, 0 for the side that wins ties.  Sorting by (YMin, that path) reproduces it.
+static uint32_t merge_tie_key(uint32_t i, uint32_t n)
+{
+    uint32_t key = 0, lo = 0, cnt = n;
+    int depth = 0;
+    while(cnt > 2)
+    {
+        uint32_t half0 = cnt/2;
+        uint32_t bit;
+        if(i - lo < half0) { bit = 1; cnt = half0; }
+        else { bit = 0; lo += half0; cnt -= half0; }
+        key = (key << 1) | bit; ++depth;
+    }
+    if(cnt == 2) { key = (key << 1) | (i - lo); ++depth; }
+    return key << (32 - depth);
+}
+
+int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
+                          const game_render_commands *cmd, b32 phong)
+{
+    if(!c) return B200R_E_INVALID;
+    if(!obj || !cmd) return fail(c, B200R_E_INVALID, "null argument");
+    if(phong || obj->PhongShading || obj->Bitmap) return fail(c, B200R_E_UNSUPPORTED, "Phong / textured edge tables are not implemented");
+    if(!obj->EdgeMemory) return fail(c, B200R_E_INVALID, "null EdgeMemory");
+    CU(cudaSetDevice(c->device));
+    int rc = settle_pending(c);
+    if(rc != B200R_OK) return rc;
+    std::vector<b200r_device_mesh> meshes;
+    rc = upload_objects(c, obj, 1, meshes);
+    if(rc != B200R_OK) return rc;
+    const u32 tris = meshes[0].TriangleCount;
+    if(tris == 0) return 0;
+
+    // Only the set-up kernel runs.  Height only clamps MaxY in the record header (unused here);
+    // a 1x1 dummy band keeps the tile bookkeeping trivial.
+    b200r_device_target t;
+    memset(&t, 0, sizeof(t));
+    t.Width = 1 << 20; t.Height = 1 << 20; t.BandFirstRow = 0; t.BandRows = 1;
+    t.ColorPitch = t.Width*4; t.DepthStride = t.Width;
+    t.Color = (u32 *)16; t.Depth = (r32 *)16;    // never dereferenced: raster is not launched
+    ViewParams v;
+    rc = fill_view(c, cmd, &t, v);
+    if(rc != B200R_OK) return rc;
+    v.tiles_x = 1; v.tiles_y = 1; v.tile_w = 1 << 21; v.tile_h = 1 << 21;
+    CU(c->recs.reserve((size_t)tris*kRecWords*sizeof(uint32_t)));
+    CU(c->rects.reserve((size_t)tris*sizeof(uint2)));
+    CU(c->tiles.reserve(3*sizeof(unsigned)));
+    unsigned *tile_count = (unsigned *)c->tiles.ptr;
+    FrameWords *words = (FrameWords *)c->words.ptr;
+    CU(cudaMemsetAsync(tile_count, 0, 3*sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
+    SetupOutputs so;
+    so.recs = (uint32_t *)c->recs.ptr; so.rects = (uint2 *)c->rects.ptr;
+    so.tile_count = tile_count; so.counters = words->counters;
+    MeshParams mp;
+    mp.pos = meshes[0].Positions; mp.col = meshes[0].Colors; mp.nrm = meshes[0].Normals;
+    mp.ntri = tris; mp.px = obj->P.x; mp.py = obj->P.y; mp.pz = obj->P.z; mp.prim_base = 0;
+    launch_setup(v, mp, so, c->stream);
+    c->stats.KernelLaunches += 1;
+    CU(cudaGetLastError());
+    std::vector<uint32_t> recs((size_t)tris*kRecWords);
+    CU(cudaMemcpyAsync(recs.data(), c->recs.ptr, recs.size()*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+
+    // Host side of FillEdgeTable's tail: append each triangle's edges in the reference's
+    // emission order (edge 0-1, 1-2, 2-0; projekt.cpp:3947) and apply MergeSort's permutation.
+    struct Ref { uint64_t key; const uint32_t *edge; };
+    std::vector<Ref> order;
+    order.reserve((size_t)tris*3);
+    for(u32 tri = 0; tri < tris; ++tri)
+    {
+        const uint32_t *rec = recs.data() + (size_t)tri*kRecWords;
+        const int ne = (int)rec[R_NEDGES];
+        const uint32_t emit = rec[R_EDGE0 + 3*kEdgeWords];     // slot of the k-th emitted edge, 2 bits each
+        for(int k = 0; k < ne; ++k)
+        {
+            int slot = (emit >> (2*k)) & 3;
+            order.push_back({0, rec + R_EDGE0 + slot*kEdgeWords});
+        }
+    }
+    const uint32_t n = (uint32_t)order.size();
+    for(uint32_t i = 0; i < n; ++i)
+    {
+        uint32_t ymin = order[i].edge[E_YMIN];
+        order[i].key = ((uint64_t)(ymin ^ 0x80000000u) << 32) | merge_tie_key(i, n);
+    }
+    std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.key < b.key; });
+    edge_info *outp = (edge_info *)obj->EdgeMemory;
+    for(uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t *E = order[i].edge;
+        edge_info &o = outp[i];
+        auto f = [&](int w) { float x; memcpy(&x, E + w, 4); return x; };
+        o.YMin = (s32)E[E_YMIN]; o.YMax = (s32)E[E_YMAX];
+        o.XMin = f(E_X); o.Gradient = f(E_DX); o.ZMin = f(E_Z); o.ZGradient = f(E_DZ);
+        o.MinColor.x = f(E_C + 0); o.MinColor.y = f(E_C + 1); o.MinColor.z = f(E_C + 2); o.MinColor.w = f(E_C + 3);
+        o.ColorGradient.x = f(E_DC + 0); o.ColorGradient.y = f(E_DC + 1);
+        o.ColorGradient.z = f(E_DC + 2); o.ColorGradient.w = f(E_DC + 3);
+        o.Left = (b32)E[E_LEFT];
+        o.Next = nullptr;
+    }
+    return (int)n;
+}
+
+} // extern "C"

@@ -1,0 +1,158 @@
+// Shared device-side definitions for the sm_100a rasterization kernels.
+//
+// Arithmetic contract (SURVEY.md section 7 "hard parts"): every value that reaches a
+// coverage, depth or colour decision is produced by the same sequence of IEEE-754 binary32
+// operations as the reference's scalar x86 code (projekt.cpp:74-93, 162-601, 3882-4121),
+// one rounding per operation.  All such arithmetic goes through the __f*_rn intrinsics below
+// (never contracted to FMA, never reordered, independent of compiler flags); the translation
+// units are additionally built with -fmad=false and the default -prec-div/-prec-sqrt/-ftz.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200r {
+
+constexpr int kMaxLights = 8;
+
+struct DevLight { float px, py, pz; float ir, ig, ib, ia; };
+
+// Per-call view state: projective_transform + light_data (projekt.cpp:79-89, 3885-3892) and
+// the screen / band / tile geometry.
+struct ViewParams
+{
+    float m2p, cx, cy, focal, dist;
+    float amb[4];
+    int nlights;
+    DevLight lights[kMaxLights];
+    int width, height;          // logical screen (loaded_bitmap Width/Height)
+    int band_y0, band_y1;       // screen rows owned by this target
+    int tile_w, tile_h;
+    int tiles_x, tiles_y;
+};
+
+struct MeshParams
+{
+    const float *pos;           // v3 x 3 per triangle
+    const float *col;           // v4 x 3 per triangle
+    const float *nrm;           // v3 x 3 per triangle
+    unsigned ntri;
+    float px, py, pz;           // render_entry_3d_object::P
+    unsigned prim_base;         // submission index of this mesh's first triangle
+};
+
+// Compact per-triangle record written by the setup kernel and read by the raster kernel:
+// the fields of edge_info (projekt.h:17-37) that the Gouraud path defines, for the <= 3 edges
+// of one triangle in the reference's MergeSort order (projekt.cpp:2-72).
+constexpr int kEdgeWords = 15;      // ymin ymax x dx z dz c[4] dc[4] left
+constexpr int kRecWords = 52;       // 4 header + 3*15 + 3 pad  = 208 bytes = 13 float4
+constexpr int kRecVec4 = kRecWords/4;
+enum { E_YMIN = 0, E_YMAX = 1, E_X = 2, E_DX = 3, E_Z = 4, E_DZ = 5, E_C = 6, E_DC = 10, E_LEFT = 14 };
+enum { R_NEDGES = 0, R_FIRSTROW = 1, R_MAXY = 2, R_PRIM = 3, R_EDGE0 = 4 };
+
+struct RasterParams
+{
+    ViewParams v;
+    const uint32_t *recs;       // kRecWords per triangle
+    const unsigned *tile_count;
+    const unsigned *tile_offset;
+    const unsigned *pair_list;
+    const unsigned *pair_total; // device word: total (triangle,tile) pairs this frame
+    unsigned pair_capacity;
+    unsigned *work_counter;
+    unsigned ntiles;
+    uint32_t *color;            // band rows
+    float *depth;
+    int color_pitch_words;      // u32 per row
+    int depth_stride;           // floats per row
+    int bulk_ok;                // rows may be moved with cp.async.bulk (16-byte aligned)
+};
+
+// ---------------------------------------------------------------- exact binary32 helpers
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// RoundR32ToS32 = cvtss2si (projekt.cpp:402, 3988): nearest-even; NaN / out of range -> INT_MIN.
+__device__ __forceinline__ int round_s32(float v)
+{
+    return (fabsf(v) < 2147483648.0f) ? __float2int_rn(v) : (int)0x80000000;
+}
+// Clamp01 (projekt.cpp:474, 4047): comparisons, so NaN passes through as on the host.
+__device__ __forceinline__ float clamp01(float v)
+{
+    if(v < 0.0f) v = 0.0f; else if(v > 1.0f) v = 1.0f;
+    return v;
+}
+
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while(!mbar_try_wait(bar, parity)) { }
+}
+// global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// shared -> global, tracked by the bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------- launchers (one per kernel)
+struct SetupOutputs
+{
+    uint32_t *recs;             // kRecWords per triangle
+    uint2 *rects;               // packed tile rectangle per triangle (x: tx0 | tx1<<16, y: ty0 | ty1<<16), tx0 > tx1 = empty
+    unsigned *tile_count;
+    unsigned long long *counters;   // [0] binned triangles, [1] tile pairs
+};
+
+void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
+void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
+                      unsigned *pair_total, cudaStream_t s);
+void launch_scatter(const uint2 *rects, unsigned ntri, int tiles_x, const unsigned *tile_offset,
+                    unsigned *tile_fill, unsigned *pair_list, const unsigned *pair_total,
+                    unsigned pair_capacity, cudaStream_t s);
+cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s);
+void launch_clear(uint32_t *color, int color_pitch_words, float *depth, int depth_stride,
+                  int width, int rows, uint32_t cval, float dval, cudaStream_t s);
+
+} // namespace b200r

@@ -1,0 +1,291 @@
+// Geometry / triangle set-up kernel (sm_100a).
+//
+// Restates, per triangle, the body of FillEdgeTable for the Gouraud branch
+// (projekt.cpp:3894-4115): translate by Object->P, ProjectVertex (74-93), back-face test
+// (3926-3927, 3943), per-edge y-ordering, reject / top-clip, start values and per-row
+// gradients (3947-4111), vertex lighting (4020-4064), and the MergeSort order (2-72) of the
+// <= 3 edges of the triangle ("one triangle = one object").
+//
+// Mapping: one thread per triangle, one CTA per 128 triangles.  A warp handles 32 triangles:
+// their 32 x 120 B of vertex attributes are fetched with fully coalesced loads into shared
+// memory and the 32 x 208 B records leave the CTA as coalesced 128-bit stores, so the kernel
+// streams 120 B in / 208 B out per triangle at HBM speed.  (A literal warp-per-triangle
+// mapping would spend 32 lanes on ~3 edges x 2 ends of scalar work; see DESIGN.md.)
+#include "raster_device.cuh"
+
+namespace b200r {
+
+constexpr int kSetupThreads = 128;
+
+struct V3 { float x, y, z; };
+
+// projekt.cpp:74-93
+__device__ __forceinline__ V3 project_vertex(V3 cam, const ViewParams &v)
+{
+    V3 r = {0.0f, 0.0f, 0.0f};
+    float d = fsub(v.dist, cam.z);                          // :81
+    if(d > 0.2f)                                            // :82, :86
+    {
+        float s = fmul(fdiv(1.0f, d), v.focal);             // :88 (1/d)*FocalLength first
+        float px = fmul(s, cam.x);
+        float py = fmul(s, cam.y);
+        r.x = fadd(v.cx, fmul(v.m2p, px));                  // :89
+        r.y = fadd(v.cy, fmul(v.m2p, py));
+        r.z = fadd(d, fmul(v.m2p, 0.0f));
+    }
+    return r;
+}
+
+__device__ __forceinline__ float inner3(V3 a, V3 b)         // left to right
+{
+    return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z));
+}
+// Normalize(a) = a * (1/sqrt(a.a))  (SURVEY.md Appendix A pin; projekt.cpp:3926, 4029)
+__device__ __forceinline__ V3 normalize3(V3 a)
+{
+    float s = fdiv(1.0f, __fsqrt_rn(inner3(a, a)));
+    V3 r = { fmul(s, a.x), fmul(s, a.y), fmul(s, a.z) };
+    return r;
+}
+
+// projekt.cpp:4022-4062, non-bitmap branch; value depends only on the vertex.
+__device__ __forceinline__ void light_vertex(V3 cam, V3 nrm, const float col[4], const ViewParams &v,
+                                             float out[4])
+{
+    float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for(int l = 0; l < v.nlights; ++l)
+    {
+        const DevLight &L = v.lights[l];
+        V3 to = { fsub(L.px, cam.x), fsub(L.py, cam.y), fsub(L.pz, cam.z) };
+        V3 dir = normalize3(to);                            // :4029
+        if(l == 0)                                          // :4032-4044
+        {
+#pragma unroll
+            for(int i = 0; i < 4; ++i) c[i] = fmul(col[i], v.amb[i]);
+        }
+        float dot = clamp01(inner3(dir, nrm));              // :4047
+        const float I[4] = { L.ir, L.ig, L.ib, L.ia };
+#pragma unroll
+        for(int i = 0; i < 4; ++i)                          // :4058
+        {
+            c[i] = clamp01(fadd(c[i], fmul(dot, fmul(col[i], I[i]))));
+        }
+    }
+#pragma unroll
+    for(int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+__global__ void __launch_bounds__(kSetupThreads)
+setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
+{
+    __shared__ float s_pos[kSetupThreads*9];
+    __shared__ __align__(16) float s_col[kSetupThreads*12];
+    __shared__ float s_nrm[kSetupThreads*9];
+    __shared__ __align__(16) uint32_t s_rec[kSetupThreads*kRecWords];
+    __shared__ unsigned s_binned, s_pairs;
+
+    const unsigned base = blockIdx.x*kSetupThreads;
+    const unsigned n = min((unsigned)kSetupThreads, m.ntri - base);
+    const int t = threadIdx.x;
+    if(t == 0) { s_binned = 0; s_pairs = 0; }
+
+    // coalesced attribute fetch: consecutive lanes read consecutive words
+    {
+        const float *gp = m.pos + (size_t)base*9;
+        const float *gc = m.col + (size_t)base*12;
+        const float *gn = m.nrm + (size_t)base*9;
+        for(unsigned i = t; i < n*9; i += kSetupThreads) { s_pos[i] = __ldg(gp + i); s_nrm[i] = __ldg(gn + i); }
+        for(unsigned i = t; i < n*12; i += kSetupThreads) s_col[i] = __ldg(gc + i);
+    }
+    __syncthreads();
+
+    if((unsigned)t < n)
+    {
+        uint32_t *rec = s_rec + t*kRecWords;
+        V3 cam[3], prj[3];
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+        {
+            cam[k].x = fadd(s_pos[t*9 + 3*k + 0], m.px);    // :3900
+            cam[k].y = fadd(s_pos[t*9 + 3*k + 1], m.py);
+            cam[k].z = fadd(s_pos[t*9 + 3*k + 2], m.pz);
+            prj[k] = project_vertex(cam[k], v);             // :3907
+        }
+        // back-face test, :3926-3927, :3943, Eye = (0,0,-1)
+        V3 d1 = { fsub(prj[1].x, prj[0].x), fsub(prj[1].y, prj[0].y), fsub(prj[1].z, prj[0].z) };
+        V3 d2 = { fsub(prj[2].x, prj[0].x), fsub(prj[2].y, prj[0].y), fsub(prj[2].z, prj[0].z) };
+        V3 n1 = normalize3(d1), n2 = normalize3(d2);
+        float crx = fsub(fmul(n1.y, n2.z), fmul(n1.z, n2.y));
+        float cry = fsub(fmul(n1.z, n2.x), fmul(n1.x, n2.z));
+        float crz = fsub(fmul(n1.x, n2.y), fmul(n1.y, n2.x));
+        float facing = fadd(fadd(fmul(0.0f, crx), fmul(0.0f, cry)), fmul(-1.0f, crz));
+
+        int nedges = 0, first_row = 0, max_y = 0;
+        uint32_t emit = 0;                                  // slot of the k-th edge FillEdgeTable emits, 2 bits each
+        int slot_of[3] = {-1, -1, -1};
+        int mn[3], mx[3];                                   // per edge: index of upper / lower end
+        float minx_s = 0.0f, maxx_s = 0.0f;
+
+        if(facing > 0.0f)
+        {
+            // pass 1: which edges survive and where MergeSort puts them (needs only y)
+            int key[3];
+            bool counted[3];
+#pragma unroll
+            for(int e = 0; e < 3; ++e)
+            {
+                int i0 = e, i1 = (e + 1)%3;                 // :3936-3941
+                int a = i0, b = i1;
+                if(prj[a].y > prj[b].y) { int s = a; a = b; b = s; }     // :3957
+                mn[e] = a; mx[e] = b;
+                counted[e] = (prj[b].y > 0.0f) && (fsub(prj[a].y, prj[b].y) != 0.0f);   // :3968, :4066
+                float rmin = __int2float_rn(round_s32(prj[a].y));
+                key[e] = __float2int_rz((0.0f > rmin) ? 0.0f : rmin);                   // :3999
+            }
+            int order[3]; int k = 0;
+#pragma unroll
+            for(int e = 0; e < 3; ++e) if(counted[e]) order[k++] = e;
+            nedges = k;
+            if(k == 2)                                      // projekt.cpp:9-19
+            {
+                if(key[order[0]] > key[order[1]]) { int s = order[0]; order[0] = order[1]; order[1] = s; }
+            }
+            else if(k == 3)                                 // projekt.cpp:20-59 with Half0 = 1
+            {
+                int a = order[1], b = order[2], c = order[0];
+                if(key[a] > key[b]) { int s = a; a = b; b = s; }
+                if(key[c] < key[a]) { order[0] = c; order[1] = a; order[2] = b; }
+                else if(key[c] < key[b]) { order[0] = a; order[1] = c; order[2] = b; }
+                else { order[0] = a; order[1] = b; order[2] = c; }
+            }
+            for(int s = 0; s < k; ++s) slot_of[order[s]] = s;
+            {
+                int q = 0;
+#pragma unroll
+                for(int e = 0; e < 3; ++e) if(counted[e]) { emit |= (uint32_t)slot_of[e] << (2*q); ++q; }
+            }
+
+            if(k > 0)
+            {
+                float lit[3][4];
+#pragma unroll
+                for(int q = 0; q < 3; ++q)
+                {
+                    float4 c4 = *reinterpret_cast<const float4 *>(&s_col[t*12 + 4*q]);
+                    float col[4] = { c4.x, c4.y, c4.z, c4.w };
+                    V3 nr = { s_nrm[t*9 + 3*q + 0], s_nrm[t*9 + 3*q + 1], s_nrm[t*9 + 3*q + 2] };
+                    light_vertex(cam[q], nr, col, v, lit[q]);
+                }
+                int max_row = (int)0x80000000;
+#pragma unroll
+                for(int e = 0; e < 3; ++e)
+                {
+                    if(slot_of[e] < 0) continue;
+                    uint32_t *E = rec + R_EDGE0 + slot_of[e]*kEdgeWords;
+                    const V3 minv = prj[mn[e]], maxv = prj[mx[e]];
+                    int ymax = round_s32(maxv.y);                           // :3988
+                    float clipped = 0.0f, tt = 0.0f;
+                    if(minv.y < 0.0f)                                       // :3993-3997
+                    {
+                        clipped = -minv.y;
+                        tt = fdiv(-minv.y, fsub(maxv.y, minv.y));
+                    }
+                    int ymin = key[e];
+                    float ydiff = fsub(__int2float_rn(ymax), __int2float_rn(ymin));                  // :4070
+                    float zg = fdiv(fsub(cam[mx[e]].z, cam[mn[e]].z), ydiff);                        // :4072
+                    float g = fdiv(fsub(maxv.x, minv.x), fsub(maxv.y, minv.y));                      // :4073
+                    float x = fadd(minv.x, fmul(clipped, g));                                        // :4075
+                    float z = fadd(cam[mn[e]].z, fmul(clipped, zg));                                 // :4076
+                    E[E_YMIN] = (uint32_t)ymin; E[E_YMAX] = (uint32_t)ymax;
+                    E[E_X] = __float_as_uint(x); E[E_DX] = __float_as_uint(g);
+                    E[E_Z] = __float_as_uint(z); E[E_DZ] = __float_as_uint(zg);
+                    float omt = fsub(1.0f, tt);
+#pragma unroll
+                    for(int i = 0; i < 4; ++i)
+                    {
+                        float c0 = fadd(fmul(omt, lit[mn[e]][i]), fmul(tt, lit[mx[e]][i]));          // :4091
+                        E[E_C + i] = __float_as_uint(c0);
+                        E[E_DC + i] = __float_as_uint(fdiv(fsub(lit[mx[e]][i], c0), ydiff));         // :4096
+                    }
+                    E[E_LEFT] = (ymin == round_s32(prj[e].y)) ? 1u : 0u;                             // :4093
+                    if(ymax > max_row) max_row = ymax;
+                    if(slot_of[e] == 0) first_row = ymin;                                            // projekt.cpp:173
+                }
+                max_y = (max_row > v.height) ? v.height : max_row;                                   // :187-196
+            }
+            minx_s = fminf(prj[0].x, fminf(prj[1].x, prj[2].x));
+            maxx_s = fmaxf(prj[0].x, fmaxf(prj[1].x, prj[2].x));
+        }
+        rec[R_NEDGES] = (uint32_t)nedges; rec[R_FIRSTROW] = (uint32_t)first_row;
+        rec[R_MAXY] = (uint32_t)max_y; rec[R_PRIM] = m.prim_base + base + t;
+        rec[R_EDGE0 + 3*kEdgeWords] = emit; rec[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec[R_EDGE0 + 3*kEdgeWords + 2] = 0;
+
+        // Conservative screen rectangle for the binner.  Span ends are edge x values, which lie
+        // on the projected edges, i.e. inside [min vertex x, max vertex x] up to the rounding
+        // drift of the row-by-row accumulation (<= rows * 2^-23 * |x|); columns are clamped the
+        // way the span code clamps them (projekt.cpp:381-400), so fully off-screen spans still
+        // land in column 0 / Width-1.
+        uint2 rect = make_uint2(1u, 0u);                    // tx0 > tx1: empty
+        int ra = max(first_row, v.band_y0), rb = min(max_y, v.band_y1);
+        if(nedges >= 2 && ra < rb)
+        {
+            float rows = (float)(max_y - first_row);
+            float mag = fmaxf(fmaxf(fabsf(minx_s), fabsf(maxx_s)), 1.0f);
+            float slack = 1.5f + rows*mag*1.1920929e-7f;
+            float x0f = fminf(fmaxf(floorf(minx_s - slack), 0.0f), (float)(v.width - 1));
+            float x1f = fminf(fmaxf(ceilf(maxx_s + slack), 0.0f), (float)(v.width - 1));
+            if(!(x0f <= x1f)) { x0f = 0.0f; x1f = (float)(v.width - 1); }   // NaN: be conservative
+            int tx0 = (int)x0f/v.tile_w, tx1 = (int)x1f/v.tile_w;
+            int ty0 = (ra - v.band_y0)/v.tile_h, ty1 = (rb - 1 - v.band_y0)/v.tile_h;
+            rect = make_uint2((unsigned)tx0 | ((unsigned)tx1 << 16), (unsigned)ty0 | ((unsigned)ty1 << 16));
+            for(int ty = ty0; ty <= ty1; ++ty)
+                for(int tx = tx0; tx <= tx1; ++tx)
+                    atomicAdd(&out.tile_count[ty*v.tiles_x + tx], 1u);
+            atomicAdd(&s_binned, 1u);
+            atomicAdd(&s_pairs, (unsigned)((tx1 - tx0 + 1)*(ty1 - ty0 + 1)));
+        }
+        out.rects[m.prim_base + base + t] = rect;
+    }
+    __syncthreads();
+
+    // coalesced 128-bit record store
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(s_rec);
+        float4 *dst = reinterpret_cast<float4 *>(out.recs) + (size_t)(m.prim_base + base)*kRecVec4;
+        for(unsigned i = t; i < n*kRecVec4; i += kSetupThreads) dst[i] = src[i];
+    }
+    if(t == 0 && s_binned)
+    {
+        atomicAdd(&out.counters[0], (unsigned long long)s_binned);
+        atomicAdd(&out.counters[1], (unsigned long long)s_pairs);
+    }
+}
+
+void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s)
+{
+    if(m.ntri == 0) return;
+    unsigned blocks = (m.ntri + kSetupThreads - 1)/kSetupThreads;
+    setup_kernel<<<blocks, kSetupThreads, 0, s>>>(v, m, out);
+}
+
+// ---------------------------------------------------------------- clear
+__global__ void clear_kernel(uint32_t *color, int cpw, float *depth, int ds, int width, int rows,
+                             uint32_t cval, float dval)
+{
+    int x = blockIdx.x*blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if(x < width && y < rows)
+    {
+        color[(size_t)y*cpw + x] = cval;
+        depth[(size_t)y*ds + x] = dval;
+    }
+}
+
+void launch_clear(uint32_t *color, int color_pitch_words, float *depth, int depth_stride,
+                  int width, int rows, uint32_t cval, float dval, cudaStream_t s)
+{
+    dim3 grid((width + 255)/256, rows);
+    clear_kernel<<<grid, 256, 0, s>>>(color, color_pitch_words, depth, depth_stride, width, rows, cval, dval);
+}
+
+} // namespace b200r

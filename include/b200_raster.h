@@ -1,0 +1,217 @@
+/* b200_raster.h -- C ABI of the B200 rasterization back end (libb200raster.so).
+ *
+ * Drop-in boundary for the reference's per-object call pair:
+ *     u32  FillEdgeTable(render_entry_3d_object*, game_render_commands*, b32)   projekt.cpp:3882
+ *     void DrawModel(loaded_bitmap*, edge_info*, u32, game_render_commands*,
+ *                    loaded_bitmap *Bitmap, b32 Phong)                          projekt.cpp:162
+ * (and its thread-pool variants projekt.cpp:2350, 3362, 3615, which only redistribute the same
+ * work).  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * The structs of projekt.h:2-37 are reproduced byte-for-byte.  The structs projekt.h *uses* but
+ * does not define (loaded_bitmap, game_render_commands, light_data, light_info,
+ * projective_transform, v2/v3/v4) are absent from the reference snapshot; their layouts are
+ * pinned here and become part of this published header.  When this file
+ * is included from inside the reference's own unity build, define B200R_NO_REFERENCE_TYPES
+ * first so the renderer's own definitions are used.
+ *
+ * Semantics: Gouraud path (PhongShading == 0, Bitmap == 0); one triangle = one
+ * object ("level 1"); coverage and depth bit-exact with the reference's
+ * scalar arithmetic; equal depth resolved as in the reference (first submitted wins,
+ * projekt.cpp:525).  There is no CPU fallback: every entry point fails with
+ * B200R_E_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef B200_RASTER_H
+#define B200_RASTER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef B200R_NO_REFERENCE_TYPES
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef int32_t s32;
+typedef float r32;
+typedef int32_t b32;
+
+typedef struct v2 { r32 x, y; } v2;
+typedef struct v3 { r32 x, y, z; } v3;
+typedef struct v4 { r32 x, y, z, w; } v4;          /* colours: x=r y=g z=b w=a */
+
+typedef struct loaded_bitmap               /* projekt.cpp:387, 414-416 */
+{
+    s32 Width;
+    s32 Height;
+    s32 Pitch;                             /* bytes per row */
+    void *Memory;                          /* u32 ARGB8 */
+} loaded_bitmap;
+
+typedef struct projective_transform        /* projekt.cpp:79-89, 152-155 */
+{
+    r32 MetersToPixels;
+    v2 ScreenCenter;
+    r32 FocalLength;
+    r32 DistanceAboveTarget;
+} projective_transform;
+
+typedef struct light_info { v3 P; v4 Intensity; } light_info;      /* projekt.cpp:4026-4027 */
+
+typedef struct light_data                  /* projekt.cpp:3885, 3892, 4010, 4023 */
+{
+    v4 AmbientIntensity;
+    u32 LightCount;
+    light_info *Lights;
+} light_data;
+
+typedef struct game_render_commands        /* projekt.cpp:170-171, 452, 1017, 2325-2331, 4117 */
+{
+    u32 Width;                             /* depth row stride, in floats */
+    r32 *ZBuffer;
+    u8 *ZMask;                             /* CPU spin-lock bytes; unused on the GPU path */
+    light_data LightData;
+    projective_transform Transform;
+    void *ThreadMemory;                    /* CPU work arena; unused on the GPU path */
+    u32 ThreadMemorySize;
+    u32 ThreadMemorySizeUsed;
+    void *SortMemory;                      /* MergeSort scratch; unused on the GPU path */
+} game_render_commands;
+
+typedef struct render_entry_3d_object      /* projekt.h:2-15 */
+{
+    v3 P;
+    u32 VertexCount;
+    b32 Optimized;
+    b32 PhongShading;
+    void *VertexData;                      /* v3[VertexCount], 3 per triangle */
+    void *ColorData;                       /* v4[VertexCount] */
+    void *NormalData;                      /* v3[VertexCount] */
+    void *UVData;                          /* v2[VertexCount] */
+    void *EdgeMemory;                      /* edge_info[VertexCount] */
+    loaded_bitmap *Bitmap;
+} render_entry_3d_object;
+
+typedef struct edge_info                   /* projekt.h:17-37, 120 bytes */
+{
+    s32 YMax;
+    r32 XMin;
+    r32 ZMin;
+    r32 OneOverZMin;
+    r32 Gradient;
+    r32 ZGradient;
+    r32 OneOverZGradient;
+    s32 YMin;
+    r32 UMin;
+    r32 VMin;
+    r32 UGradient;
+    r32 VGradient;
+    b32 Left;
+    v4 MinColor;
+    v4 ColorGradient;
+    v3 MinNormal;
+    v3 NormalGradient;
+    struct edge_info *Next;
+} edge_info;
+#endif /* B200R_NO_REFERENCE_TYPES */
+
+/* ---- status codes: the reference has only Assert (projekt.cpp:25, 2327); we never abort --- */
+#define B200R_OK             0
+#define B200R_E_INVALID     (-1)   /* null / inconsistent arguments                           */
+#define B200R_E_CUDA        (-2)   /* a CUDA call failed; see b200r_last_error                 */
+#define B200R_E_UNSUPPORTED (-3)   /* Phong / textured object, LightCount == 0 or > 8          */
+#define B200R_E_NOMEM       (-4)
+#define B200R_E_NO_DEVICE   (-5)   /* no CUDA device of compute capability 10.x                */
+
+#define B200R_MAX_LIGHTS 8
+
+/* flags of the render calls */
+#define B200R_WHOLE_OBJECT_AEL 1u  /* reserved: reproduce the whole-object active-edge pairing of
+                                      projekt.cpp:198-303; -> UNSUPPORTED   */
+
+typedef struct b200r_context b200r_context;
+
+/* One context per GPU.  Device < 0 keeps the calling thread's current device. */
+int b200r_create(b200r_context **Context, int Device);
+void b200r_destroy(b200r_context *Context);
+const char *b200r_last_error(const b200r_context *Context);
+
+/* Launch on an existing CUDA stream (a cudaStream_t cast to void*); 0 = the context's own. */
+int b200r_set_stream(b200r_context *Context, void *CudaStream);
+int b200r_sync(b200r_context *Context);
+
+/* Screen tile staged in shared memory by the raster kernel: 64x32 (default), 32x32, 128x16
+ * or 64x16 pixels. */
+int b200r_set_tile(b200r_context *Context, int TileWidth, int TileHeight);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-pointer drop-in: replaces, for a batch of objects, the pair
+ *   FillEdgeTable(Object, Commands, 0); DrawModel(OutputTarget, Object->EdgeMemory, n, Commands)
+ * (projekt.cpp:3882 + 162).  Colour (OutputTarget->Memory) and depth (Commands->ZBuffer) are
+ * read from and written back to the caller's host buffers, so pre-existing contents take part
+ * in the depth test exactly as in the reference (projekt.cpp:525); nothing is cleared.
+ * EdgeMemory / SortMemory / ThreadMemory / ZMask may be null.  Blocking.
+ * ------------------------------------------------------------------------------------------ */
+int b200r_render_objects(b200r_context *Context, const render_entry_3d_object *Objects,
+                         u32 ObjectCount, const game_render_commands *Commands,
+                         const loaded_bitmap *OutputTarget, u32 Flags);
+
+/* Replaces FillEdgeTable alone (projekt.cpp:3882): sorted edge_info records are written to
+ * Object->EdgeMemory (host, room for VertexCount records) in the reference's MergeSort order
+ * (projekt.cpp:2-72, ties included).  Only the fields the Gouraud path defines are written
+ * (YMin YMax XMin Gradient ZMin ZGradient MinColor ColorGradient Left, plus Next = 0).
+ * Returns the edge count (>= 0) or a negative status. */
+int b200r_fill_edge_table(b200r_context *Context, const render_entry_3d_object *Object,
+                          const game_render_commands *Commands, b32 PhongShading);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident path (what the host-pointer call is built from).  All pointers below are
+ * device pointers; calls are asynchronous on the context's stream.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200r_device_mesh
+{
+    const r32 *Positions;      /* v3 per vertex (VertexData)  */
+    const r32 *Colors;         /* v4 per vertex (ColorData)   */
+    const r32 *Normals;        /* v3 per vertex (NormalData)  */
+    u32 TriangleCount;         /* VertexCount / 3             */
+    v3 P;                      /* render_entry_3d_object::P   */
+} b200r_device_mesh;
+
+typedef struct b200r_device_target
+{
+    u32 *Color;                /* first row of the band, ARGB8                                  */
+    r32 *Depth;
+    s32 Width, Height;         /* the logical screen (loaded_bitmap Width/Height)              */
+    s32 ColorPitch;            /* bytes per row                                                 */
+    s32 DepthStride;           /* floats per row (game_render_commands::Width)                  */
+    s32 BandFirstRow;          /* this target holds screen rows [BandFirstRow, +BandRows)       */
+    s32 BandRows;              /* = Height for a whole frame                                    */
+} b200r_device_target;
+
+/* Lights and transform are taken from Commands (host struct; ZBuffer etc. ignored). */
+int b200r_render_device(b200r_context *Context, const b200r_device_mesh *Meshes, u32 MeshCount,
+                        const game_render_commands *Commands, const b200r_device_target *Target,
+                        u32 Flags);
+
+/* Fill a device target band with a clear colour / depth (the reference never clears,
+ * SURVEY.md 8b "Persistence"; callers do). */
+int b200r_clear_device(b200r_context *Context, const b200r_device_target *Target, u32 Color,
+                       r32 Depth);
+
+typedef struct b200r_frame_stats
+{
+    uint64_t Triangles;        /* submitted in the last render call                             */
+    uint64_t Binned;           /* triangles with >= 2 edge records that touch the band          */
+    uint64_t TilePairs;        /* (triangle, tile) pairs produced by the binner                 */
+    uint64_t Tiles;            /* screen tiles of the band                                      */
+    uint64_t KernelLaunches;   /* kernels launched by this context since creation               */
+    uint64_t Reruns;           /* frames re-issued because the pair list had to grow            */
+} b200r_frame_stats;
+
+/* Valid after b200r_sync (or any blocking call). */
+int b200r_get_stats(b200r_context *Context, b200r_frame_stats *Stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_RASTER_H */
