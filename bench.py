@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""Benchmark of the rasterization hot path (BASELINE.json metric) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3] [--impl ours|reference]
+
+A "step" is one frame: the whole hot path (setup -> bin -> raster) over one synthetic scene.
+Default workload = BASELINE.json configs[1] ("C2": 1 M ~10-pixel triangles, 1920x1080,
+depth-tested, Gouraud).  With N > 1 ranks (torchrun, one process per GPU) the path shards by
+FRAME: every rank renders its own 1 M-triangle frame (weak scaling, no data-path collective);
+the NCCL gather of the finished colour images to rank 0 is timed separately ("with_gather").
+
+Prints ONE JSON line (see the contract in the task statement): value = device-resident
+throughput (CUDA events, max over ranks), e2e = same metric through the host-pointer C-ABI call
+(H2D + kernels + D2H inside the timed region), roofline = dominant kernel vs measured HBM peak,
+cpu_baseline = the verbatim reference scalar path on this box's host cores.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the verbatim
+FillEdgeTable + DrawModel per single-triangle object, all host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRICS = {
+    "c2": ("Mtriangles/s", "C2: 1M ~10px triangles, 1920x1080, depth-tested Gouraud (setup/binning bound)"),
+    "c3": ("Mpixels/s", "C3: 50k large overlapping triangles, 3840x2160, ~35x overdraw (fill bound)"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(config):
+    """dram bytes per raster_kernel launch from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(config)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        self.marks = []
+
+    def mark(self):
+        self.marks.append(time.time())
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for n, v in zip(names, r[4:8]):
+                    if v.strip().lower() == "active":
+                        reasons.add(n)
+            except Exception:
+                continue
+        if sm:
+            # samples under load = upper half (the sampler also sees idle gaps between passes)
+            s = sorted(sm)
+            out.update(sm_mhz=float(np.median(s[len(s) // 2:])), sm_max_mhz=mx,
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_scene(config, rank):
+    from cpu_renderer_b200 import scene as sc
+    cfg = dict(sc.CONFIGS[config])
+    cfg["seed"] = cfg["seed"] + 0x1000 * rank       # every rank renders its own frame
+    return sc.triangle_soup(config, **cfg)
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from cpu_renderer_b200 import scene as sc
+    unit, workload = METRICS[args.config]
+    scene = build_scene(args.config, 0)
+    # bounded sample: a prefix of the frame's triangle list
+    sample = min(scene.triangle_count, args.ref_sample or (250_000 if args.config == "c2" else 4000))
+    s = sc.Scene(scene.name, scene.width, scene.height, scene.transform, scene.positions[:sample * 3],
+                 scene.colors[:sample * 3], scene.normals[:sample * 3], scene.uvs[:sample * 3])
+    threads = args.ref_threads or (os.cpu_count() or 1)
+    kind = "reference" if ol.ref_available() else "port"
+    res = time_cpu(ol, s, threads, args.steps, args.warmup, kind)
+    ms = res["ms_per_step"]
+    units = sample if unit == "Mtriangles/s" else scene.width * scene.height * (sample / scene.triangle_count)
+    value = units / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": unit, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "triangles_per_step": sample, "width": scene.width,
+                   "height": scene.height},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind,
+                         "sample": res["sample"]},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cpu_count": os.cpu_count(), "model": cpu_model()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_model():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def time_cpu(ol, s, threads, steps, warmup, kind):
+    """Time the reference's scalar path (verbatim build if present, else the port) on scene s."""
+    lib_o = ol.oracle()
+    pre = ol.oracle_render(s)                     # untimed: tells which triangles crash the reference
+    skip = pre["would_crash"]
+    n = s.triangle_count
+    os_ = ol.OracleScene(s)
+    times = []
+    if kind == "reference":
+        lib = ol.ref()
+        colors = [np.zeros((s.height, s.width), np.uint32) for _ in range(threads)]
+        zs = [np.zeros((s.height, s.width), np.float32) for _ in range(threads)]
+        bmps = (ol.RefLoadedBitmap * threads)(*[
+            ol.RefLoadedBitmap(s.width, s.height, c.strides[0], c.ctypes.data) for c in colors])
+        zptrs = (ol.f32p * threads)(*[z.ctypes.data_as(ol.f32p) for z in zs])
+        cmd = os_.ref_commands(zs[0])
+        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc))
+        fb = C.cast(lib_o.orc_ref_fallback, C.c_void_p)
+        user = C.cast(C.pointer(ctx), C.c_void_p)
+        for i in range(warmup + steps):
+            colors[0].fill(s.clear_color); zs[0].fill(s.clear_depth)
+            t0 = time.perf_counter()
+            lib.ref_render_triangles_mt(os_.pos_p, os_.col_p, os_.nrm_p, os_.uvs_p, n, os_.P,
+                                        C.byref(cmd), bmps, zptrs, threads, skip.ctypes.data, fb, user)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        same = bool(np.array_equal(zs[0].view(np.uint32), pre["z"].view(np.uint32)) and
+                    np.array_equal(colors[0], pre["color"]))
+        note = (f"verbatim FillEdgeTable+DrawModel per single-triangle object (oracle/_ref), {threads} threads with "
+                f"private targets folded in submission order; {int(skip.sum())} of {n} triangles that null-deref "
+                f"in the reference go through the oracle port; image identical to 1-thread oracle: {same}")
+    else:
+        for i in range(warmup + steps):
+            color, z, _ = ol.new_targets(s)
+            t = ol._orc_target(color, z, None)
+            st = ol.OrcStats()
+            t0 = time.perf_counter()
+            lib_o.orc_render_triangles_mt(os_.pos_p, os_.col_p, os_.nrm_p, n, os_.P, C.byref(os_.orc),
+                                          C.byref(t), threads, C.byref(st))
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+        note = f"oracle port (oracle/raster_oracle.c), {threads} threads"
+    ms = 1e3 * float(np.mean(times))
+    return {"ms_per_step": ms, "sample": f"{n} triangles of the frame per step, {len(times)} steps; {note}"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cpu_renderer_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    unit, workload = METRICS[args.config]
+    scene = build_scene(args.config, rank)
+    ntri, W, H = scene.triangle_count, scene.width, scene.height
+    K, Wm = args.steps, args.warmup
+    wpad = (W + 63) // 64 * 64
+
+    stream = torch.cuda.Stream(device=dev)
+    r = api.Renderer(local_rank)
+    if args.tile:
+        tw, th = (int(x) for x in args.tile.split("x"))
+        r.set_tile(tw, th)
+    r.set_stream(stream.cuda_stream)
+
+    d_pos = torch.from_numpy(scene.positions).to(dev)
+    d_col = torch.from_numpy(scene.colors).to(dev)
+    d_nrm = torch.from_numpy(scene.normals).to(dev)
+    mesh = api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*scene.object_p))
+    cmd, keep = api.make_commands(scene)
+    nsets = max(K, Wm, 1)
+    colors = [torch.empty((H, wpad), dtype=torch.int32, device=dev) for _ in range(nsets)]
+    depths = [torch.empty((H, wpad), dtype=torch.float32, device=dev) for _ in range(nsets)]
+    targets = [api.device_target(c.data_ptr(), z.data_ptr(), W, H, wpad * 4, wpad, 0, H)
+               for c, z in zip(colors, depths)]
+
+    def clear_all():
+        for c, z in zip(colors, depths):
+            c.fill_(scene.clear_color); z.fill_(scene.clear_depth)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- device-resident throughput: W warm-up frames, then exactly K timed frames ----------
+    clear_all()
+    with torch.cuda.stream(stream):
+        for i in range(Wm):
+            r.render_device([mesh], cmd, targets[i % nsets])
+        r.sync()
+    clear_all()                                   # every timed frame starts from cleared targets
+    launches0 = r.stats()["KernelLaunches"]
+    barrier(); torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for i in range(K):
+            r.render_device([mesh], cmd, targets[i])
+        ev1.record(stream)
+        r.sync()
+    torch.cuda.synchronize(); barrier()
+    ms_local = ev0.elapsed_time(ev1) / K
+    launches = r.stats()["KernelLaunches"] - launches0
+    stats = r.stats()
+    ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+
+    # ---- per-kernel durations (CUDA events on the launching stream, separate pass) ---------
+    clear_all()
+    r.set_profiling(True)
+    stage = {k: [] for k in api.STAGES}
+    t_end = time.time() + 1.0
+    with torch.cuda.stream(stream):
+        i = 0
+        while i < K or (time.time() < t_end and i < 64 * K):
+            if i % nsets == 0 and i:
+                clear_all()
+            r.render_device([mesh], cmd, targets[i % nsets])
+            for k, v in r.stage_ms().items():
+                stage[k].append(v)
+            i += 1
+    r.set_profiling(False)
+    stage_ms = {k: float(np.mean(v)) for k, v in stage.items()}
+    dominant = max(stage_ms, key=stage_ms.get)
+
+    # ---- optional: NCCL gather of the finished colour images to rank 0 ----------------------
+    with_gather = None
+    if world > 1:
+        clear_all()
+        gl = [torch.empty_like(colors[0]) for _ in range(world)] if rank == 0 else None
+        barrier(); torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for i in range(K):
+                r.render_device([mesh], cmd, targets[i])
+                dist.gather(colors[i], gl, dst=0)     # stream-ordered after this frame's kernels
+            ev1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        g = torch.tensor([ev0.elapsed_time(ev1) / K], dtype=torch.float64, device=dev)
+        dist.all_reduce(g, op=dist.ReduceOp.MAX)
+        with_gather = {"ms_per_step": float(g.item()), "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1))}
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers) --------------------
+    r.set_stream(0)
+    e2e_steps = min(K, 10)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()      # noqa: E731
+    from cpu_renderer_b200 import scene as sc
+    hs = sc.Scene(scene.name, W, H, scene.transform, pin(scene.positions), pin(scene.colors),
+                  pin(scene.normals), scene.uvs, scene.object_p, scene.ambient, scene.lights)
+    hcol = [torch.full((H, W), scene.clear_color, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+            for _ in range(e2e_steps + 1)]
+    hz = [torch.full((H, W), scene.clear_depth, dtype=torch.float32).pin_memory().numpy()
+          for _ in range(e2e_steps + 1)]
+    r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps])       # warm-up (allocations)
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r.render_scene_host(hs, hcol[i], hz[i])
+    torch.cuda.synchronize()
+    e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
+    e_t = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e_t.item())
+    covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
+
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def to_value(ms_step, n_ranks):
+        units = ntri if unit == "Mtriangles/s" else W * H
+        return n_ranks * units / (ms_step * 1e-3) / 1e6
+
+    peak, peak_src = measured_peak()
+    a_frame = 120.0 * ntri + 16.0 * W * H
+    own_bytes = {"setup_kernel": 120.0 * ntri, "raster_kernel": 16.0 * W * H,
+                 "tile_scan_kernel": 0.0, "scatter_kernel": 0.0}[dominant]
+    achieved = own_bytes / (stage_ms[dominant] * 1e-3) / 1e9
+    frame_achieved = a_frame / (ms * 1e-3) / 1e9
+    traffic = ncu_traffic(args.config)
+    line = {
+        "metric": unit, "value": to_value(ms, world), "unit": unit, "n_gpus": world, "steps": K,
+        "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "triangles": ntri, "width": W, "height": H,
+                   "parallelism": f"frame-parallel x{world}" if world > 1 else "1 GPU",
+                   "tile": args.tile or "64x32",
+                   "l2": "each timed frame streams >126 MB (vertices + records + pair lists + its own "
+                         "pre-cleared target), i.e. inputs larger than L2; no explicit flush",
+                   "targets": "one pre-cleared colour/depth pair per timed frame (clear outside the timed region)"},
+        "mpixels_per_s": world * W * H / (ms * 1e-3) / 1e6,
+        "mtriangles_per_s": world * ntri / (ms * 1e-3) / 1e6,
+        "frame_ms": ms,
+        "gpu_launches": int(launches),
+        "stage_ms": stage_ms,
+        "binner": {"binned_triangles": stats["Binned"], "tile_pairs": stats["TilePairs"], "tiles": stats["Tiles"],
+                   "reruns": stats["Reruns"]},
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": own_bytes,
+                     "kernel_ms": stage_ms[dominant],
+                     "kernel_share_of_step": stage_ms[dominant] / max(sum(stage_ms.values()), 1e-9),
+                     "frame": {"algorithmic_bytes": a_frame, "achieved": frame_achieved,
+                               "frac": frame_achieved / peak}},
+        "e2e": {"value": to_value(e2e_ms, world), "unit": unit, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(ntri * 120 + 2 * W * H * 4), "d2h_bytes_per_step": int(2 * W * H * 4),
+                "steps": e2e_steps, "covered_pixels": covered,
+                "api": "b200r_render_objects (host pointers, pinned)"},
+        "clocks": clocks,
+    }
+    if with_gather:
+        with_gather["value"] = to_value(with_gather["ms_per_step"], world)
+        line["with_gather"] = with_gather
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol
+            from cpu_renderer_b200 import scene as sc2
+            sample = min(ntri, 250_000 if args.config == "c2" else 4000)
+            s = sc2.Scene(scene.name, W, H, scene.transform, scene.positions[:sample * 3], scene.colors[:sample * 3],
+                          scene.normals[:sample * 3], scene.uvs[:sample * 3])
+            threads = os.cpu_count() or 1
+            kind = "reference" if ol.ref_available() else "port"
+            res = time_cpu(ol, s, threads, 3, 1, kind)
+            units = sample if unit == "Mtriangles/s" else W * H * (sample / ntri)
+            line["cpu_baseline"] = {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit,
+                                    "cores": threads, "kind": kind, "sample": res["sample"],
+                                    "host": cpu_model()}
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the line
+            line["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port",
+                                    "sample": f"failed: {e!r}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="c2", choices=sorted(METRICS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tile", default=None, help="WxH: 64x32 (default), 32x32, 128x16, 64x16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--ref-threads", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

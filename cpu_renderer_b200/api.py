@@ -20,8 +20,9 @@ WHOLE_OBJECT_AEL = 1
 EXPORTS = [
     "b200r_create", "b200r_destroy", "b200r_last_error", "b200r_set_stream", "b200r_sync",
     "b200r_set_tile", "b200r_render_objects", "b200r_fill_edge_table", "b200r_render_device",
-    "b200r_clear_device", "b200r_get_stats",
+    "b200r_clear_device", "b200r_get_stats", "b200r_set_profiling", "b200r_get_stage_ms",
 ]
+STAGES = ("setup_kernel", "tile_scan_kernel", "scatter_kernel", "raster_kernel")
 
 
 class v2(C.Structure):
@@ -81,7 +82,8 @@ class device_target(C.Structure):
 
 
 class frame_stats(C.Structure):
-    _fields_ = [("Triangles", C.c_uint64), ("Binned", C.c_uint64), ("TilePairs", C.c_uint64),
+    _fields_ = [("Triangles", C.c_uint64), ("Binned", C.c_uint64), ("Segments", C.c_uint64),
+                ("TilePairs", C.c_uint64),
                 ("Tiles", C.c_uint64), ("KernelLaunches", C.c_uint64), ("Reruns", C.c_uint64)]
 
     def as_dict(self):
@@ -136,6 +138,8 @@ def load_library():
                                             C.POINTER(device_target), C.c_uint32]
         lib.b200r_clear_device.argtypes = [ctx, C.POINTER(device_target), C.c_uint32, C.c_float]
         lib.b200r_get_stats.argtypes = [ctx, C.POINTER(frame_stats)]
+        lib.b200r_set_profiling.argtypes = [ctx, C.c_int]
+        lib.b200r_get_stage_ms.argtypes = [ctx, C.POINTER(C.c_float)]
         _lib = lib
     return _lib
 
@@ -195,6 +199,14 @@ class Renderer:
 
     def sync(self):
         self._check(self.lib.b200r_sync(self.ctx))
+
+    def set_profiling(self, enable: bool):
+        self._check(self.lib.b200r_set_profiling(self.ctx, 1 if enable else 0))
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * len(STAGES))()
+        self._check(self.lib.b200r_get_stage_ms(self.ctx, ms))
+        return dict(zip(STAGES, [float(x) for x in ms]))
 
     def stats(self) -> dict:
         s = frame_stats()

@@ -43,6 +43,8 @@ struct FrameWords
 {
     unsigned pair_total;
     unsigned work_counter;
+    unsigned seg_total;
+    unsigned pad;
     unsigned long long counters[2];     // binned triangles, tile pairs
 };
 
@@ -58,7 +60,7 @@ struct b200r_context
     std::string error;
     int tile_w = 64, tile_h = 32;
 
-    DeviceBuffer recs, rects, tiles, pairs, words;
+    DeviceBuffer recs, segs, seg_tiles, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
 
     // the last issued frame, kept so it can be issued again after the pair list grew
@@ -70,6 +72,8 @@ struct b200r_context
     unsigned ntiles = 0;
 
     b200r_frame_stats stats = {};
+    bool profiling = false;
+    cudaEvent_t stage_ev[B200R_STAGES + 1] = {};
 
     // host-pointer path mirrors
     DeviceBuffer d_pos, d_col, d_nrm, d_color, d_depth;
@@ -137,29 +141,39 @@ static int issue_frame(b200r_context *c)
     CU(cudaMemsetAsync(tile_count, 0, (size_t)ntiles*2*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
 
+    const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/(kSegWords*sizeof(uint32_t)), 0xffffffffu);
     SetupOutputs so;
-    so.recs = (uint32_t *)c->recs.ptr;
-    so.rects = (uint2 *)c->rects.ptr;
+    so.recs = nullptr;
+    so.segs = (uint32_t *)c->segs.ptr;
+    so.seg_tiles = (uint2 *)c->seg_tiles.ptr;
+    so.seg_total = &words->seg_total;
+    so.seg_capacity = seg_cap;
     so.tile_count = tile_count;
     so.counters = words->counters;
+    if(c->profiling) CU(cudaEventRecord(c->stage_ev[0], c->stream));
     for(const MeshParams &m : c->meshes)
     {
         launch_setup(v, m, so, c->stream);
         if(m.ntri) c->stats.KernelLaunches += 1;
     }
+    if(c->profiling) CU(cudaEventRecord(c->stage_ev[1], c->stream));
     launch_tile_scan(tile_count, tile_offset, ntiles, &words->pair_total, c->stream);
     c->stats.KernelLaunches += 1;
+    if(c->profiling) CU(cudaEventRecord(c->stage_ev[2], c->stream));
     CU(cudaMemcpyAsync(c->h_words, words, sizeof(FrameWords), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->total_ready, c->stream));
 
     const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
-    launch_scatter(so.rects, c->total_tris, v.tiles_x, tile_offset, tile_fill, (unsigned *)c->pairs.ptr,
-                   &words->pair_total, pair_cap, c->stream);
+    launch_scatter(so.seg_tiles, &words->seg_total, seg_cap, seg_cap, v.tiles_x, tile_offset, tile_fill,
+                   (unsigned *)c->pairs.ptr, &words->pair_total, pair_cap, c->stream);
     if(c->total_tris) c->stats.KernelLaunches += 1;
+    if(c->profiling) CU(cudaEventRecord(c->stage_ev[3], c->stream));
 
     RasterParams rp;
     rp.v = v;
-    rp.recs = so.recs;
+    rp.segs = so.segs;
+    rp.seg_total = &words->seg_total;
+    rp.seg_capacity = seg_cap;
     rp.tile_count = tile_count;
     rp.tile_offset = tile_offset;
     rp.pair_list = (const unsigned *)c->pairs.ptr;
@@ -177,6 +191,7 @@ static int issue_frame(b200r_context *c)
     cudaError_t e = launch_raster(rp, c->sm_count, c->stream);
     if(e != cudaSuccess) return fail(c, B200R_E_CUDA, "raster_kernel launch", e);
     c->stats.KernelLaunches += 1;
+    if(c->profiling) CU(cudaEventRecord(c->stage_ev[4], c->stream));
     CU(cudaGetLastError());
     c->pending = true;
     return B200R_OK;
@@ -189,14 +204,24 @@ static int settle_pending(b200r_context *c)
     {
         CU(cudaEventSynchronize(c->total_ready));
         const unsigned total = c->h_words->pair_total;
+        const unsigned nseg = c->h_words->seg_total;
         const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
+        const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/(kSegWords*sizeof(uint32_t)), 0xffffffffu);
         c->stats.Binned = c->h_words->counters[0];
         c->stats.TilePairs = c->h_words->counters[1];
+        c->stats.Segments = nseg;
         c->pending = false;
-        if(total > pair_cap)
+        if(total > pair_cap || nseg > seg_cap)
         {
+            // the scatter and raster kernels of that frame saw the same totals and did nothing
             CU(cudaStreamSynchronize(c->stream));
-            CU(c->pairs.reserve((size_t)total*sizeof(unsigned)));
+            if(nseg > seg_cap)
+            {
+                CU(c->segs.reserve((size_t)nseg*kSegWords*sizeof(uint32_t)));
+                CU(c->seg_tiles.reserve((size_t)nseg*sizeof(uint2)));
+            }
+            // with the segment list truncated the pair total was an under-count: leave headroom
+            CU(c->pairs.reserve((size_t)std::max<uint64_t>(total, nseg > seg_cap ? (uint64_t)nseg*2 : 0)*sizeof(unsigned)));
             c->stats.Reruns += 1;
             int rc = issue_frame(c);
             if(rc != B200R_OK) return rc;
@@ -242,8 +267,9 @@ void b200r_destroy(b200r_context *c)
     if(!c) return;
     cudaSetDevice(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
-    c->recs.release(); c->rects.release(); c->tiles.release(); c->pairs.release(); c->words.release();
+    c->recs.release(); c->segs.release(); c->seg_tiles.release(); c->tiles.release(); c->pairs.release(); c->words.release();
     c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_color.release(); c->d_depth.release();
+    for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
     if(c->h_words) cudaFreeHost(c->h_words);
     if(c->total_ready) cudaEventDestroy(c->total_ready);
     if(c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -276,8 +302,9 @@ int b200r_sync(b200r_context *c)
 int b200r_set_tile(b200r_context *c, int w, int h)
 {
     if(!c) return B200R_E_INVALID;
-    if(!((w == 64 && h == 32) || (w == 32 && h == 32) || (w == 128 && h == 16) || (w == 64 && h == 16)))
-        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16 or 64x16");
+    if(!((w == 64 && h == 32) || (w == 32 && h == 32) || (w == 128 && h == 16) || (w == 64 && h == 16) ||
+         (w == 128 && h == 32)))
+        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16, 64x16 or 128x32");
     int rc = b200r_sync(c);
     if(rc != B200R_OK) return rc;
     c->tile_w = w; c->tile_h = h;
@@ -317,11 +344,16 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     if(total > 0x7fffffffull) return fail(c, B200R_E_UNSUPPORTED, "more than 2^31-1 triangles per call");
 
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
-    CU(c->recs.reserve((size_t)std::max<uint64_t>(total, 1)*kRecWords*sizeof(uint32_t)));
-    CU(c->rects.reserve((size_t)std::max<uint64_t>(total, 1)*sizeof(uint2)));
+    // first guess: ~2.5 segments and ~3 tile pairs per triangle; both lists grow on demand
+    if(c->segs.bytes == 0)
+    {
+        const uint64_t guess = std::max<uint64_t>(total*5/2, 1u << 16);
+        CU(c->segs.reserve((size_t)guess*kSegWords*sizeof(uint32_t)));
+        CU(c->seg_tiles.reserve((size_t)guess*sizeof(uint2)));
+    }
     CU(c->tiles.reserve((size_t)ntiles*3*sizeof(unsigned)));
     if(c->pairs.bytes == 0)
-        CU(c->pairs.reserve((size_t)std::max<uint64_t>(total + total/2, 1u << 16)*sizeof(unsigned)));
+        CU(c->pairs.reserve((size_t)std::max<uint64_t>(total*3, 1u << 16)*sizeof(unsigned)));
 
     c->view = v;
     c->meshes.swap(ms);
@@ -342,6 +374,28 @@ int b200r_clear_device(b200r_context *c, const b200r_device_target *t, u32 color
     launch_clear(t->Color, t->ColorPitch/4, t->Depth, t->DepthStride, t->Width, t->BandRows, color, depth, c->stream);
     c->stats.KernelLaunches += 1;
     CU(cudaGetLastError());
+    return B200R_OK;
+}
+
+int b200r_set_profiling(b200r_context *c, int enable)
+{
+    if(!c) return B200R_E_INVALID;
+    CU(cudaSetDevice(c->device));
+    int rc = b200r_sync(c);
+    if(rc != B200R_OK) return rc;
+    if(enable && !c->stage_ev[0])
+        for(cudaEvent_t &e : c->stage_ev) CU(cudaEventCreate(&e));
+    c->profiling = enable != 0;
+    return B200R_OK;
+}
+
+int b200r_get_stage_ms(b200r_context *c, float ms[B200R_STAGES])
+{
+    if(!c || !ms) return B200R_E_INVALID;
+    if(!c->profiling) return fail(c, B200R_E_INVALID, "profiling is not enabled");
+    int rc = b200r_sync(c);
+    if(rc != B200R_OK) return rc;
+    for(int i = 0; i < B200R_STAGES; ++i) CU(cudaEventElapsedTime(&ms[i], c->stage_ev[i], c->stage_ev[i + 1]));
     return B200R_OK;
 }
 
@@ -482,14 +536,14 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     if(rc != B200R_OK) return rc;
     v.tiles_x = 1; v.tiles_y = 1; v.tile_w = 1 << 21; v.tile_h = 1 << 21;
     CU(c->recs.reserve((size_t)tris*kRecWords*sizeof(uint32_t)));
-    CU(c->rects.reserve((size_t)tris*sizeof(uint2)));
     CU(c->tiles.reserve(3*sizeof(unsigned)));
     unsigned *tile_count = (unsigned *)c->tiles.ptr;
     FrameWords *words = (FrameWords *)c->words.ptr;
     CU(cudaMemsetAsync(tile_count, 0, 3*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
     SetupOutputs so;
-    so.recs = (uint32_t *)c->recs.ptr; so.rects = (uint2 *)c->rects.ptr;
+    so.recs = (uint32_t *)c->recs.ptr; so.segs = nullptr; so.seg_tiles = nullptr;
+    so.seg_total = &words->seg_total; so.seg_capacity = 0;
     so.tile_count = tile_count; so.counters = words->counters;
     MeshParams mp;
     mp.pos = meshes[0].Positions; mp.col = meshes[0].Colors; mp.nrm = meshes[0].Normals;

@@ -1,11 +1,11 @@
-// Sort-middle binner (sm_100a): per-tile triangle lists from the set-up kernel's tile
-// rectangles.  The reference has no binning (its nearest analogue is MergeSort by YMin plus
+// Sort-middle binner (sm_100a): per-tile lists of trapezoid segments from the set-up kernel's
+// exact per-segment tile columns.  The reference has no binning (its nearest analogue is MergeSort by YMin plus
 // one work item per scan line, projekt.cpp:2-72, 3509-3609); this stage exists because the
 // raster kernel keeps a screen tile on chip.
 //
-//   count   (inside setup_kernel)   tile_count[t] += 1 per covered tile
+//   count   (inside setup_kernel)   tile_count[t] += 1 per tile a segment touches
 //   scan    tile_scan_kernel        exclusive prefix sum over tiles -> tile_offset, pair_total
-//   scatter scatter_kernel          list[tile_offset[t] + slot] = triangle
+//   scatter scatter_kernel          list[tile_offset[t] + slot] = segment
 //
 // List order inside a bin is NOT submission order (slots are handed out by atomics): the
 // raster kernel resolves depth with the order-independent rule
@@ -57,27 +57,26 @@ tile_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offs
     for(unsigned i = lo; i < hi; ++i) { offset[i] = run; run += count[i]; }
 }
 
-// One thread per triangle; lanes whose triangles fall into the same tile contend on that
-// tile's cursor, which the L2 atomic unit serialises.
+// One thread per segment; lanes whose segments fall into the same tile contend on that tile's
+// cursor, which the L2 atomic unit serialises.
 __global__ void __launch_bounds__(256)
-scatter_kernel(const uint2 *__restrict__ rects, unsigned ntri, int tiles_x,
+scatter_kernel(const uint2 *__restrict__ seg_tiles, const unsigned *__restrict__ seg_total,
+               unsigned seg_capacity, int tiles_x,
                const unsigned *__restrict__ tile_offset, unsigned *__restrict__ tile_fill,
                unsigned *__restrict__ pair_list, const unsigned *__restrict__ pair_total,
                unsigned pair_capacity)
 {
-    if(*pair_total > pair_capacity) return;             // host grows the list and re-issues
-    unsigned tri = blockIdx.x*blockDim.x + threadIdx.x;
-    if(tri >= ntri) return;
-    uint2 r = rects[tri];
-    int tx0 = r.x & 0xffff, tx1 = r.x >> 16, ty0 = r.y & 0xffff, ty1 = r.y >> 16;
-    if(tx0 > tx1) return;
-    for(int ty = ty0; ty <= ty1; ++ty)
+    const unsigned nseg = *seg_total;
+    if(nseg > seg_capacity || *pair_total > pair_capacity) return;   // host grows and re-issues
+    for(unsigned seg = blockIdx.x*blockDim.x + threadIdx.x; seg < nseg; seg += gridDim.x*blockDim.x)
     {
+        const uint2 r = seg_tiles[seg];
+        const int tx0 = r.y & 0xffff, tx1 = r.y >> 16;
         for(int tx = tx0; tx <= tx1; ++tx)
         {
-            unsigned tile = (unsigned)(ty*tiles_x + tx);
-            unsigned slot = atomicAdd(&tile_fill[tile], 1u);
-            pair_list[tile_offset[tile] + slot] = tri;
+            const unsigned tile = r.x*(unsigned)tiles_x + (unsigned)tx;
+            const unsigned slot = atomicAdd(&tile_fill[tile], 1u);
+            pair_list[tile_offset[tile] + slot] = seg;
         }
     }
 }
@@ -88,13 +87,17 @@ void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigne
     tile_scan_kernel<<<1, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, pair_total);
 }
 
-void launch_scatter(const uint2 *rects, unsigned ntri, int tiles_x, const unsigned *tile_offset,
+void launch_scatter(const uint2 *seg_tiles, const unsigned *seg_total, unsigned seg_capacity,
+                    unsigned max_segments, int tiles_x, const unsigned *tile_offset,
                     unsigned *tile_fill, unsigned *pair_list, const unsigned *pair_total,
                     unsigned pair_capacity, cudaStream_t s)
 {
-    if(ntri == 0) return;
-    scatter_kernel<<<(ntri + 255)/256, 256, 0, s>>>(rects, ntri, tiles_x, tile_offset, tile_fill,
-                                                    pair_list, pair_total, pair_capacity);
+    if(max_segments == 0) return;
+    // the segment count lives on the device: size the grid for the capacity, grid-stride inside
+    unsigned blocks = (max_segments + 255)/256;
+    if(blocks > 148*16) blocks = 148*16;
+    scatter_kernel<<<blocks, 256, 0, s>>>(seg_tiles, seg_total, seg_capacity, tiles_x, tile_offset, tile_fill,
+                                          pair_list, pair_total, pair_capacity);
 }
 
 } // namespace b200r

@@ -50,10 +50,21 @@ constexpr int kRecVec4 = kRecWords/4;
 enum { E_YMIN = 0, E_YMAX = 1, E_X = 2, E_DX = 3, E_Z = 4, E_DZ = 5, E_C = 6, E_DC = 10, E_LEFT = 14 };
 enum { R_NEDGES = 0, R_FIRSTROW = 1, R_MAXY = 2, R_PRIM = 3, R_EDGE0 = 4 };
 
+// Trapezoid segment: the rows of one triangle that (a) share one pair of active edges and
+// (b) lie in one tile-row band, with both edges' running values at the segment's first row.
+// Written by the set-up kernel (which walks each triangle's rows once), consumed by the raster
+// kernel, which therefore needs no active-list logic and never replays rows above its tile.
+constexpr int kSegWords = 28;       // 112 bytes = 7 float4
+constexpr int kSegVec4 = kSegWords/4;
+enum { S_PRIM = 0, S_Y0 = 1, S_ROWS = 2, S_TX = 3, S_L = 4, S_R = 16 };   // L/R: x z c[4] dx dz dc[4]
+constexpr unsigned kSegNonFinite = 0x10000u;   // S_ROWS flag: colours may be NaN/Inf -> guarded pack
+
 struct RasterParams
 {
     ViewParams v;
-    const uint32_t *recs;       // kRecWords per triangle
+    const uint32_t *segs;       // kSegWords per segment
+    const unsigned *seg_total;  // device word: segments emitted this frame
+    unsigned seg_capacity;
     const unsigned *tile_count;
     const unsigned *tile_offset;
     const unsigned *pair_list;
@@ -139,8 +150,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // ---------------------------------------------------------------- launchers (one per kernel)
 struct SetupOutputs
 {
-    uint32_t *recs;             // kRecWords per triangle
-    uint2 *rects;               // packed tile rectangle per triangle (x: tx0 | tx1<<16, y: ty0 | ty1<<16), tx0 > tx1 = empty
+    uint32_t *recs;             // optional (b200r_fill_edge_table): kRecWords per triangle
+    uint32_t *segs;             // kSegWords per segment (null: no row walk, records only)
+    uint2 *seg_tiles;           // per segment: x = tile row, y = tx0 | tx1 << 16 (tx0 > tx1: touches no tile)
+    unsigned *seg_total;        // device counter
+    unsigned seg_capacity;
     unsigned *tile_count;
     unsigned long long *counters;   // [0] binned triangles, [1] tile pairs
 };
@@ -148,7 +162,8 @@ struct SetupOutputs
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
 void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
                       unsigned *pair_total, cudaStream_t s);
-void launch_scatter(const uint2 *rects, unsigned ntri, int tiles_x, const unsigned *tile_offset,
+void launch_scatter(const uint2 *seg_tiles, const unsigned *seg_total, unsigned seg_capacity,
+                    unsigned max_segments, int tiles_x, const unsigned *tile_offset,
                     unsigned *tile_fill, unsigned *pair_list, const unsigned *pair_total,
                     unsigned pair_capacity, cudaStream_t s);
 cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s);

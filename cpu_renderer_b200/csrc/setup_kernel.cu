@@ -6,12 +6,19 @@
 // gradients (3947-4111), vertex lighting (4020-4064), and the MergeSort order (2-72) of the
 // <= 3 edges of the triangle ("one triangle = one object").
 //
+// It then walks the triangle's rows ONCE (DrawModel's active-edge maintenance and edge stepping,
+// projekt.cpp:198-303, 542-572, no pixels) and emits self-contained trapezoid segments -- one per
+// (edge pair, tile-row band) -- carrying both edges' running values at the segment's first row
+// and the exact tile columns its spans touch.  The raster kernel never re-derives any of this.
+//
 // Mapping: one thread per triangle, one CTA per 128 triangles.  A warp handles 32 triangles:
 // their 32 x 120 B of vertex attributes are fetched with fully coalesced loads into shared
-// memory and the 32 x 208 B records leave the CTA as coalesced 128-bit stores, so the kernel
-// streams 120 B in / 208 B out per triangle at HBM speed.  (A literal warp-per-triangle
-// mapping would spend 32 lanes on ~3 edges x 2 ends of scalar work; see DESIGN.md.)
+// memory.  Segment slots are handed out with a CTA-wide prefix sum of per-triangle segment
+// counts (warp __shfl_up_sync scans) and ONE global atomicAdd per CTA.  (A literal
+// warp-per-triangle mapping would spend 32 lanes on ~3 edges x 2 ends of scalar work; see
+// DESIGN.md.)
 #include "raster_device.cuh"
+#include "edge_walk.cuh"
 
 namespace b200r {
 
@@ -82,12 +89,16 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     __shared__ __align__(16) float s_col[kSetupThreads*12];
     __shared__ float s_nrm[kSetupThreads*9];
     __shared__ __align__(16) uint32_t s_rec[kSetupThreads*kRecWords];
-    __shared__ unsigned s_binned, s_pairs;
+    __shared__ unsigned s_binned, s_pairs, s_seg_base;
+    __shared__ unsigned s_warp_sum[kSetupThreads/32];
 
     const unsigned base = blockIdx.x*kSetupThreads;
     const unsigned n = min((unsigned)kSetupThreads, m.ntri - base);
     const int t = threadIdx.x;
     if(t == 0) { s_binned = 0; s_pairs = 0; }
+    int my_segs = 0, walk_end = 0, first_row = 0, max_y = 0, nedges = 0, nonfinite = 0;
+    bool have_walk = false;
+    unsigned seg_at = 0;
 
     // coalesced attribute fetch: consecutive lanes read consecutive words
     {
@@ -120,11 +131,9 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         float crz = fsub(fmul(n1.x, n2.y), fmul(n1.y, n2.x));
         float facing = fadd(fadd(fmul(0.0f, crx), fmul(0.0f, cry)), fmul(-1.0f, crz));
 
-        int nedges = 0, first_row = 0, max_y = 0;
         uint32_t emit = 0;                                  // slot of the k-th edge FillEdgeTable emits, 2 bits each
         int slot_of[3] = {-1, -1, -1};
         int mn[3], mx[3];                                   // per edge: index of upper / lower end
-        float minx_s = 0.0f, maxx_s = 0.0f;
 
         if(facing > 0.0f)
         {
@@ -213,42 +222,167 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                 }
                 max_y = (max_row > v.height) ? v.height : max_row;                                   // :187-196
             }
-            minx_s = fminf(prj[0].x, fminf(prj[1].x, prj[2].x));
-            maxx_s = fmaxf(prj[0].x, fmaxf(prj[1].x, prj[2].x));
         }
         rec[R_NEDGES] = (uint32_t)nedges; rec[R_FIRSTROW] = (uint32_t)first_row;
         rec[R_MAXY] = (uint32_t)max_y; rec[R_PRIM] = m.prim_base + base + t;
         rec[R_EDGE0 + 3*kEdgeWords] = emit; rec[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec[R_EDGE0 + 3*kEdgeWords + 2] = 0;
 
-        // Conservative screen rectangle for the binner.  Span ends are edge x values, which lie
-        // on the projected edges, i.e. inside [min vertex x, max vertex x] up to the rounding
-        // drift of the row-by-row accumulation (<= rows * 2^-23 * |x|); columns are clamped the
-        // way the span code clamps them (projekt.cpp:381-400), so fully off-screen spans still
-        // land in column 0 / Width-1.
-        uint2 rect = make_uint2(1u, 0u);                    // tx0 > tx1: empty
-        int ra = max(first_row, v.band_y0), rb = min(max_y, v.band_y1);
-        if(nedges >= 2 && ra < rb)
+        have_walk = (nedges >= 2) && out.segs != nullptr;
+        nonfinite = 0;
+        if(have_walk)
         {
-            float rows = (float)(max_y - first_row);
-            float mag = fmaxf(fmaxf(fabsf(minx_s), fabsf(maxx_s)), 1.0f);
-            float slack = 1.5f + rows*mag*1.1920929e-7f;
-            float x0f = fminf(fmaxf(floorf(minx_s - slack), 0.0f), (float)(v.width - 1));
-            float x1f = fminf(fmaxf(ceilf(maxx_s + slack), 0.0f), (float)(v.width - 1));
-            if(!(x0f <= x1f)) { x0f = 0.0f; x1f = (float)(v.width - 1); }   // NaN: be conservative
-            int tx0 = (int)x0f/v.tile_w, tx1 = (int)x1f/v.tile_w;
-            int ty0 = (ra - v.band_y0)/v.tile_h, ty1 = (rb - 1 - v.band_y0)/v.tile_h;
-            rect = make_uint2((unsigned)tx0 | ((unsigned)tx1 << 16), (unsigned)ty0 | ((unsigned)ty1 << 16));
-            for(int ty = ty0; ty <= ty1; ++ty)
-                for(int tx = tx0; tx <= tx1; ++tx)
-                    atomicAdd(&out.tile_count[ty*v.tiles_x + tx], 1u);
-            atomicAdd(&s_binned, 1u);
-            atomicAdd(&s_pairs, (unsigned)((tx1 - tx0 + 1)*(ty1 - ty0 + 1)));
+            // RoundR32ToU32 (cvtss2si) and cvt.rni.s32.f32 agree only for |c*255| < 2^31.  Colours of
+            // finite scenes stay near [0,1]; a segment whose edge colours could leave that range
+            // (NaN/Inf or absurd input) takes the guarded pack in the raster kernel.  Edges that
+            // never step (YMax <= YMin: inserted and expired in the same row) are never drawn.
+#pragma unroll
+            for(int e = 0; e < 3; ++e)
+            {
+                if(e >= nedges) break;
+                const uint32_t *E = rec + R_EDGE0 + e*kEdgeWords;
+                if((int)E[E_YMAX] <= (int)E[E_YMIN]) continue;
+#pragma unroll
+                for(int i = 0; i < 4; ++i)
+                    if(!(fabsf(__uint_as_float(E[E_C + i])) <= 4.0f) || !(fabsf(__uint_as_float(E[E_DC + i])) <= 4.0f))
+                        nonfinite = 1;
+            }
         }
-        out.rects[m.prim_base + base + t] = rect;
+        // Row range this GPU's band needs: rows above the band are walked (state), rows below not.
+        walk_end = min(max_y, v.band_y1);
+        if(have_walk && !(first_row < walk_end && max_y > v.band_y0)) have_walk = false;
+
+        // Number of segments, without walking: between consecutive list-change rows the set of
+        // active edges {e : YMin <= row < YMax} is constant; a stretch with >= 2 of them yields one
+        // segment per tile-row band it touches.  The walk below splits at exactly the same rows.
+        if(have_walk)
+        {
+            int y = first_row;
+            while(y < walk_end)
+            {
+                int nxt = walk_end, act = 0;
+#pragma unroll
+                for(int e = 0; e < 3; ++e)
+                {
+                    if(e >= nedges) break;
+                    const int ymn = (int)rec[R_EDGE0 + e*kEdgeWords + E_YMIN];
+                    const int ymx = (int)rec[R_EDGE0 + e*kEdgeWords + E_YMAX];
+                    if(ymn <= y && y < ymx) ++act;
+                    if(ymn > y && ymn < nxt) nxt = ymn;
+                    if(ymx > ymn && ymx > y && ymx < nxt) nxt = ymx;
+                }
+                if(act >= 2)
+                {
+                    const int a = max(y, v.band_y0);
+                    if(a < nxt) my_segs += (nxt - 1 - v.band_y0)/v.tile_h - (a - v.band_y0)/v.tile_h + 1;
+                }
+                y = nxt;
+            }
+        }
+    }
+
+    // ---- CTA-wide exclusive scan of segment counts: warp shuffles + one atomicAdd per CTA ----
+    {
+        const unsigned lane = t & 31, warp = t >> 5;
+        unsigned incl = (unsigned)my_segs;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1)
+        {
+            unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+            if(lane >= (unsigned)d) incl += up;
+        }
+        if(lane == 31) s_warp_sum[warp] = incl;
+        __syncthreads();
+        if(t == 0)
+        {
+            unsigned run = 0;
+            for(int w = 0; w < kSetupThreads/32; ++w) { unsigned c = s_warp_sum[w]; s_warp_sum[w] = run; run += c; }
+            s_seg_base = run ? atomicAdd(out.seg_total, run) : 0u;
+        }
+        __syncthreads();
+        seg_at = s_seg_base + s_warp_sum[warp] + (incl - (unsigned)my_segs);
+    }
+
+    if((unsigned)t < n && have_walk && my_segs > 0 && (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity)
+    {
+        const uint32_t *rec = s_rec + t*kRecWords;
+        const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
+        ActiveEdge L, R;
+        L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;
+        L.ymax = 0; L.id = -1; R = L;
+        int nact = 0, next_ev = first_row;
+        bool open = false;
+        unsigned seg = seg_at;
+        int seg_y0 = 0, seg_rows = 0, seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
+        unsigned pairs = 0;
+        const unsigned prim = m.prim_base + base + t;
+
+        auto close_segment = [&]()
+        {
+            if(!open) return;
+            uint32_t *S = out.segs + (size_t)seg*kSegWords;
+            int tx0 = 1, tx1 = 0;
+            if(seg_minx <= seg_maxx) { tx0 = seg_minx/v.tile_w; tx1 = seg_maxx/v.tile_w; }
+            const int trow = (seg_y0 - v.band_y0)/v.tile_h;
+            uint4 h = make_uint4(prim, (unsigned)seg_y0, (unsigned)seg_rows | (nonfinite ? kSegNonFinite : 0u),
+                                 (unsigned)tx0 | ((unsigned)tx1 << 16));
+            *reinterpret_cast<uint4 *>(S) = h;
+            out.seg_tiles[seg] = make_uint2((unsigned)trow, (unsigned)tx0 | ((unsigned)tx1 << 16));
+            for(int tx = tx0; tx <= tx1; ++tx) atomicAdd(&out.tile_count[trow*v.tiles_x + tx], 1u);
+            if(tx0 <= tx1) pairs += (unsigned)(tx1 - tx0 + 1);
+            ++seg; open = false;
+        };
+
+        for(int y = first_row; y < walk_end; ++y)
+        {
+            bool brk = false;
+            if(y == next_ev) { active_list_event(y, rec, nedges, L, R, nact, next_ev); brk = true; }
+            if(nact == 2)
+            {
+                if(y >= v.band_y0)
+                {
+                    if(brk || !open || ((y - v.band_y0) % v.tile_h) == 0)
+                    {
+                        close_segment();
+                        // open: both edges' state at this row goes straight to the segment slot
+                        uint32_t *S = out.segs + (size_t)seg*kSegWords;
+                        float4 *Q = reinterpret_cast<float4 *>(S);
+                        Q[1] = make_float4(L.x, L.z, L.c0, L.c1);  Q[2] = make_float4(L.c2, L.c3, L.dx, L.dz);
+                        Q[3] = make_float4(L.d0, L.d1, L.d2, L.d3);
+                        Q[4] = make_float4(R.x, R.z, R.c0, R.c1);  Q[5] = make_float4(R.c2, R.c3, R.dx, R.dz);
+                        Q[6] = make_float4(R.d0, R.d1, R.d2, R.d3);
+                        open = true; seg_y0 = y; seg_rows = 0; seg_minx = 0x7fffffff; seg_maxx = (int)0x80000000;
+                    }
+                    // the columns this row's span paints: same clamps and roundings as the span
+                    // code (projekt.cpp:381-406), so the binner's tile columns are exact
+                    float leftx = L.x;
+                    if(leftx < 0.0f) leftx = 0.0f; else if(leftx >= wf) leftx = wf_m1;
+                    float rightx = R.x;
+                    if(rightx < 0.0f) rightx = 0.0f; else if(rightx >= wf) rightx = wf_m1;
+                    const int minx = round_s32(leftx), maxx = round_s32(rightx);
+                    if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
+                    ++seg_rows;
+                }
+                step_edge(L); step_edge(R);                                   // :542-549
+                if(L.x > R.x) { ActiveEdge tmp = L; L = R; R = tmp; }          // :562-572
+            }
+            else
+            {
+                close_segment();
+            }
+        }
+        close_segment();
+        // slots promised by the count but not produced (cannot happen for finite input) are blanked
+        for(; seg < seg_at + (unsigned)my_segs; ++seg)
+        {
+            *reinterpret_cast<uint4 *>(out.segs + (size_t)seg*kSegWords) = make_uint4(prim, 0u, 0u, 1u);
+            out.seg_tiles[seg] = make_uint2(0u, 1u);
+        }
+        if(pairs) { atomicAdd(&s_binned, 1u); atomicAdd(&s_pairs, pairs); }
     }
     __syncthreads();
 
-    // coalesced 128-bit record store
+    // coalesced 128-bit record store (only b200r_fill_edge_table asks for the records)
+    if(out.recs)
     {
         const float4 *src = reinterpret_cast<const float4 *>(s_rec);
         float4 *dst = reinterpret_cast<float4 *>(out.recs) + (size_t)(m.prim_base + base)*kRecVec4;

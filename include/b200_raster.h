@@ -140,8 +140,8 @@ const char *b200r_last_error(const b200r_context *Context);
 int b200r_set_stream(b200r_context *Context, void *CudaStream);
 int b200r_sync(b200r_context *Context);
 
-/* Screen tile staged in shared memory by the raster kernel: 64x32 (default), 32x32, 128x16
- * or 64x16 pixels. */
+/* Screen tile staged in shared memory by the raster kernel: 64x32 (default), 32x32, 128x16,
+ * 64x16 or 128x32 pixels. */
 int b200r_set_tile(b200r_context *Context, int TileWidth, int TileHeight);
 
 /* ------------------------------------------------------------------------------------------
@@ -201,8 +201,9 @@ int b200r_clear_device(b200r_context *Context, const b200r_device_target *Target
 typedef struct b200r_frame_stats
 {
     uint64_t Triangles;        /* submitted in the last render call                             */
-    uint64_t Binned;           /* triangles with >= 2 edge records that touch the band          */
-    uint64_t TilePairs;        /* (triangle, tile) pairs produced by the binner                 */
+    uint64_t Binned;           /* triangles that produced at least one (segment, tile) pair     */
+    uint64_t Segments;         /* trapezoid segments emitted by the set-up kernel               */
+    uint64_t TilePairs;        /* (segment, tile) pairs produced by the binner                  */
     uint64_t Tiles;            /* screen tiles of the band                                      */
     uint64_t KernelLaunches;   /* kernels launched by this context since creation               */
     uint64_t Reruns;           /* frames re-issued because the pair list had to grow            */
@@ -210,6 +211,14 @@ typedef struct b200r_frame_stats
 
 /* Valid after b200r_sync (or any blocking call). */
 int b200r_get_stats(b200r_context *Context, b200r_frame_stats *Stats);
+
+/* Per-kernel timing of the device path with CUDA events recorded on the launching stream
+ * (the reference has no timers at all).  While enabled, every frame
+ * records an event between stages; b200r_get_stage_ms syncs and returns the durations of the
+ * last frame: [0] setup_kernel, [1] tile_scan_kernel, [2] scatter_kernel, [3] raster_kernel. */
+#define B200R_STAGES 4
+int b200r_set_profiling(b200r_context *Context, int Enable);
+int b200r_get_stage_ms(b200r_context *Context, float StageMs[B200R_STAGES]);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def compare(renderer, scene, splits=None, tile=None):
     return dict(zdiff=zdiff, covdiff=covdiff, cdiff=cdiff, maxlsb=int(ch.max()), stats=o["stats"])
 
 
-@pytest.mark.parametrize("tile", [(64, 32), (32, 32), (128, 16), (64, 16)])
+@pytest.mark.parametrize("tile", [(64, 32), (32, 32), (128, 16), (64, 16), (128, 32)])
 def test_small_triangles_1080p(renderer, tile):
     s = sc.triangle_soup("small", 0xB2000002, 100_000, 1920, 1080, 1.5, 4.0)
     r = compare(renderer, s, tile=tile)
