@@ -44,7 +44,7 @@ struct FrameWords
     unsigned pair_total;
     unsigned work_counter;
     unsigned seg_total;
-    unsigned pad;
+    unsigned span_total;
     unsigned long long counters[2];     // binned triangles, tile pairs
 };
 
@@ -60,7 +60,7 @@ struct b200r_context
     std::string error;
     int tile_w = 64, tile_h = 32;
 
-    DeviceBuffer recs, segs, seg_tiles, tiles, pairs, words;
+    DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
 
     // the last issued frame, kept so it can be issued again after the pair list grew
@@ -141,13 +141,16 @@ static int issue_frame(b200r_context *c)
     CU(cudaMemsetAsync(tile_count, 0, (size_t)ntiles*2*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
 
-    const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/(kSegWords*sizeof(uint32_t)), 0xffffffffu);
+    const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
+    const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(kSpanWords*sizeof(uint32_t)), 0xffffffffu);
     SetupOutputs so;
     so.recs = nullptr;
-    so.segs = (uint32_t *)c->segs.ptr;
-    so.seg_tiles = (uint2 *)c->seg_tiles.ptr;
+    so.spans = (uint32_t *)c->spans.ptr;
+    so.segs = (SegInfo *)c->segs.ptr;
     so.seg_total = &words->seg_total;
+    so.span_total = &words->span_total;
     so.seg_capacity = seg_cap;
+    so.span_capacity = span_cap;
     so.tile_count = tile_count;
     so.counters = words->counters;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[0], c->stream));
@@ -164,16 +167,23 @@ static int issue_frame(b200r_context *c)
     CU(cudaEventRecord(c->total_ready, c->stream));
 
     const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
-    launch_scatter(so.seg_tiles, &words->seg_total, seg_cap, seg_cap, v.tiles_x, tile_offset, tile_fill,
-                   (unsigned *)c->pairs.ptr, &words->pair_total, pair_cap, c->stream);
+    ScatterParams sp;
+    sp.segs = so.segs;
+    sp.seg_total = &words->seg_total; sp.span_total = &words->span_total; sp.pair_total = &words->pair_total;
+    sp.seg_capacity = seg_cap; sp.span_capacity = span_cap; sp.pair_capacity = pair_cap;
+    sp.tiles_x = v.tiles_x;
+    sp.tile_offset = tile_offset; sp.tile_fill = tile_fill; sp.pair_list = (unsigned *)c->pairs.ptr;
+    launch_scatter(sp, c->stream);
     if(c->total_tris) c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[3], c->stream));
 
     RasterParams rp;
     rp.v = v;
-    rp.segs = so.segs;
+    rp.spans = so.spans;
     rp.seg_total = &words->seg_total;
+    rp.span_total = &words->span_total;
     rp.seg_capacity = seg_cap;
+    rp.span_capacity = span_cap;
     rp.tile_count = tile_count;
     rp.tile_offset = tile_offset;
     rp.pair_list = (const unsigned *)c->pairs.ptr;
@@ -204,24 +214,24 @@ static int settle_pending(b200r_context *c)
     {
         CU(cudaEventSynchronize(c->total_ready));
         const unsigned total = c->h_words->pair_total;
-        const unsigned nseg = c->h_words->seg_total;
+        const unsigned nseg = c->h_words->seg_total, nspan = c->h_words->span_total;
         const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
-        const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/(kSegWords*sizeof(uint32_t)), 0xffffffffu);
+        const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
+        const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(kSpanWords*sizeof(uint32_t)), 0xffffffffu);
         c->stats.Binned = c->h_words->counters[0];
         c->stats.TilePairs = c->h_words->counters[1];
         c->stats.Segments = nseg;
+        c->stats.Spans = nspan;
         c->pending = false;
-        if(total > pair_cap || nseg > seg_cap)
+        if(total > pair_cap || nseg > seg_cap || nspan > span_cap)
         {
             // the scatter and raster kernels of that frame saw the same totals and did nothing
             CU(cudaStreamSynchronize(c->stream));
-            if(nseg > seg_cap)
-            {
-                CU(c->segs.reserve((size_t)nseg*kSegWords*sizeof(uint32_t)));
-                CU(c->seg_tiles.reserve((size_t)nseg*sizeof(uint2)));
-            }
-            // with the segment list truncated the pair total was an under-count: leave headroom
-            CU(c->pairs.reserve((size_t)std::max<uint64_t>(total, nseg > seg_cap ? (uint64_t)nseg*2 : 0)*sizeof(unsigned)));
+            const bool truncated = nseg > seg_cap || nspan > span_cap;
+            if(nseg > seg_cap) CU(c->segs.reserve((size_t)nseg*sizeof(SegInfo)));
+            if(nspan > span_cap) CU(c->spans.reserve((size_t)nspan*kSpanWords*sizeof(uint32_t)));
+            // with truncated lists the pair total was an under-count: leave headroom
+            CU(c->pairs.reserve((size_t)std::max<uint64_t>(total, truncated ? (uint64_t)nspan*2 : 0)*sizeof(unsigned)));
             c->stats.Reruns += 1;
             int rc = issue_frame(c);
             if(rc != B200R_OK) return rc;
@@ -267,7 +277,7 @@ void b200r_destroy(b200r_context *c)
     if(!c) return;
     cudaSetDevice(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
-    c->recs.release(); c->segs.release(); c->seg_tiles.release(); c->tiles.release(); c->pairs.release(); c->words.release();
+    c->recs.release(); c->segs.release(); c->spans.release(); c->tiles.release(); c->pairs.release(); c->words.release();
     c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_color.release(); c->d_depth.release();
     for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
     if(c->h_words) cudaFreeHost(c->h_words);
@@ -344,16 +354,12 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     if(total > 0x7fffffffull) return fail(c, B200R_E_UNSUPPORTED, "more than 2^31-1 triangles per call");
 
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
-    // first guess: ~2.5 segments and ~3 tile pairs per triangle; both lists grow on demand
-    if(c->segs.bytes == 0)
-    {
-        const uint64_t guess = std::max<uint64_t>(total*5/2, 1u << 16);
-        CU(c->segs.reserve((size_t)guess*kSegWords*sizeof(uint32_t)));
-        CU(c->seg_tiles.reserve((size_t)guess*sizeof(uint2)));
-    }
+    // first guesses (2.5 segments, 6 spans, 8 queue entries per triangle); all lists grow on demand
+    if(c->segs.bytes == 0) CU(c->segs.reserve((size_t)std::max<uint64_t>(total*5/2, 1u << 16)*sizeof(SegInfo)));
+    if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*kSpanWords*sizeof(uint32_t)));
     CU(c->tiles.reserve((size_t)ntiles*3*sizeof(unsigned)));
     if(c->pairs.bytes == 0)
-        CU(c->pairs.reserve((size_t)std::max<uint64_t>(total*3, 1u << 16)*sizeof(unsigned)));
+        CU(c->pairs.reserve((size_t)std::max<uint64_t>(total*8, 1u << 16)*sizeof(unsigned)));
 
     c->view = v;
     c->meshes.swap(ms);
@@ -542,8 +548,9 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     CU(cudaMemsetAsync(tile_count, 0, 3*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
     SetupOutputs so;
-    so.recs = (uint32_t *)c->recs.ptr; so.segs = nullptr; so.seg_tiles = nullptr;
-    so.seg_total = &words->seg_total; so.seg_capacity = 0;
+    so.recs = (uint32_t *)c->recs.ptr; so.spans = nullptr; so.segs = nullptr;
+    so.seg_total = &words->seg_total; so.span_total = &words->span_total;
+    so.seg_capacity = 0; so.span_capacity = 0;
     so.tile_count = tile_count; so.counters = words->counters;
     MeshParams mp;
     mp.pos = meshes[0].Positions; mp.col = meshes[0].Colors; mp.nrm = meshes[0].Normals;

@@ -57,26 +57,23 @@ tile_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offs
     for(unsigned i = lo; i < hi; ++i) { offset[i] = run; run += count[i]; }
 }
 
-// One thread per segment; lanes whose segments fall into the same tile contend on that tile's
-// cursor, which the L2 atomic unit serialises.
+// One thread per segment and tile column: reserve nrows consecutive slots of that tile's list
+// with one atomic and fill them with the segment's span indices, so the raster kernel's queue is
+// a flat list of spans while the number of atomics stays per segment.
 __global__ void __launch_bounds__(256)
-scatter_kernel(const uint2 *__restrict__ seg_tiles, const unsigned *__restrict__ seg_total,
-               unsigned seg_capacity, int tiles_x,
-               const unsigned *__restrict__ tile_offset, unsigned *__restrict__ tile_fill,
-               unsigned *__restrict__ pair_list, const unsigned *__restrict__ pair_total,
-               unsigned pair_capacity)
+scatter_kernel(const ScatterParams p)
 {
-    const unsigned nseg = *seg_total;
-    if(nseg > seg_capacity || *pair_total > pair_capacity) return;   // host grows and re-issues
+    const unsigned nseg = *p.seg_total;
+    if(nseg > p.seg_capacity || *p.span_total > p.span_capacity || *p.pair_total > p.pair_capacity) return;
     for(unsigned seg = blockIdx.x*blockDim.x + threadIdx.x; seg < nseg; seg += gridDim.x*blockDim.x)
     {
-        const uint2 r = seg_tiles[seg];
-        const int tx0 = r.y & 0xffff, tx1 = r.y >> 16;
+        const SegInfo si = p.segs[seg];
+        const int tx0 = si.tx & 0xffff, tx1 = si.tx >> 16;
         for(int tx = tx0; tx <= tx1; ++tx)
         {
-            const unsigned tile = r.x*(unsigned)tiles_x + (unsigned)tx;
-            const unsigned slot = atomicAdd(&tile_fill[tile], 1u);
-            pair_list[tile_offset[tile] + slot] = seg;
+            const unsigned tile = si.tile_row*(unsigned)p.tiles_x + (unsigned)tx;
+            const unsigned slot = p.tile_offset[tile] + atomicAdd(&p.tile_fill[tile], si.nrows);
+            for(unsigned r = 0; r < si.nrows; ++r) p.pair_list[slot + r] = si.span_base + r;
         }
     }
 }
@@ -87,17 +84,13 @@ void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigne
     tile_scan_kernel<<<1, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, pair_total);
 }
 
-void launch_scatter(const uint2 *seg_tiles, const unsigned *seg_total, unsigned seg_capacity,
-                    unsigned max_segments, int tiles_x, const unsigned *tile_offset,
-                    unsigned *tile_fill, unsigned *pair_list, const unsigned *pair_total,
-                    unsigned pair_capacity, cudaStream_t s)
+void launch_scatter(const ScatterParams &p, cudaStream_t s)
 {
-    if(max_segments == 0) return;
+    if(p.seg_capacity == 0) return;
     // the segment count lives on the device: size the grid for the capacity, grid-stride inside
-    unsigned blocks = (max_segments + 255)/256;
+    unsigned blocks = (p.seg_capacity + 255)/256;
     if(blocks > 148*16) blocks = 148*16;
-    scatter_kernel<<<blocks, 256, 0, s>>>(seg_tiles, seg_total, seg_capacity, tiles_x, tile_offset, tile_fill,
-                                          pair_list, pair_total, pair_capacity);
+    scatter_kernel<<<blocks, 256, 0, s>>>(p);
 }
 
 } // namespace b200r

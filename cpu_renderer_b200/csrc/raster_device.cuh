@@ -50,21 +50,31 @@ constexpr int kRecVec4 = kRecWords/4;
 enum { E_YMIN = 0, E_YMAX = 1, E_X = 2, E_DX = 3, E_Z = 4, E_DZ = 5, E_C = 6, E_DC = 10, E_LEFT = 14 };
 enum { R_NEDGES = 0, R_FIRSTROW = 1, R_MAXY = 2, R_PRIM = 3, R_EDGE0 = 4 };
 
-// Trapezoid segment: the rows of one triangle that (a) share one pair of active edges and
-// (b) lie in one tile-row band, with both edges' running values at the segment's first row.
-// Written by the set-up kernel (which walks each triangle's rows once), consumed by the raster
-// kernel, which therefore needs no active-list logic and never replays rows above its tile.
-constexpr int kSegWords = 28;       // 112 bytes = 7 float4
-constexpr int kSegVec4 = kSegWords/4;
-enum { S_PRIM = 0, S_Y0 = 1, S_ROWS = 2, S_TX = 3, S_L = 4, S_R = 16 };   // L/R: x z c[4] dx dz dc[4]
-constexpr unsigned kSegNonFinite = 0x10000u;   // S_ROWS flag: colours may be NaN/Inf -> guarded pack
+// Span record: one row of one triangle, fully set up (projekt.cpp:306-412 done once, in the
+// set-up kernel): the inclusive column range, the values at the first column and the per-pixel
+// increments.  The raster kernel only replays the per-pixel adds and depth-tests.
+constexpr int kSpanWords = 16;      // 64 bytes = 4 float4
+constexpr int kSpanVec4 = kSpanWords/4;
+enum { P_PRIM = 0, P_Y = 1, P_MINX = 2, P_MAXX = 3, P_Z = 4, P_C = 5, P_ZI = 9, P_CI = 10, P_FLAGS = 14 };
+constexpr unsigned kSpanNonFinite = 1u;   // colours may be NaN/Inf/huge -> guarded pack
+
+// Segment: the consecutive spans of one triangle that share one pair of active edges and lie in
+// one tile-row band; the unit the binner scatters (its spans are contiguous in the span array).
+struct SegInfo
+{
+    unsigned tile_row;          // band-relative tile row
+    unsigned tx;                // tx0 | tx1 << 16 (tx0 > tx1: touches no tile)
+    unsigned span_base;         // index of its first span record
+    unsigned nrows;             // number of span records
+};
 
 struct RasterParams
 {
     ViewParams v;
-    const uint32_t *segs;       // kSegWords per segment
-    const unsigned *seg_total;  // device word: segments emitted this frame
-    unsigned seg_capacity;
+    const uint32_t *spans;      // kSpanWords per span
+    const unsigned *seg_total;  // device words: segments / spans emitted this frame
+    const unsigned *span_total;
+    unsigned seg_capacity, span_capacity;
     const unsigned *tile_count;
     const unsigned *tile_offset;
     const unsigned *pair_list;
@@ -151,10 +161,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 struct SetupOutputs
 {
     uint32_t *recs;             // optional (b200r_fill_edge_table): kRecWords per triangle
-    uint32_t *segs;             // kSegWords per segment (null: no row walk, records only)
-    uint2 *seg_tiles;           // per segment: x = tile row, y = tx0 | tx1 << 16 (tx0 > tx1: touches no tile)
-    unsigned *seg_total;        // device counter
-    unsigned seg_capacity;
+    uint32_t *spans;            // kSpanWords per span (null: no row walk, records only)
+    SegInfo *segs;
+    unsigned *seg_total;        // device counters
+    unsigned *span_total;
+    unsigned seg_capacity, span_capacity;
     unsigned *tile_count;
     unsigned long long *counters;   // [0] binned triangles, [1] tile pairs
 };
@@ -162,10 +173,17 @@ struct SetupOutputs
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
 void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
                       unsigned *pair_total, cudaStream_t s);
-void launch_scatter(const uint2 *seg_tiles, const unsigned *seg_total, unsigned seg_capacity,
-                    unsigned max_segments, int tiles_x, const unsigned *tile_offset,
-                    unsigned *tile_fill, unsigned *pair_list, const unsigned *pair_total,
-                    unsigned pair_capacity, cudaStream_t s);
+struct ScatterParams
+{
+    const SegInfo *segs;
+    const unsigned *seg_total, *span_total, *pair_total;
+    unsigned seg_capacity, span_capacity, pair_capacity;
+    int tiles_x;
+    const unsigned *tile_offset;
+    unsigned *tile_fill;
+    unsigned *pair_list;        // per tile: span indices
+};
+void launch_scatter(const ScatterParams &p, cudaStream_t s);
 cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s);
 void launch_clear(uint32_t *color, int color_pitch_words, float *depth, int depth_stride,
                   int width, int rows, uint32_t cval, float dval, cudaStream_t s);

@@ -1,47 +1,61 @@
-// Tile raster kernel (sm_100a): coverage, interpolation, depth test and Gouraud shading.
+// Tile raster kernel (sm_100a): per-pixel coverage, interpolation, depth test and colour write.
 //
-// Restates the per-row body of DrawModel's scalar Gouraud path:
-//   span set-up                           projekt.cpp:306-412
-//   pixel loop, depth test, ARGB pack     projekt.cpp:423-425, 510-538
-//   edge step and crossing exchange       projekt.cpp:542-572
-// (the active-edge insert/expire of :202-296 has already been resolved by the set-up kernel,
-// which hands this kernel trapezoid segments with both edges' running values).
+// Restates DrawModel's Gouraud pixel loop (projekt.cpp:423-425, 510-538) on the span records
+// the set-up kernel produced (span set-up, :306-412, is already done there, once per row).
 //
 // "The reference's own arithmetic" is a chain of rounded binary32 additions: the value at pixel
 // k of a span is k sequential adds from the span's left end.  There is no
-// closed form, so the unit of parallel work is the segment, not the pixel:
+// closed form, so the unit of parallel work is the SPAN, not the pixel:
 //
 //   * a CTA owns one screen tile at a time, staged in shared memory as ONE 128-bit word per
 //     pixel: { depth bits, owner (submission index), ARGB colour, 0 }.  Tile rows enter and
 //     leave with TMA bulk copies (cp.async.bulk + mbarrier) and 128-bit shared accesses;
-//   * the tile's bin is consumed 32 segments at a time by whichever warp is free (shared-memory
-//     ticket counter); each LANE walks one segment: per row the reference's span set-up, then the
-//     span pixel by pixel.  Pixels left of the tile are replayed in registers only (adds, no
-//     memory); pixels inside the tile are depth-tested against shared memory;
-//   * different lanes and warps hold different triangles that may hit the same pixel, so a
-//     pixel is updated with one 128-bit compare-and-swap (ATOMS.CAS.128) under the rule
-//         z > zold || (z == zold && prim < primold)
-//     which is the reference's strict '>' with first-submitted-wins (projekt.cpp:525) made
-//     order independent; depth, owner and colour change together, so no ordering between lanes
-//     or warps is needed and the pixel loop contains no barrier.
+//   * the tile's queue is a flat list of spans.  Lanes are persistent: a lane that runs out of
+//     pixels waits until kRefill lanes of its warp are idle, then the idle lanes take new spans
+//     with ONE warp-aggregated ticket (ballot + popc + shuffle) on a shared-memory counter;
+//   * lanes with pixels advance in lock step, one pixel per iteration; pixels left of the tile
+//     are the same iteration with the memory part predicated off (adds only, in registers);
+//   * a pixel whose depth test may pass parks its lane; when kPend lanes are parked they run the
+//     update together: pack ARGB (:520-523) and one 128-bit compare-and-swap (ATOMS.CAS.128)
+//     under the rule   z > zold || (z == zold && prim < primold)
+//     which is the reference's strict '>' with first-submitted-wins (:525) made order
+//     independent.  Depth, owner and colour change together, so no ordering between lanes or
+//     warps is needed and the pixel loop contains no barrier.
 #include "raster_device.cuh"
 
 namespace b200r {
 
 struct __align__(16) Pixel { unsigned z, prim, color, pad; };
 
-__device__ __forceinline__ Pixel lds_pixel(const Pixel *p)
+// shared-state-space (32-bit) addressing: no generic-address conversion in the pixel loop
+__device__ __forceinline__ Pixel lds_pixel(uint32_t addr)
 {
     Pixel r;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.z), "=r"(r.prim), "=r"(r.color), "=r"(r.pad) : "r"(smem_addr(p)) : "memory");
+                 : "=r"(r.z), "=r"(r.prim), "=r"(r.color), "=r"(r.pad) : "r"(addr) : "memory");
     return r;
 }
-__device__ __forceinline__ float lds_depth(const Pixel *p)
+__device__ __forceinline__ float lds_depth(uint32_t addr)
 {
     float z;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z) : "r"(smem_addr(p)) : "memory");
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z) : "r"(addr) : "memory");
     return z;
+}
+// 128-bit compare-and-swap on a shared-memory pixel (SASS: ATOMS.CAS.128)
+__device__ __forceinline__ Pixel cas_pixel(uint32_t addr, const Pixel &cmp, const Pixel &val)
+{
+    unsigned long long clo = ((unsigned long long)cmp.prim << 32) | cmp.z, chi = ((unsigned long long)cmp.pad << 32) | cmp.color;
+    unsigned long long vlo = ((unsigned long long)val.prim << 32) | val.z, vhi = ((unsigned long long)val.pad << 32) | val.color;
+    unsigned long long rlo, rhi;
+    asm volatile("{\n\t.reg .b128 c, s, r;\n\t"
+                 "mov.b128 c, {%3, %4};\n\t"
+                 "mov.b128 s, {%5, %6};\n\t"
+                 "atom.shared.cas.b128 r, [%2], c, s;\n\t"
+                 "mov.b128 {%0, %1}, r;\n\t}"
+                 : "=l"(rlo), "=l"(rhi) : "r"(addr), "l"(clo), "l"(chi), "l"(vlo), "l"(vhi) : "memory");
+    Pixel r;
+    r.z = (unsigned)rlo; r.prim = (unsigned)(rlo >> 32); r.color = (unsigned)rhi; r.pad = (unsigned)(rhi >> 32);
+    return r;
 }
 
 // RoundR32ToU32(c*255) per channel, A R G B from a r g b (projekt.cpp:520-523); no clamp.
@@ -74,7 +88,7 @@ raster_kernel(const RasterParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned s_tile, s_ticket;
 
-    if(*p.seg_total > p.seg_capacity || *p.pair_total > p.pair_capacity) return;   // host re-issues
+    if(*p.seg_total > p.seg_capacity || *p.span_total > p.span_capacity || *p.pair_total > p.pair_capacity) return;   // host re-issues
 
     const int tid = threadIdx.x, lane = tid & 31;
     Pixel *tile = reinterpret_cast<Pixel *>(smem_raw);
@@ -87,8 +101,6 @@ raster_kernel(const RasterParams p)
     __syncthreads();
     uint32_t phase = 0;
 
-    const float wf = (float)p.v.width;
-    const float wf_m1 = fsub(wf, 1.0f);
     const int band_rows = p.v.band_y1 - p.v.band_y0;
 
     while(true)
@@ -148,100 +160,105 @@ raster_kernel(const RasterParams p)
         }
         __syncthreads();
 
-        // ---------------- rasterise the bin, 32 segments per ticket ----------------------------
-        while(true)
+        // ---------------- rasterise the tile's span queue: persistent lanes --------------------
         {
-            unsigned b = 0;
-            if(lane == 0) b = atomicAdd(&s_ticket, 32u);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if(b >= cnt) break;
-            const bool have = (b + lane) < cnt;
-            const unsigned seg = have ? __ldg(p.pair_list + off + b + lane) : 0u;
-            const float4 *S = reinterpret_cast<const float4 *>(p.segs + (size_t)seg*kSegWords);
-            const uint4 h = __ldg(reinterpret_cast<const uint4 *>(S));
-            const float4 q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
-            const float4 q4 = __ldg(S + 4), q5 = __ldg(S + 5), q6 = __ldg(S + 6);
-            const int prim = (int)h.x;
-            const int y0 = (int)h.y;
-            const int nrows = have ? (int)(h.z & 0xffffu) : 0;
-            const bool guarded = (h.z & kSegNonFinite) != 0;
-            // L / R: running XMin, ZMin, MinColor and their per-row gradients
-            float lx = q1.x, lz = q1.y, l0 = q1.z, l1 = q1.w, l2 = q2.x, l3 = q2.y;
-            float ldx = q2.z, ldz = q2.w, ld0 = q3.x, ld1 = q3.y, ld2 = q3.z, ld3 = q3.w;
-            float rx = q4.x, rz = q4.y, r0 = q4.z, r1 = q4.w, r2 = q5.x, r3 = q5.y;
-            float rdx = q5.z, rdz = q5.w, rd0 = q6.x, rd1 = q6.y, rd2 = q6.z, rd3 = q6.w;
-
-            for(int k = 0; k < nrows; ++k)
+            constexpr int kRefill = 8;                     // idle lanes that trigger a refill
+            constexpr int kPend = 8;                       // parked lanes that trigger the update path
+            constexpr unsigned FULL = 0xffffffffu;
+            const uint32_t tile_addr = smem_addr(tile);
+            const int xlast = x0 + cols - 1;
+            float z = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, zi = 0, i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+            int prim = 0, n_left = 0, x = 0;
+            uint32_t rowaddr = tile_addr;                  // shared address of column 0 of the span's row
+            bool guarded = false, exhausted = false, pending = false;
+            while(true)
             {
-                const int y = y0 + k;
-                // ---- span set-up, projekt.cpp:306-412 ----
-                const float xdiff = roundf(fsub(rx, lx));                     // :311-312
-                float zi = 0.0f, i0 = 0.0f, i1 = 0.0f, i2 = 0.0f, i3 = 0.0f;
-                if(xdiff != 0.0f)                                             // :333-363
+                const bool need = !pending && n_left == 0 && !exhausted;
+                const unsigned need_mask = __ballot_sync(FULL, need);
+                const unsigned busy_mask = __ballot_sync(FULL, n_left > 0 && !pending);
+                const unsigned pend_mask = __ballot_sync(FULL, pending);
+                if((need_mask | busy_mask | pend_mask) == 0) break;
+
+                if(pend_mask && (busy_mask == 0 || __popc(pend_mask) >= kPend))
                 {
-                    i0 = fdiv(fsub(r0, l0), xdiff); i1 = fdiv(fsub(r1, l1), xdiff);
-                    i2 = fdiv(fsub(r2, l2), xdiff); i3 = fdiv(fsub(r3, l3), xdiff);
-                    zi = fdiv(fsub(rz, lz), xdiff);
-                }
-                float z = lz, c0 = l0, c1 = l1, c2 = l2, c3 = l3;             // :375-379
-                float xoff = 0.0f, leftx = lx;                                // :381-390
-                if(leftx < 0.0f) { xoff = -leftx; leftx = 0.0f; }
-                else if(leftx >= wf) { leftx = wf_m1; }
-                float rightx = rx;                                            // :392-400
-                if(rightx < 0.0f) { rightx = 0.0f; }
-                else if(rightx >= wf) { rightx = wf_m1; }
-                const int minx = round_s32(leftx), maxx = round_s32(rightx);  // :402-406
-                z = fadd(z, fmul(xoff, zi));                                  // :408
-                c0 = fadd(c0, fmul(xoff, i0)); c1 = fadd(c1, fmul(xoff, i1)); // :412
-                c2 = fadd(c2, fmul(xoff, i2)); c3 = fadd(c3, fmul(xoff, i3));
-                const int xe = min(maxx, x0 + cols - 1);
-                if(minx <= xe && maxx >= x0)
-                {
-                    // pixels left of the tile: the reference's per-pixel adds (:534-535), registers only
-                    for(int s = minx; s < x0; ++s)
+                    // ---- depth-test passes, projekt.cpp:520-529, for all parked lanes at once ----
+                    if(pending)
                     {
-                        c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);
-                        z = fadd(z, zi);
-                    }
-                    // ---- pixel loop, projekt.cpp:423-425, 510-538 ----
-                    Pixel *row = tile + (y - ys0)*TW - x0;
-                    for(int x = max(minx, x0); x <= xe; ++x)
-                    {
-                        const float zo = lds_depth(row + x);
-                        if(z >= zo)
+                        const uint32_t pa = rowaddr + (uint32_t)x*16u;
+                        Pixel mine;
+                        mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
+                        mine.color = pack_argb(c0, c1, c2, c3, guarded); mine.pad = 0;
+                        Pixel old = lds_pixel(pa);
+                        while(true)
                         {
-                            Pixel mine;
-                            mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
-                            mine.color = pack_argb(c0, c1, c2, c3, guarded); mine.pad = 0;
-                            Pixel old = lds_pixel(row + x);
-                            while(true)
-                            {
-                                const float oz = __uint_as_float(old.z);
-                                const int op = (int)old.prim;
-                                if(!(z > oz || (z == oz && prim < op))) break;        // :525 + tie rule
-                                const Pixel prev = atomicCAS(row + x, old, mine);
-                                if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
-                                old = prev;
-                            }
+                            const float oz = __uint_as_float(old.z);
+                            const int op = (int)old.prim;
+                            if(!(z > oz || (z == oz && prim < op))) break;            // :525 + tie rule
+                            const Pixel prev = cas_pixel(pa, old, mine);
+                            if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
+                            old = prev;
                         }
                         c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
                         z = fadd(z, zi);                                                              // :535
+                        ++x; --n_left;
+                        pending = false;
                     }
+                    continue;
                 }
-                // ---- one row down both edges, projekt.cpp:542-549; exchange if crossed, :562-572 ----
-                lx = fadd(lx, ldx); lz = fadd(lz, ldz);
-                l0 = fadd(l0, ld0); l1 = fadd(l1, ld1); l2 = fadd(l2, ld2); l3 = fadd(l3, ld3);
-                rx = fadd(rx, rdx); rz = fadd(rz, rdz);
-                r0 = fadd(r0, rd0); r1 = fadd(r1, rd1); r2 = fadd(r2, rd2); r3 = fadd(r3, rd3);
-                if(lx > rx)
+
+                if(need_mask && (busy_mask == 0 || __popc(need_mask) >= kRefill))
                 {
-                    float t;
-                    t = lx; lx = rx; rx = t;       t = lz; lz = rz; rz = t;
-                    t = l0; l0 = r0; r0 = t;       t = l1; l1 = r1; r1 = t;
-                    t = l2; l2 = r2; r2 = t;       t = l3; l3 = r3; r3 = t;
-                    t = ldx; ldx = rdx; rdx = t;   t = ldz; ldz = rdz; rdz = t;
-                    t = ld0; ld0 = rd0; rd0 = t;   t = ld1; ld1 = rd1; rd1 = t;
-                    t = ld2; ld2 = rd2; rd2 = t;   t = ld3; ld3 = rd3; rd3 = t;
+                    // ---- idle lanes take the next spans of the queue: one ticket per warp ----
+                    const int leader = __ffs(need_mask) - 1;
+                    unsigned base = 0;
+                    if(lane == leader) base = atomicAdd(&s_ticket, (unsigned)__popc(need_mask));
+                    base = __shfl_sync(FULL, base, leader);
+                    if(need)
+                    {
+                        const unsigned idx = base + (unsigned)__popc(need_mask & ((1u << lane) - 1u));
+                        if(idx < cnt)
+                        {
+                            const unsigned sp = __ldg(p.pair_list + off + idx);
+                            const float4 *S = reinterpret_cast<const float4 *>(p.spans + (size_t)sp*kSpanWords);
+                            const float4 q0 = __ldg(S), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
+                            prim = __float_as_int(q0.x);
+                            const int y = __float_as_int(q0.y);
+                            const int minx = __float_as_int(q0.z), maxx = __float_as_int(q0.w);
+                            z = q1.x; c0 = q1.y; c1 = q1.z; c2 = q1.w;
+                            c3 = q2.x; zi = q2.y; i0 = q2.z; i1 = q2.w;
+                            i2 = q3.x; i3 = q3.y;
+                            guarded = (__float_as_uint(q3.z) & kSpanNonFinite) != 0;
+                            const int xe = min(maxx, xlast);
+                            x = minx;
+                            n_left = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
+                            rowaddr = tile_addr + (uint32_t)(((y - ys0)*TW - x0)*16);
+                        }
+                        else
+                        {
+                            exhausted = true;
+                        }
+                    }
+                    continue;
+                }
+
+                // ---- pixel steps, projekt.cpp:423-425, 525, 534-535 (a few per ballot round) ----
+#pragma unroll
+                for(int u = 0; u < 4; ++u)
+                {
+                    if(n_left > 0 && !pending)
+                    {
+                        if(x >= x0)
+                        {
+                            const float zo = lds_depth(rowaddr + (uint32_t)x*16u);
+                            pending = (z >= zo);                              // may pass: park
+                        }
+                        if(!pending)
+                        {
+                            c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
+                            z = fadd(z, zi);                                                              // :535
+                            ++x; --n_left;
+                        }
+                    }
                 }
             }
         }

@@ -6,10 +6,11 @@
 // gradients (3947-4111), vertex lighting (4020-4064), and the MergeSort order (2-72) of the
 // <= 3 edges of the triangle ("one triangle = one object").
 //
-// It then walks the triangle's rows ONCE (DrawModel's active-edge maintenance and edge stepping,
-// projekt.cpp:198-303, 542-572, no pixels) and emits self-contained trapezoid segments -- one per
-// (edge pair, tile-row band) -- carrying both edges' running values at the segment's first row
-// and the exact tile columns its spans touch.  The raster kernel never re-derives any of this.
+// It then walks the triangle's rows ONCE (DrawModel's active-edge maintenance, span set-up and
+// edge stepping, projekt.cpp:198-412, 542-572; no pixels) and emits one 64-byte SPAN record per
+// row -- column range, start values, per-pixel increments -- grouped into segments (one per edge
+// pair and tile-row band) that carry the exact tile columns their spans touch.  The raster
+// kernel never re-derives any of this: it only replays per-pixel adds and depth-tests.
 //
 // Mapping: one thread per triangle, one CTA per 128 triangles.  A warp handles 32 triangles:
 // their 32 x 120 B of vertex attributes are fetched with fully coalesced loads into shared
@@ -89,16 +90,16 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     __shared__ __align__(16) float s_col[kSetupThreads*12];
     __shared__ float s_nrm[kSetupThreads*9];
     __shared__ __align__(16) uint32_t s_rec[kSetupThreads*kRecWords];
-    __shared__ unsigned s_binned, s_pairs, s_seg_base;
-    __shared__ unsigned s_warp_sum[kSetupThreads/32];
+    __shared__ unsigned s_binned, s_pairs, s_seg_base, s_span_base;
+    __shared__ unsigned s_warp_sum[kSetupThreads/32], s_warp_sum2[kSetupThreads/32];
 
     const unsigned base = blockIdx.x*kSetupThreads;
     const unsigned n = min((unsigned)kSetupThreads, m.ntri - base);
     const int t = threadIdx.x;
     if(t == 0) { s_binned = 0; s_pairs = 0; }
-    int my_segs = 0, walk_end = 0, first_row = 0, max_y = 0, nedges = 0, nonfinite = 0;
+    int my_segs = 0, my_spans = 0, walk_end = 0, first_row = 0, max_y = 0, nedges = 0, nonfinite = 0;
     bool have_walk = false;
-    unsigned seg_at = 0;
+    unsigned seg_at = 0, span_at = 0;
 
     // coalesced attribute fetch: consecutive lanes read consecutive words
     {
@@ -227,12 +228,12 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         rec[R_MAXY] = (uint32_t)max_y; rec[R_PRIM] = m.prim_base + base + t;
         rec[R_EDGE0 + 3*kEdgeWords] = emit; rec[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec[R_EDGE0 + 3*kEdgeWords + 2] = 0;
 
-        have_walk = (nedges >= 2) && out.segs != nullptr;
+        have_walk = (nedges >= 2) && out.spans != nullptr;
         nonfinite = 0;
         if(have_walk)
         {
             // RoundR32ToU32 (cvtss2si) and cvt.rni.s32.f32 agree only for |c*255| < 2^31.  Colours of
-            // finite scenes stay near [0,1]; a segment whose edge colours could leave that range
+            // finite scenes stay near [0,1]; a triangle whose edge colours could leave that range
             // (NaN/Inf or absurd input) takes the guarded pack in the raster kernel.  Edges that
             // never step (YMax <= YMin: inserted and expired in the same row) are never drawn.
 #pragma unroll
@@ -251,9 +252,10 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         walk_end = min(max_y, v.band_y1);
         if(have_walk && !(first_row < walk_end && max_y > v.band_y0)) have_walk = false;
 
-        // Number of segments, without walking: between consecutive list-change rows the set of
-        // active edges {e : YMin <= row < YMax} is constant; a stretch with >= 2 of them yields one
-        // segment per tile-row band it touches.  The walk below splits at exactly the same rows.
+        // Number of segments and spans, without walking: between consecutive list-change rows the
+        // set of active edges {e : YMin <= row < YMax} is constant; a stretch with >= 2 of them
+        // yields one span per row and one segment per tile-row band it touches.  The walk below
+        // splits at exactly the same rows.
         if(have_walk)
         {
             int y = first_row;
@@ -273,36 +275,50 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                 if(act >= 2)
                 {
                     const int a = max(y, v.band_y0);
-                    if(a < nxt) my_segs += (nxt - 1 - v.band_y0)/v.tile_h - (a - v.band_y0)/v.tile_h + 1;
+                    if(a < nxt)
+                    {
+                        my_segs += (nxt - 1 - v.band_y0)/v.tile_h - (a - v.band_y0)/v.tile_h + 1;
+                        my_spans += nxt - a;
+                    }
                 }
                 y = nxt;
             }
         }
     }
 
-    // ---- CTA-wide exclusive scan of segment counts: warp shuffles + one atomicAdd per CTA ----
+    // ---- CTA-wide exclusive scans of segment and span counts: warp shuffles, then ONE pair of
+    //      global atomicAdds per CTA hands out the output ranges ----
     {
         const unsigned lane = t & 31, warp = t >> 5;
-        unsigned incl = (unsigned)my_segs;
+        unsigned incl_g = (unsigned)my_segs, incl_p = (unsigned)my_spans;
 #pragma unroll
         for(int d = 1; d < 32; d <<= 1)
         {
-            unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
-            if(lane >= (unsigned)d) incl += up;
+            unsigned ug = __shfl_up_sync(0xffffffffu, incl_g, d);
+            unsigned up = __shfl_up_sync(0xffffffffu, incl_p, d);
+            if(lane >= (unsigned)d) { incl_g += ug; incl_p += up; }
         }
-        if(lane == 31) s_warp_sum[warp] = incl;
+        if(lane == 31) { s_warp_sum[warp] = incl_g; s_warp_sum2[warp] = incl_p; }
         __syncthreads();
         if(t == 0)
         {
-            unsigned run = 0;
-            for(int w = 0; w < kSetupThreads/32; ++w) { unsigned c = s_warp_sum[w]; s_warp_sum[w] = run; run += c; }
-            s_seg_base = run ? atomicAdd(out.seg_total, run) : 0u;
+            unsigned run_g = 0, run_p = 0;
+            for(int w = 0; w < kSetupThreads/32; ++w)
+            {
+                unsigned cg = s_warp_sum[w], cp = s_warp_sum2[w];
+                s_warp_sum[w] = run_g; s_warp_sum2[w] = run_p; run_g += cg; run_p += cp;
+            }
+            s_seg_base = run_g ? atomicAdd(out.seg_total, run_g) : 0u;
+            s_span_base = run_p ? atomicAdd(out.span_total, run_p) : 0u;
         }
         __syncthreads();
-        seg_at = s_seg_base + s_warp_sum[warp] + (incl - (unsigned)my_segs);
+        seg_at = s_seg_base + s_warp_sum[warp] + (incl_g - (unsigned)my_segs);
+        span_at = s_span_base + s_warp_sum2[warp] + (incl_p - (unsigned)my_spans);
     }
 
-    if((unsigned)t < n && have_walk && my_segs > 0 && (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity)
+    if((unsigned)t < n && have_walk && my_segs > 0 &&
+       (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity &&
+       (unsigned long long)span_at + (unsigned)my_spans <= out.span_capacity)
     {
         const uint32_t *rec = s_rec + t*kRecWords;
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
@@ -311,24 +327,25 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         L.ymax = 0; L.id = -1; R = L;
         int nact = 0, next_ev = first_row;
         bool open = false;
-        unsigned seg = seg_at;
-        int seg_y0 = 0, seg_rows = 0, seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
+        unsigned seg = seg_at, span = span_at;
+        int seg_y0 = 0, seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
+        unsigned seg_span0 = 0;
         unsigned pairs = 0;
         const unsigned prim = m.prim_base + base + t;
 
         auto close_segment = [&]()
         {
             if(!open) return;
-            uint32_t *S = out.segs + (size_t)seg*kSegWords;
             int tx0 = 1, tx1 = 0;
             if(seg_minx <= seg_maxx) { tx0 = seg_minx/v.tile_w; tx1 = seg_maxx/v.tile_w; }
-            const int trow = (seg_y0 - v.band_y0)/v.tile_h;
-            uint4 h = make_uint4(prim, (unsigned)seg_y0, (unsigned)seg_rows | (nonfinite ? kSegNonFinite : 0u),
-                                 (unsigned)tx0 | ((unsigned)tx1 << 16));
-            *reinterpret_cast<uint4 *>(S) = h;
-            out.seg_tiles[seg] = make_uint2((unsigned)trow, (unsigned)tx0 | ((unsigned)tx1 << 16));
-            for(int tx = tx0; tx <= tx1; ++tx) atomicAdd(&out.tile_count[trow*v.tiles_x + tx], 1u);
-            if(tx0 <= tx1) pairs += (unsigned)(tx1 - tx0 + 1);
+            SegInfo si;
+            si.tile_row = (unsigned)((seg_y0 - v.band_y0)/v.tile_h);
+            si.tx = (unsigned)tx0 | ((unsigned)tx1 << 16);
+            si.span_base = seg_span0;
+            si.nrows = span - seg_span0;
+            out.segs[seg] = si;
+            for(int tx = tx0; tx <= tx1; ++tx) atomicAdd(&out.tile_count[si.tile_row*v.tiles_x + tx], si.nrows);
+            if(tx0 <= tx1) pairs += (unsigned)(tx1 - tx0 + 1)*si.nrows;
             ++seg; open = false;
         };
 
@@ -343,24 +360,34 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     if(brk || !open || ((y - v.band_y0) % v.tile_h) == 0)
                     {
                         close_segment();
-                        // open: both edges' state at this row goes straight to the segment slot
-                        uint32_t *S = out.segs + (size_t)seg*kSegWords;
-                        float4 *Q = reinterpret_cast<float4 *>(S);
-                        Q[1] = make_float4(L.x, L.z, L.c0, L.c1);  Q[2] = make_float4(L.c2, L.c3, L.dx, L.dz);
-                        Q[3] = make_float4(L.d0, L.d1, L.d2, L.d3);
-                        Q[4] = make_float4(R.x, R.z, R.c0, R.c1);  Q[5] = make_float4(R.c2, R.c3, R.dx, R.dz);
-                        Q[6] = make_float4(R.d0, R.d1, R.d2, R.d3);
-                        open = true; seg_y0 = y; seg_rows = 0; seg_minx = 0x7fffffff; seg_maxx = (int)0x80000000;
+                        open = true; seg_y0 = y; seg_span0 = span; seg_minx = 0x7fffffff; seg_maxx = (int)0x80000000;
                     }
-                    // the columns this row's span paints: same clamps and roundings as the span
-                    // code (projekt.cpp:381-406), so the binner's tile columns are exact
-                    float leftx = L.x;
-                    if(leftx < 0.0f) leftx = 0.0f; else if(leftx >= wf) leftx = wf_m1;
-                    float rightx = R.x;
-                    if(rightx < 0.0f) rightx = 0.0f; else if(rightx >= wf) rightx = wf_m1;
-                    const int minx = round_s32(leftx), maxx = round_s32(rightx);
+                    // ---- span set-up, projekt.cpp:306-412, once per row ----
+                    const float xdiff = roundf(fsub(R.x, L.x));                   // :311-312
+                    float zi = 0.0f, i0 = 0.0f, i1 = 0.0f, i2 = 0.0f, i3 = 0.0f;
+                    if(xdiff != 0.0f)                                             // :333-363
+                    {
+                        i0 = fdiv(fsub(R.c0, L.c0), xdiff); i1 = fdiv(fsub(R.c1, L.c1), xdiff);
+                        i2 = fdiv(fsub(R.c2, L.c2), xdiff); i3 = fdiv(fsub(R.c3, L.c3), xdiff);
+                        zi = fdiv(fsub(R.z, L.z), xdiff);
+                    }
+                    float xoff = 0.0f, leftx = L.x;                               // :381-390
+                    if(leftx < 0.0f) { xoff = -leftx; leftx = 0.0f; }
+                    else if(leftx >= wf) { leftx = wf_m1; }
+                    float rightx = R.x;                                           // :392-400
+                    if(rightx < 0.0f) { rightx = 0.0f; }
+                    else if(rightx >= wf) { rightx = wf_m1; }
+                    const int minx = round_s32(leftx), maxx = round_s32(rightx);  // :402-406
+                    const float z = fadd(L.z, fmul(xoff, zi));                    // :375, :408
+                    const float c0 = fadd(L.c0, fmul(xoff, i0)), c1 = fadd(L.c1, fmul(xoff, i1));   // :379, :412
+                    const float c2 = fadd(L.c2, fmul(xoff, i2)), c3 = fadd(L.c3, fmul(xoff, i3));
+                    float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+                    Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
+                    Q[1] = make_float4(z, c0, c1, c2);
+                    Q[2] = make_float4(c3, zi, i0, i1);
+                    Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), 0.0f);
+                    ++span;
                     if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
-                    ++seg_rows;
                 }
                 step_edge(L); step_edge(R);                                   // :542-549
                 if(L.x > R.x) { ActiveEdge tmp = L; L = R; R = tmp; }          // :562-572
@@ -371,11 +398,17 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             }
         }
         close_segment();
-        // slots promised by the count but not produced (cannot happen for finite input) are blanked
+        // slots promised by the counts but not produced (cannot happen for finite input) are blanked
+        for(; span < span_at + (unsigned)my_spans; ++span)
+        {
+            float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+            Q[0] = make_float4(__uint_as_float(prim), 0.0f, __int_as_float(1), __int_as_float(0));
+            Q[1] = Q[2] = Q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         for(; seg < seg_at + (unsigned)my_segs; ++seg)
         {
-            *reinterpret_cast<uint4 *>(out.segs + (size_t)seg*kSegWords) = make_uint4(prim, 0u, 0u, 1u);
-            out.seg_tiles[seg] = make_uint2(0u, 1u);
+            SegInfo si; si.tile_row = 0; si.tx = 1u; si.span_base = 0; si.nrows = 0;
+            out.segs[seg] = si;
         }
         if(pairs) { atomicAdd(&s_binned, 1u); atomicAdd(&s_pairs, pairs); }
     }

@@ -202,8 +202,9 @@ typedef struct b200r_frame_stats
 {
     uint64_t Triangles;        /* submitted in the last render call                             */
     uint64_t Binned;           /* triangles that produced at least one (segment, tile) pair     */
-    uint64_t Segments;         /* trapezoid segments emitted by the set-up kernel               */
-    uint64_t TilePairs;        /* (segment, tile) pairs produced by the binner                  */
+    uint64_t Segments;         /* segments (edge pair x tile-row band) emitted by the set-up kernel */
+    uint64_t Spans;            /* span records (one per covered row) emitted by the set-up kernel */
+    uint64_t TilePairs;        /* (span, tile) queue entries produced by the binner             */
     uint64_t Tiles;            /* screen tiles of the band                                      */
     uint64_t KernelLaunches;   /* kernels launched by this context since creation               */
     uint64_t Reruns;           /* frames re-issued because the pair list had to grow            */
