@@ -45,6 +45,8 @@ struct FrameWords
     unsigned work_counter;
     unsigned seg_total;
     unsigned span_total;
+    unsigned extra_total;
+    unsigned pad;
     unsigned long long counters[2];     // binned triangles, tile pairs
 };
 
@@ -124,6 +126,7 @@ static int fill_view(b200r_context *c, const game_render_commands *cmd, const b2
     v.tile_w = c->tile_w; v.tile_h = c->tile_h;
     v.tiles_x = (t->Width + c->tile_w - 1)/c->tile_w;
     v.tiles_y = (t->BandRows + c->tile_h - 1)/c->tile_h;
+    v.alias_rows = (t->ColorPitch == t->Width*4 && t->DepthStride == t->Width) ? 1 : 0;
     if(v.tiles_x > 65535 || v.tiles_y > 65535) return fail(c, B200R_E_UNSUPPORTED, "more than 65535 tiles per axis");
     return B200R_OK;
 }
@@ -149,6 +152,7 @@ static int issue_frame(b200r_context *c)
     so.segs = (SegInfo *)c->segs.ptr;
     so.seg_total = &words->seg_total;
     so.span_total = &words->span_total;
+    so.extra_total = &words->extra_total;
     so.seg_capacity = seg_cap;
     so.span_capacity = span_cap;
     so.tile_count = tile_count;
@@ -169,7 +173,8 @@ static int issue_frame(b200r_context *c)
     const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
     ScatterParams sp;
     sp.segs = so.segs;
-    sp.seg_total = &words->seg_total; sp.span_total = &words->span_total; sp.pair_total = &words->pair_total;
+    sp.seg_total = &words->seg_total; sp.span_total = &words->span_total; sp.extra_total = &words->extra_total;
+    sp.pair_total = &words->pair_total;
     sp.seg_capacity = seg_cap; sp.span_capacity = span_cap; sp.pair_capacity = pair_cap;
     sp.tiles_x = v.tiles_x;
     sp.tile_offset = tile_offset; sp.tile_fill = tile_fill; sp.pair_list = (unsigned *)c->pairs.ptr;
@@ -182,6 +187,7 @@ static int issue_frame(b200r_context *c)
     rp.spans = so.spans;
     rp.seg_total = &words->seg_total;
     rp.span_total = &words->span_total;
+    rp.extra_total = &words->extra_total;
     rp.seg_capacity = seg_cap;
     rp.span_capacity = span_cap;
     rp.tile_count = tile_count;
@@ -214,7 +220,8 @@ static int settle_pending(b200r_context *c)
     {
         CU(cudaEventSynchronize(c->total_ready));
         const unsigned total = c->h_words->pair_total;
-        const unsigned nseg = c->h_words->seg_total, nspan = c->h_words->span_total;
+        const unsigned nextra = c->h_words->extra_total;
+        const uint64_t nseg = (uint64_t)c->h_words->seg_total + nextra, nspan = (uint64_t)c->h_words->span_total + nextra;
         const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
         const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
         const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(kSpanWords*sizeof(uint32_t)), 0xffffffffu);
@@ -222,6 +229,7 @@ static int settle_pending(b200r_context *c)
         c->stats.TilePairs = c->h_words->counters[1];
         c->stats.Segments = nseg;
         c->stats.Spans = nspan;
+        c->stats.AliasPixels = nextra;
         c->pending = false;
         if(total > pair_cap || nseg > seg_cap || nspan > span_cap)
         {
@@ -549,7 +557,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
     SetupOutputs so;
     so.recs = (uint32_t *)c->recs.ptr; so.spans = nullptr; so.segs = nullptr;
-    so.seg_total = &words->seg_total; so.span_total = &words->span_total;
+    so.seg_total = &words->seg_total; so.span_total = &words->span_total; so.extra_total = &words->extra_total;
     so.seg_capacity = 0; so.span_capacity = 0;
     so.tile_count = tile_count; so.counters = words->counters;
     MeshParams mp;
@@ -590,7 +598,12 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     {
         const uint32_t *E = order[i].edge;
         edge_info &o = outp[i];
-        auto f = [&](int w) { float x; memcpy(&x, E + w, 4); return x; };
+        // NaN sign/payload is not part of the arithmetic contract: SSE's invalid-operation result
+        // is the default NaN 0xFFC00000 (and it propagates), the GPU's is 0x7FFFFFFF.  Such values
+        // only occur in edges that are never drawn (YMax == YMin: gradients 0/0); export them in
+        // the x86 encoding so that the table is byte-identical to the reference's.
+        auto f = [&](int w) { uint32_t u = E[w]; if((u & 0x7fffffffu) > 0x7f800000u) u = 0xffc00000u;
+                              float x; memcpy(&x, &u, 4); return x; };
         o.YMin = (s32)E[E_YMIN]; o.YMax = (s32)E[E_YMAX];
         o.XMin = f(E_X); o.Gradient = f(E_DX); o.ZMin = f(E_Z); o.ZGradient = f(E_DZ);
         o.MinColor.x = f(E_C + 0); o.MinColor.y = f(E_C + 1); o.MinColor.z = f(E_C + 2); o.MinColor.w = f(E_C + 3);

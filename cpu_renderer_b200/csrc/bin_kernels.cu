@@ -63,10 +63,12 @@ tile_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offs
 __global__ void __launch_bounds__(256)
 scatter_kernel(const ScatterParams p)
 {
-    const unsigned nseg = *p.seg_total;
-    if(nseg > p.seg_capacity || *p.span_total > p.span_capacity || *p.pair_total > p.pair_capacity) return;
-    for(unsigned seg = blockIdx.x*blockDim.x + threadIdx.x; seg < nseg; seg += gridDim.x*blockDim.x)
+    const unsigned nseg = *p.seg_total, nextra = *p.extra_total;
+    if(lists_overflowed(nseg, *p.span_total, nextra, *p.pair_total, p.seg_capacity, p.span_capacity, p.pair_capacity)) return;
+    // ordinary segments occupy [0, nseg); alias-pixel segments the last nextra slots
+    for(unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < nseg + nextra; i += gridDim.x*blockDim.x)
     {
+        const unsigned seg = (i < nseg) ? i : p.seg_capacity - 1u - (i - nseg);
         const SegInfo si = p.segs[seg];
         const int tx0 = si.tx & 0xffff, tx1 = si.tx >> 16;
         for(int tx = tx0; tx <= tx1; ++tx)

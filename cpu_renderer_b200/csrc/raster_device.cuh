@@ -29,6 +29,8 @@ struct ViewParams
     int band_y0, band_y1;       // screen rows owned by this target
     int tile_w, tile_h;
     int tiles_x, tiles_y;
+    int alias_rows;             // rows are contiguous (Pitch == Width*4, depth stride == Width): a pixel the
+                                // reference writes at column == Width lands in column 0 of the next row
 };
 
 struct MeshParams
@@ -72,8 +74,9 @@ struct RasterParams
 {
     ViewParams v;
     const uint32_t *spans;      // kSpanWords per span
-    const unsigned *seg_total;  // device words: segments / spans emitted this frame
+    const unsigned *seg_total;  // device words: segments / spans / next-row alias pixels this frame
     const unsigned *span_total;
+    const unsigned *extra_total;
     unsigned seg_capacity, span_capacity;
     const unsigned *tile_count;
     const unsigned *tile_offset;
@@ -88,6 +91,15 @@ struct RasterParams
     int depth_stride;           // floats per row
     int bulk_ok;                // rows may be moved with cp.async.bulk (16-byte aligned)
 };
+
+// Every consumer of the lists uses the same test, so a frame whose lists overflowed is skipped
+// consistently and re-issued by the host after growing them.
+__device__ __forceinline__ bool lists_overflowed(unsigned nseg, unsigned nspan, unsigned nextra, unsigned npair,
+                                                 unsigned seg_cap, unsigned span_cap, unsigned pair_cap)
+{
+    return (unsigned long long)nseg + nextra > seg_cap || (unsigned long long)nspan + nextra > span_cap ||
+           npair > pair_cap;
+}
 
 // ---------------------------------------------------------------- exact binary32 helpers
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -165,6 +177,8 @@ struct SetupOutputs
     SegInfo *segs;
     unsigned *seg_total;        // device counters
     unsigned *span_total;
+    unsigned *extra_total;      // alias pixels: one-pixel span + segment each, allocated downwards
+                                // from the END of the span / segment arrays
     unsigned seg_capacity, span_capacity;
     unsigned *tile_count;
     unsigned long long *counters;   // [0] binned triangles, [1] tile pairs
@@ -176,7 +190,7 @@ void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigne
 struct ScatterParams
 {
     const SegInfo *segs;
-    const unsigned *seg_total, *span_total, *pair_total;
+    const unsigned *seg_total, *span_total, *extra_total, *pair_total;
     unsigned seg_capacity, span_capacity, pair_capacity;
     int tiles_x;
     const unsigned *tile_offset;

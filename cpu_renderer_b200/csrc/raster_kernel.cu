@@ -88,7 +88,8 @@ raster_kernel(const RasterParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned s_tile, s_ticket;
 
-    if(*p.seg_total > p.seg_capacity || *p.span_total > p.span_capacity || *p.pair_total > p.pair_capacity) return;   // host re-issues
+    if(lists_overflowed(*p.seg_total, *p.span_total, *p.extra_total, *p.pair_total, p.seg_capacity, p.span_capacity,
+                        p.pair_capacity)) return;                          // host grows the lists and re-issues
 
     const int tid = threadIdx.x, lane = tid & 31;
     Pixel *tile = reinterpret_cast<Pixel *>(smem_raw);

@@ -249,8 +249,9 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             }
         }
         // Row range this GPU's band needs: rows above the band are walked (state), rows below not.
+        // (with contiguous rows, the row just above the band can still drop an alias pixel into it)
         walk_end = min(max_y, v.band_y1);
-        if(have_walk && !(first_row < walk_end && max_y > v.band_y0)) have_walk = false;
+        if(have_walk && !(first_row < walk_end && max_y > v.band_y0 - (v.alias_rows ? 1 : 0))) have_walk = false;
 
         // Number of segments and spans, without walking: between consecutive list-change rows the
         // set of active edges {e : YMin <= row < YMax} is constant; a stretch with >= 2 of them
@@ -316,7 +317,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         span_at = s_span_base + s_warp_sum2[warp] + (incl_p - (unsigned)my_spans);
     }
 
-    if((unsigned)t < n && have_walk && my_segs > 0 &&
+    if((unsigned)t < n && have_walk &&
        (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity &&
        (unsigned long long)span_at + (unsigned)my_spans <= out.span_capacity)
     {
@@ -355,9 +356,10 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             if(y == next_ev) { active_list_event(y, rec, nedges, L, R, nact, next_ev); brk = true; }
             if(nact == 2)
             {
-                if(y >= v.band_y0)
+                const bool in_band = y >= v.band_y0;
+                if(in_band || (v.alias_rows && y == v.band_y0 - 1))
                 {
-                    if(brk || !open || ((y - v.band_y0) % v.tile_h) == 0)
+                    if(in_band && (brk || !open || ((y - v.band_y0) % v.tile_h) == 0))
                     {
                         close_segment();
                         open = true; seg_y0 = y; seg_span0 = span; seg_minx = 0x7fffffff; seg_maxx = (int)0x80000000;
@@ -377,17 +379,55 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     float rightx = R.x;                                           // :392-400
                     if(rightx < 0.0f) { rightx = 0.0f; }
                     else if(rightx >= wf) { rightx = wf_m1; }
-                    const int minx = round_s32(leftx), maxx = round_s32(rightx);  // :402-406
+                    const int minx = round_s32(leftx);                            // :402-406
+                    int maxx = round_s32(rightx);
                     const float z = fadd(L.z, fmul(xoff, zi));                    // :375, :408
                     const float c0 = fadd(L.c0, fmul(xoff, i0)), c1 = fadd(L.c1, fmul(xoff, i1));   // :379, :412
                     const float c2 = fadd(L.c2, fmul(xoff, i2)), c3 = fadd(L.c3, fmul(xoff, i3));
-                    float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
-                    Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
-                    Q[1] = make_float4(z, c0, c1, c2);
-                    Q[2] = make_float4(c3, zi, i0, i1);
-                    Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), 0.0f);
-                    ++span;
-                    if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
+                    if(maxx >= v.width && minx <= maxx)
+                    {
+                        // An end in [Width-0.5, Width) is not clamped (:387, :397) and rounds up to
+                        // column == Width (:402-403); the reference's pointer arithmetic (:414-419)
+                        // puts that pixel into column 0 of the NEXT row when rows are contiguous, into
+                        // row padding otherwise, past the buffer on the last row.  The next-row write
+                        // is reproduced as a one-pixel span of its own; the others are dropped.
+                        const int ay = y + 1;
+                        if(v.alias_rows && ay < v.height && ay >= v.band_y0 && ay < v.band_y1)
+                        {
+                            float az = z, a0 = c0, a1 = c1, a2 = c2, a3 = c3;
+                            for(int sx = minx; sx < v.width; ++sx)                // :534-535 up to that column
+                            {
+                                a0 = fadd(a0, i0); a1 = fadd(a1, i1); a2 = fadd(a2, i2); a3 = fadd(a3, i3);
+                                az = fadd(az, zi);
+                            }
+                            const unsigned ex = atomicAdd(out.extra_total, 1u);
+                            if(ex < out.span_capacity && ex < out.seg_capacity)
+                            {
+                                const unsigned asp = out.span_capacity - 1u - ex, asg = out.seg_capacity - 1u - ex;
+                                float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)asp*kSpanWords);
+                                Q[0] = make_float4(__uint_as_float(prim), __int_as_float(ay), __int_as_float(0), __int_as_float(0));
+                                Q[1] = make_float4(az, a0, a1, a2);
+                                Q[2] = make_float4(a3, 0.0f, 0.0f, 0.0f);
+                                Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), 0.0f);
+                                SegInfo si;
+                                si.tile_row = (unsigned)((ay - v.band_y0)/v.tile_h); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
+                                out.segs[asg] = si;
+                                atomicAdd(&out.tile_count[si.tile_row*v.tiles_x], 1u);
+                                pairs += 1u;
+                            }
+                        }
+                        maxx = v.width - 1;
+                    }
+                    if(in_band)
+                    {
+                        float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+                        Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
+                        Q[1] = make_float4(z, c0, c1, c2);
+                        Q[2] = make_float4(c3, zi, i0, i1);
+                        Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), 0.0f);
+                        ++span;
+                        if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
+                    }
                 }
                 step_edge(L); step_edge(R);                                   // :542-549
                 if(L.x > R.x) { ActiveEdge tmp = L; L = R; R = tmp; }          // :562-572

@@ -204,6 +204,8 @@ typedef struct b200r_frame_stats
     uint64_t Binned;           /* triangles that produced at least one (segment, tile) pair     */
     uint64_t Segments;         /* segments (edge pair x tile-row band) emitted by the set-up kernel */
     uint64_t Spans;            /* span records (one per covered row) emitted by the set-up kernel */
+    uint64_t AliasPixels;      /* pixels the reference writes at column == Width, i.e. into column 0
+                                  of the next row of a contiguous target (projekt.cpp:402-419)    */
     uint64_t TilePairs;        /* (span, tile) queue entries produced by the binner             */
     uint64_t Tiles;            /* screen tiles of the band                                      */
     uint64_t KernelLaunches;   /* kernels launched by this context since creation               */

@@ -221,8 +221,22 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
     float *ZPixel = T->Z + MinX + (size_t)Row*T->ZStride;        /* :418 */
     int32_t *Prim = T->Prim ? T->Prim + MinX + (size_t)Row*T->ZStride : 0;
     if(Stats) Stats->SpanRows += 1;
+    /* Column == Width is reachable: an end in [Width-0.5, Width) is not clamped (:387, :397) and
+     * rounds up (:402-403).  The reference then writes through Row*Pitch + Width*4, i.e. into
+     * column 0 of the NEXT row when rows are contiguous (Pitch == Width*4, ZBufferWidth == Width),
+     * into row padding otherwise, and past the end of the buffer on the last row (undefined).
+     * Defined here: the next-row write is kept (it is what the reference's image shows), the
+     * padding / out-of-buffer writes are dropped. */
+    const int Contiguous = (T->Pitch == T->Width*4) && ((int32_t)T->ZStride == T->Width);
     for(int32_t X = MinX; X <= MaxX; ++X)                        /* :423 */
     {
+        if(X >= T->Width && !(Contiguous && Row + 1 < T->Height))
+        {
+            ++ZPixel; ++Pixel; if(Prim) ++Prim;
+            for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];
+            Z += ZInc;
+            continue;
+        }
         /* colour is r,g,b,a = C[0..3]; packed A R G B (:520-523) */
         uint32_t Color32 = (round_u32(C[3]*255.0f) << 24) | (round_u32(C[0]*255.0f) << 16) |
                            (round_u32(C[1]*255.0f) << 8) | (round_u32(C[2]*255.0f) << 0);

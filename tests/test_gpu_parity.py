@@ -1,14 +1,29 @@
-"""GPU parity proper: the CUDA path, called through the C ABI, against the CPU oracle on the
-same seeded inputs.  Coverage mask and depth bit-exact; colour bit-exact too (the stated bar is
-+-1 LSB per 8-bit channel, the arithmetic is identical so 0 is expected and asserted)."""
+"""GPU parity proper: the CUDA path, called through the C ABI (include/b200_raster.h), against
+the CPU oracle and the committed golden vectors on the same seeded inputs.
+
+Bar (BASELINE.json north_star): coverage masks and depth-test outcomes bit-exact; shaded colour
+within +-1 LSB per 8-bit channel.  The arithmetic is restated operation for operation, so the
+tests assert the stronger result -- colour identical too -- and report the LSB distance.
+"""
+import ctypes as C
+import os
+
 import numpy as np
 import pytest
 
+import kat_scenes
 import oracle_lib as ol
+from cpu_renderer_b200 import api
 from cpu_renderer_b200 import scene as sc
+from cpu_renderer_b200 import shard
 from cpu_renderer_b200.api import Renderer
 
 pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+MESH = np.load(os.path.join(os.path.dirname(__file__), "golden", "sphere_mesh.npz"))
+TILES = [(64, 32), (32, 32), (128, 16), (64, 16), (128, 32)]
+COLOR_TOLERANCE_LSB = 1          # the stated bar; 0 is what we expect and check
 
 
 @pytest.fixture(scope="module")
@@ -18,30 +33,251 @@ def renderer():
     r.close()
 
 
-def compare(renderer, scene, splits=None, tile=None):
-    o = ol.oracle_render(scene)
+def diff(want_color, want_z, color, z, clear_depth):
+    zdiff = int((want_z.view(np.uint32) != z.view(np.uint32)).sum())
+    cov = int(((want_z != np.float32(clear_depth)) != (z != np.float32(clear_depth))).sum())
+    cdiff = int((want_color != color).sum())
+    ch = np.abs(want_color.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    return dict(zdiff=zdiff, covdiff=cov, cdiff=cdiff, maxlsb=int(ch.max()))
+
+
+def check(renderer, scene, splits=None, tile=(64, 32), want=None):
+    want = want or ol.oracle_render(scene)
     color, z, _ = ol.new_targets(scene)
-    if tile:
-        renderer.set_tile(*tile)
+    renderer.set_tile(*tile)
     renderer.render_scene_host(scene, color, z, splits=splits)
-    zdiff = int((o["z"].view(np.uint32) != z.view(np.uint32)).sum())
-    cov_o = o["z"] != np.float32(scene.clear_depth)
-    cov_g = z != np.float32(scene.clear_depth)
-    covdiff = int((cov_o != cov_g).sum())
-    cdiff = int((o["color"] != color).sum())
-    ch = np.abs(o["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
-    return dict(zdiff=zdiff, covdiff=covdiff, cdiff=cdiff, maxlsb=int(ch.max()), stats=o["stats"])
+    d = diff(want["color"], want["z"], color, z, scene.clear_depth)
+    assert d["covdiff"] == 0 and d["zdiff"] == 0, d
+    assert d["maxlsb"] <= COLOR_TOLERANCE_LSB and d["cdiff"] == 0, d
+    return color, z
 
 
-@pytest.mark.parametrize("tile", [(64, 32), (32, 32), (128, 16), (64, 16), (128, 32)])
+@pytest.mark.parametrize("tile", TILES)
 def test_small_triangles_1080p(renderer, tile):
-    s = sc.triangle_soup("small", 0xB2000002, 100_000, 1920, 1080, 1.5, 4.0)
-    r = compare(renderer, s, tile=tile)
-    assert r["covdiff"] == 0 and r["zdiff"] == 0 and r["cdiff"] == 0, r
+    check(renderer, sc.triangle_soup("small", 0xB2000002, 100_000, 1920, 1080, 1.5, 4.0), tile=tile)
+
+
+@pytest.mark.parametrize("tile", TILES)
+def test_large_overlapping(renderer, tile):
+    check(renderer, sc.triangle_soup("large", 0xB2000003, 4000, 1920, 1080, 32.0, 96.0), tile=tile)
 
 
 @pytest.mark.parametrize("tile", [(64, 32), (128, 16)])
-def test_large_overlapping(renderer, tile):
-    s = sc.triangle_soup("large", 0xB2000003, 4000, 1920, 1080, 32.0, 96.0)
-    r = compare(renderer, s, tile=tile)
-    assert r["covdiff"] == 0 and r["zdiff"] == 0 and r["cdiff"] == 0, r
+def test_wild_triangles_with_edge_crossings(renderer, tile):
+    # jitter 2.5 rad: slivers whose edges cross before the last row (the reference null-derefs
+    # on 2 % of these); level-1 semantics define them
+    check(renderer, sc.triangle_soup("wild", 0x5151, 20_000, 800, 600, 1.0, 40.0, jitter=2.5), tile=tile)
+
+
+@pytest.mark.parametrize("name", sorted(kat_scenes.all_scenes()))
+def test_kat_scene_against_verbatim_reference_image(renderer, name):
+    """Top clip, side clamps, bottom clip, horizontal edges, equal-Z ties, back faces, near plane,
+    three lights + object offset -- compared with the image the VERBATIM reference produced."""
+    s = kat_scenes.all_scenes()[name]
+    for tile in [(64, 32), (32, 32)]:
+        color, z, _ = ol.new_targets(s)
+        renderer.set_tile(*tile)
+        renderer.render_scene_host(s, color, z)
+        assert np.array_equal(z.view(np.uint32), GOLD[f"kat_{name}_z"]), name
+        assert np.array_equal(color, GOLD[f"kat_{name}_color"]), name
+
+
+@pytest.mark.parametrize("tag,res", [("c1_1080p", (1920, 1080, 500.0)), ("c1_540p", (960, 540, 135.0))])
+def test_c1_demo_sphere(renderer, tag, res):
+    """Config C1: the reference's own ConstructSphere mesh (verbatim vertices from the fixture)."""
+    s = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], *res)
+    color, z = check(renderer, s)
+    assert ol.fnv1a64_words(color) == str(GOLD[f"{tag}_level1_color_hash"])
+    assert ol.fnv1a64_words(z) == str(GOLD[f"{tag}_level1_z_hash"])
+
+
+def test_fill_edge_table_matches_verbatim_records_and_order(renderer):
+    """b200r_fill_edge_table vs verbatim FillEdgeTable (projekt.cpp:3882-4121): every Gouraud
+    field of all 2 476 records of the sphere, in MergeSort's unstable order (projekt.cpp:2-72)."""
+    for tag, res in (("c1_1080p", (1920, 1080, 500.0)), ("c1_540p", (960, 540, 135.0))):
+        s = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], *res)
+        e = renderer.fill_edge_table(s)
+        assert len(e) == int(GOLD[f"{tag}_edge_count"])
+        words = np.concatenate([np.ascontiguousarray(e[f]).view(np.uint32).reshape(len(e), -1)
+                                for f in ol.GOURAUD_FIELDS], axis=1)
+        assert np.array_equal(words, GOLD[f"{tag}_edges"])
+        assert not e["Next"].any()
+
+
+def test_fill_edge_table_random_object(renderer):
+    s = sc.triangle_soup("t", 21, 5_000, 1920, 1080, 1.0, 60.0, jitter=2.5)
+    e = renderer.fill_edge_table(s)
+    want, n = ol.oracle_edge_table(s)
+    assert len(e) == n
+    for f in ol.GOURAUD_FIELDS:
+        assert np.array_equal(np.ascontiguousarray(e[f]).view(np.uint32),
+                              np.ascontiguousarray(want[f]).view(np.uint32)), f
+
+
+def test_several_objects_and_split_submission(renderer):
+    s = sc.triangle_soup("multi", 0x31, 30_000, 1280, 720, 2.0, 30.0)
+    nv = s.positions.shape[0]
+    check(renderer, s, splits=[3 * 7000, 3 * 1, 3 * 12999, nv - 3 * 20000])
+
+
+def test_preexisting_target_contents_take_part_in_the_depth_test(renderer):
+    """The reference never clears (projekt.cpp:525 tests against whatever is there): render A,
+    then B on top of A's colour/depth, as two calls -- must equal the oracle doing the same."""
+    a = sc.triangle_soup("a", 0x61, 5_000, 1024, 576, 8.0, 60.0)
+    b = sc.triangle_soup("b", 0x62, 20_000, 1024, 576, 2.0, 20.0)
+    want_c, want_z, _ = ol.new_targets(a)
+    ol.oracle_render(a, targets=(want_c, want_z, None))
+    ol.oracle_render(b, targets=(want_c, want_z, None))
+    color, z, _ = ol.new_targets(a)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(a, color, z)
+    renderer.render_scene_host(b, color, z)
+    d = diff(want_c, want_z, color, z, a.clear_depth)
+    assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), d
+
+
+@pytest.mark.parametrize("w,h", [(1001, 333), (70, 45), (1922, 1081)])
+def test_odd_sizes_and_pitches(renderer, w, h):
+    """Widths that are not a multiple of 4 pixels and padded host pitches (Buffer->Pitch,
+    Commands->Width) take the non-bulk tile path."""
+    s = sc.triangle_soup("odd", 0x71 + w, 6_000, w, h, 1.5, min(w, h) / 6.0)
+    want = ol.oracle_render(s)
+    cbuf = np.full((h, w + 13), 0xDEADBEEF, np.uint32)
+    zbuf = np.full((h, w + 5), 123.0, np.float32)
+    color, z = cbuf[:, :w], zbuf[:, :w]
+    color[:] = s.clear_color
+    z[:] = s.clear_depth
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z)
+    d = diff(want["color"], want["z"], color, z, s.clear_depth)
+    assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), d
+    assert (cbuf[:, w:] == 0xDEADBEEF).all() and (zbuf[:, w:] == 123.0).all()    # padding untouched
+
+
+def _device_render(renderer, s, tile, first, rows, world=None):
+    """Render rows [first, first+rows) of scene s into a band-sized device target via the device
+    API (what one GPU of the C4 band split does)."""
+    import torch
+    wpad = (s.width + 63) // 64 * 64
+    dev = torch.device("cuda", 0)
+    d_pos = torch.from_numpy(s.positions).to(dev)
+    d_col = torch.from_numpy(s.colors).to(dev)
+    d_nrm = torch.from_numpy(s.normals).to(dev)
+    color = torch.full((max(rows, 1), wpad), s.clear_color, dtype=torch.int32, device=dev)
+    depth = torch.full((max(rows, 1), wpad), s.clear_depth, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    mesh = api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), s.triangle_count,
+                           api.v3(*s.object_p))
+    cmd, keep = api.make_commands(s)
+    tgt = api.device_target(color.data_ptr(), depth.data_ptr(), s.width, s.height, wpad * 4, wpad, first, rows)
+    renderer.set_tile(*tile)
+    renderer.render_device([mesh], cmd, tgt)
+    renderer.sync()
+    return color[:rows, :s.width].cpu().numpy().view(np.uint32), depth[:rows, :s.width].cpu().numpy()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_screen_space_bands_reassemble_the_frame(renderer, world):
+    """C4-style split on one GPU: each band rendered separately (BandFirstRow/BandRows) from the
+    full triangle list, stacked -> identical to the single-target oracle frame."""
+    s = sc.triangle_soup("bands", 0x44, 30_000, 1280, 720, 2.0, 50.0)
+    want = ol.oracle_render(s)
+    colors, depths = [], []
+    for rank in range(world):
+        first, rows = shard.band_rows(s.height, world, rank, 32)
+        c, z = _device_render(renderer, s, (64, 32), first, rows)
+        colors.append(c); depths.append(z)
+    color, z = np.concatenate(colors), np.concatenate(depths)
+    d = diff(want["color"], want["z"], color, z, s.clear_depth)
+    assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), d
+
+
+def test_clear_device_and_stats(renderer):
+    import torch
+    dev = torch.device("cuda", 0)
+    color = torch.zeros((64, 128), dtype=torch.int32, device=dev)
+    depth = torch.zeros((64, 128), dtype=torch.float32, device=dev)
+    tgt = api.device_target(color.data_ptr(), depth.data_ptr(), 100, 64, 512, 128, 0, 64)
+    renderer.clear_device(tgt, 0x11223344, -5.0)
+    renderer.sync()
+    assert (color[:, :100].cpu().numpy() == 0x11223344).all() and (depth[:, :100].cpu().numpy() == -5.0).all()
+    assert (color[:, 100:].cpu().numpy() == 0).all()
+    s = sc.triangle_soup("st", 3, 1000, 640, 360, 2.0, 10.0)
+    check(renderer, s)
+    st = renderer.stats()
+    assert st["Triangles"] == 1000 and st["Binned"] > 900 and st["Spans"] >= st["Segments"] > 0
+    assert st["TilePairs"] >= st["Spans"] and st["KernelLaunches"] > 0
+
+
+def test_unsupported_and_invalid_inputs_return_codes(renderer):
+    s = sc.triangle_soup("e", 5, 10, 64, 64, 2.0, 8.0)
+    color, z, _ = ol.new_targets(s)
+    s.lights = []                                            # LightCount == 0: colours undefined in the reference
+    with pytest.raises(api.B200RasterError) as e:
+        renderer.render_scene_host(s, color, z)
+    assert e.value.code == api.E_UNSUPPORTED
+    s.lights = [sc.Light()]
+    with pytest.raises(api.B200RasterError) as e:
+        renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL)
+    assert e.value.code == api.E_UNSUPPORTED
+    # Phong object -> unsupported, not silently Gouraud
+    lib = renderer.lib
+    o = api.render_entry_3d_object()
+    o.VertexCount = 3
+    o.PhongShading = 1
+    o.VertexData, o.ColorData, o.NormalData = s.positions.ctypes.data, s.colors.ctypes.data, s.normals.ctypes.data
+    cmd, keep = api.make_commands(s, z.ctypes.data, s.width)
+    bmp = api.loaded_bitmap(s.width, s.height, s.width * 4, color.ctypes.data)
+    assert lib.b200r_render_objects(renderer.ctx, C.byref(o), 1, C.byref(cmd), C.byref(bmp), 0) == api.E_UNSUPPORTED
+    assert lib.b200r_render_objects(renderer.ctx, None, 1, C.byref(cmd), C.byref(bmp), 0) == api.E_INVALID
+    # an empty submission is fine and leaves the targets alone
+    assert lib.b200r_render_objects(renderer.ctx, None, 0, C.byref(cmd), C.byref(bmp), 0) == api.OK
+    assert (z == np.float32(s.clear_depth)).all()
+
+
+def test_growth_of_internal_lists_is_transparent(renderer):
+    """A fresh context sized by a tiny frame must re-issue a big one after growing its span /
+    queue lists (api.cu settle_pending) -- same image, Reruns > 0."""
+    r = Renderer(0)
+    try:
+        tiny = sc.triangle_soup("tiny", 1, 10, 640, 360, 2.0, 4.0)
+        c0, z0, _ = ol.new_targets(tiny)
+        r.render_scene_host(tiny, c0, z0)
+        big = sc.triangle_soup("big", 2, 3000, 640, 360, 30.0, 90.0)
+        check(r, big)
+        assert r.stats()["Reruns"] >= 1
+    finally:
+        r.close()
+
+
+# ---- BASELINE.json sizes -------------------------------------------------------------------------
+def test_c2_full_size(renderer):
+    """Config C2 at full size: 1 M ~10 px triangles, 1920x1080 -- whole frame against the oracle."""
+    s = sc.make_config("c2")
+    want = ol.oracle_render(s, threads=8)
+    assert 14.0e6 < want["stats"]["Fragments"] < 15.6e6
+    check(renderer, s, want=want)
+
+
+def test_c3_full_size(renderer):
+    """Config C3 at full size: 50 k large overlapping triangles, 3840x2160, ~35x overdraw."""
+    s = sc.make_config("c3")
+    want = ol.oracle_render(s, threads=8)
+    assert want["stats"]["Fragments"] > 250e6
+    check(renderer, s, tile=(128, 16), want=want)
+
+
+def test_idempotence_and_order_independence_properties(renderer):
+    """Size-independent properties: rendering the same scene twice changes nothing (equal depth
+    never replaces, projekt.cpp:525), and two disjoint halves submitted as two objects equal one."""
+    s = sc.make_config("c2", 0.2)
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z)
+    c1, z1 = color.copy(), z.copy()
+    renderer.render_scene_host(s, color, z)
+    assert np.array_equal(c1, color) and np.array_equal(z1.view(np.uint32), z.view(np.uint32))
+    nv = s.positions.shape[0]
+    c2, z2, _ = ol.new_targets(s)
+    renderer.render_scene_host(s, c2, z2, splits=[nv // 6 * 3, nv - nv // 6 * 3])
+    assert np.array_equal(c1, c2) and np.array_equal(z1.view(np.uint32), z2.view(np.uint32))
