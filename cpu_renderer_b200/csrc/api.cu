@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -47,6 +48,7 @@ struct FrameWords
     unsigned span_total;
     unsigned extra_total;
     unsigned pad;
+    unsigned zkeys[2];                  // z range of the frame: ordered keys, then {zmax, 1/range} as floats
     unsigned long long counters[2];     // binned triangles, tile pairs
 };
 
@@ -61,6 +63,7 @@ struct b200r_context
     cudaEvent_t total_ready = nullptr;
     std::string error;
     int tile_w = 64, tile_h = 32;
+    int refill_lanes = 8, pend_lanes = 8;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
@@ -136,12 +139,13 @@ static int issue_frame(b200r_context *c)
 {
     const ViewParams &v = c->view;
     const unsigned ntiles = c->ntiles;
+    const unsigned nbins = ntiles*kDepthBuckets;        // one sub-queue per tile and depth bucket
     unsigned *tile_count = (unsigned *)c->tiles.ptr;
-    unsigned *tile_fill = tile_count + ntiles;
-    unsigned *tile_offset = tile_fill + ntiles;
+    unsigned *tile_fill = tile_count + nbins;
+    unsigned *tile_offset = tile_fill + nbins;          // nbins + 1 entries
     FrameWords *words = (FrameWords *)c->words.ptr;
 
-    CU(cudaMemsetAsync(tile_count, 0, (size_t)ntiles*2*sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(tile_count, 0, (size_t)nbins*2*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
 
     const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
@@ -156,15 +160,23 @@ static int issue_frame(b200r_context *c)
     so.seg_capacity = seg_cap;
     so.span_capacity = span_cap;
     so.tile_count = tile_count;
+    so.zrange = reinterpret_cast<const float *>(words->zkeys);
     so.counters = words->counters;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[0], c->stream));
+    for(const MeshParams &m : c->meshes)
+    {
+        launch_zrange(m, words->zkeys, c->stream);
+        if(m.ntri) c->stats.KernelLaunches += 1;
+    }
+    launch_zrange_finish(words->zkeys, c->stream);
+    c->stats.KernelLaunches += 1;
     for(const MeshParams &m : c->meshes)
     {
         launch_setup(v, m, so, c->stream);
         if(m.ntri) c->stats.KernelLaunches += 1;
     }
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[1], c->stream));
-    launch_tile_scan(tile_count, tile_offset, ntiles, &words->pair_total, c->stream);
+    launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, c->stream);
     c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[2], c->stream));
     CU(cudaMemcpyAsync(c->h_words, words, sizeof(FrameWords), cudaMemcpyDeviceToHost, c->stream));
@@ -190,7 +202,6 @@ static int issue_frame(b200r_context *c)
     rp.extra_total = &words->extra_total;
     rp.seg_capacity = seg_cap;
     rp.span_capacity = span_cap;
-    rp.tile_count = tile_count;
     rp.tile_offset = tile_offset;
     rp.pair_list = (const unsigned *)c->pairs.ptr;
     rp.pair_total = &words->pair_total;
@@ -204,6 +215,8 @@ static int issue_frame(b200r_context *c)
     rp.bulk_ok = ((((uintptr_t)c->target.Color) & 15) == 0 && (((uintptr_t)c->target.Depth) & 15) == 0 &&
                   (c->target.ColorPitch & 15) == 0 && ((c->target.DepthStride*4) & 15) == 0 &&
                   (c->target.Width & 3) == 0) ? 1 : 0;
+    rp.refill_lanes = c->refill_lanes;
+    rp.pend_lanes = c->pend_lanes;
     cudaError_t e = launch_raster(rp, c->sm_count, c->stream);
     if(e != cudaSuccess) return fail(c, B200R_E_CUDA, "raster_kernel launch", e);
     c->stats.KernelLaunches += 1;
@@ -276,6 +289,8 @@ int b200r_create(b200r_context **out, int device)
     }
     c->stream = c->own_stream;
     memset(c->h_words, 0, sizeof(FrameWords));
+    if(const char *e = getenv("B200R_REFILL")) c->refill_lanes = std::max(1, std::min(32, atoi(e)));
+    if(const char *e = getenv("B200R_PEND")) c->pend_lanes = std::max(1, std::min(32, atoi(e)));
     *out = c;
     return B200R_OK;
 }
@@ -365,7 +380,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     // first guesses (2.5 segments, 6 spans, 8 queue entries per triangle); all lists grow on demand
     if(c->segs.bytes == 0) CU(c->segs.reserve((size_t)std::max<uint64_t>(total*5/2, 1u << 16)*sizeof(SegInfo)));
     if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*kSpanWords*sizeof(uint32_t)));
-    CU(c->tiles.reserve((size_t)ntiles*3*sizeof(unsigned)));
+    CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1)*sizeof(unsigned)));
     if(c->pairs.bytes == 0)
         CU(c->pairs.reserve((size_t)std::max<uint64_t>(total*8, 1u << 16)*sizeof(unsigned)));
 
@@ -550,16 +565,17 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     if(rc != B200R_OK) return rc;
     v.tiles_x = 1; v.tiles_y = 1; v.tile_w = 1 << 21; v.tile_h = 1 << 21;
     CU(c->recs.reserve((size_t)tris*kRecWords*sizeof(uint32_t)));
-    CU(c->tiles.reserve(3*sizeof(unsigned)));
+    CU(c->tiles.reserve(((size_t)kDepthBuckets*3 + 1)*sizeof(unsigned)));
     unsigned *tile_count = (unsigned *)c->tiles.ptr;
     FrameWords *words = (FrameWords *)c->words.ptr;
-    CU(cudaMemsetAsync(tile_count, 0, 3*sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(tile_count, 0, ((size_t)kDepthBuckets*3 + 1)*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
     SetupOutputs so;
     so.recs = (uint32_t *)c->recs.ptr; so.spans = nullptr; so.segs = nullptr;
     so.seg_total = &words->seg_total; so.span_total = &words->span_total; so.extra_total = &words->extra_total;
     so.seg_capacity = 0; so.span_capacity = 0;
     so.tile_count = tile_count; so.counters = words->counters;
+    so.zrange = reinterpret_cast<const float *>(words->zkeys);
     MeshParams mp;
     mp.pos = meshes[0].Positions; mp.col = meshes[0].Colors; mp.nrm = meshes[0].Normals;
     mp.ntri = tris; mp.px = obj->P.x; mp.py = obj->P.y; mp.pz = obj->P.z; mp.prim_base = 0;

@@ -55,6 +55,7 @@ tile_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offs
     __syncthreads();
     unsigned run = warp_sums[warp] + (incl - sum);
     for(unsigned i = lo; i < hi; ++i) { offset[i] = run; run += count[i]; }
+    if(hi == n && lo <= n) offset[n] = run;             // end entry (several threads may write the same total)
 }
 
 // One thread per segment and tile column: reserve nrows consecutive slots of that tile's list
@@ -71,9 +72,10 @@ scatter_kernel(const ScatterParams p)
         const unsigned seg = (i < nseg) ? i : p.seg_capacity - 1u - (i - nseg);
         const SegInfo si = p.segs[seg];
         const int tx0 = si.tx & 0xffff, tx1 = si.tx >> 16;
+        const unsigned trow = si.tile_row & 0xffffffu, bucket = si.tile_row >> 24;
         for(int tx = tx0; tx <= tx1; ++tx)
         {
-            const unsigned tile = si.tile_row*(unsigned)p.tiles_x + (unsigned)tx;
+            const unsigned tile = (trow*(unsigned)p.tiles_x + (unsigned)tx)*kDepthBuckets + bucket;
             const unsigned slot = p.tile_offset[tile] + atomicAdd(&p.tile_fill[tile], si.nrows);
             for(unsigned r = 0; r < si.nrows; ++r) p.pair_list[slot + r] = si.span_base + r;
         }

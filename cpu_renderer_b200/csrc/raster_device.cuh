@@ -14,6 +14,10 @@
 namespace b200r {
 
 constexpr int kMaxLights = 8;
+// Every tile's span queue is split into kDepthBuckets sub-queues by the camera-space depth of the
+// owning triangle, nearest first.  Processing order never changes the image (the depth rule is
+// order independent); near-to-far order only makes the cheap early depth test fail more often.
+constexpr int kDepthBuckets = 8;
 
 struct DevLight { float px, py, pz; float ir, ig, ib, ia; };
 
@@ -57,14 +61,15 @@ enum { R_NEDGES = 0, R_FIRSTROW = 1, R_MAXY = 2, R_PRIM = 3, R_EDGE0 = 4 };
 // increments.  The raster kernel only replays the per-pixel adds and depth-tests.
 constexpr int kSpanWords = 16;      // 64 bytes = 4 float4
 constexpr int kSpanVec4 = kSpanWords/4;
-enum { P_PRIM = 0, P_Y = 1, P_MINX = 2, P_MAXX = 3, P_Z = 4, P_C = 5, P_ZI = 9, P_CI = 10, P_FLAGS = 14 };
+enum { P_PRIM = 0, P_Y = 1, P_MINX = 2, P_MAXX = 3, P_Z = 4, P_C = 5, P_ZI = 9, P_CI = 10, P_FLAGS = 14, P_ZUB = 15 };
+// P_ZUB: an upper bound of every depth value the span can produce (see span_depth_bound)
 constexpr unsigned kSpanNonFinite = 1u;   // colours may be NaN/Inf/huge -> guarded pack
 
 // Segment: the consecutive spans of one triangle that share one pair of active edges and lie in
 // one tile-row band; the unit the binner scatters (its spans are contiguous in the span array).
 struct SegInfo
 {
-    unsigned tile_row;          // band-relative tile row
+    unsigned tile_row;          // band-relative tile row | depth bucket << 24
     unsigned tx;                // tx0 | tx1 << 16 (tx0 > tx1: touches no tile)
     unsigned span_base;         // index of its first span record
     unsigned nrows;             // number of span records
@@ -78,8 +83,7 @@ struct RasterParams
     const unsigned *span_total;
     const unsigned *extra_total;
     unsigned seg_capacity, span_capacity;
-    const unsigned *tile_count;
-    const unsigned *tile_offset;
+    const unsigned *tile_offset;    // [tile*kDepthBuckets + bucket], plus one end entry
     const unsigned *pair_list;
     const unsigned *pair_total; // device word: total (triangle,tile) pairs this frame
     unsigned pair_capacity;
@@ -90,6 +94,8 @@ struct RasterParams
     int color_pitch_words;      // u32 per row
     int depth_stride;           // floats per row
     int bulk_ok;                // rows may be moved with cp.async.bulk (16-byte aligned)
+    int refill_lanes;           // idle lanes of a warp that trigger a refill from the span queue
+    int pend_lanes;             // parked lanes of a warp that trigger the depth-pass path
 };
 
 // Every consumer of the lists uses the same test, so a frame whose lists overflowed is skipped
@@ -180,11 +186,16 @@ struct SetupOutputs
     unsigned *extra_total;      // alias pixels: one-pixel span + segment each, allocated downwards
                                 // from the END of the span / segment arrays
     unsigned seg_capacity, span_capacity;
-    unsigned *tile_count;
+    unsigned *tile_count;       // [tile*kDepthBuckets + bucket]
+    const float *zrange;        // device: {largest camera z, 1/(largest - smallest)} of this frame's vertices
     unsigned long long *counters;   // [0] binned triangles, [1] tile pairs
 };
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
+// zrange[0..1] start as {-inf as ordered key, +inf as ordered key}; zrange_finish turns them into
+// {zmax, 1/(zmax - zmin)}
+void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s);
+void launch_zrange_finish(unsigned *zkeys, cudaStream_t s);
 void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
                       unsigned *pair_total, cudaStream_t s);
 struct ScatterParams

@@ -87,6 +87,7 @@ raster_kernel(const RasterParams p)
     static_assert(NPIX % NT == 0, "tile must divide evenly over the CTA");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned s_tile, s_ticket;
+    __shared__ float s_rowmin[TH];                        // lower bound of the depth of each tile row
 
     if(lists_overflowed(*p.seg_total, *p.span_total, *p.extra_total, *p.pair_total, p.seg_capacity, p.span_capacity,
                         p.pair_capacity)) return;                          // host grows the lists and re-issues
@@ -110,8 +111,9 @@ raster_kernel(const RasterParams p)
         __syncthreads();
         const unsigned tile_id = s_tile;
         if(tile_id >= p.ntiles) break;
-        const unsigned cnt = p.tile_count[tile_id];
-        const unsigned off = p.tile_offset[tile_id];
+        // the tile's queue = its kDepthBuckets sub-queues, contiguous and nearest bucket first
+        const unsigned off = p.tile_offset[tile_id*kDepthBuckets];
+        const unsigned cnt = p.tile_offset[(tile_id + 1)*kDepthBuckets] - off;
         const int tx = (int)(tile_id % (unsigned)p.v.tiles_x), ty = (int)(tile_id / (unsigned)p.v.tiles_x);
         const int x0 = tx*TW;
         const int yb = ty*TH;                              // band-relative first row
@@ -161,10 +163,34 @@ raster_kernel(const RasterParams p)
         }
         __syncthreads();
 
+        // Conservative per-row depth floor for span culling.  Depth only ever rises, so a value
+        // read while other warps update pixels is at worst too low; recomputed now and every
+        // kFloorEvery spans.  A span whose depth upper bound (set-up kernel) is strictly below its
+        // row's floor cannot win or tie any pixel and is skipped without walking it.
+        constexpr unsigned kFloorEvery = 256;
+        const int warp_id = tid >> 5;
+        auto refresh_row_floor = [&](int first_row, int row_step)
+        {
+            for(int r = first_row; r < TH; r += row_step)
+            {
+                float m = __int_as_float(0x7f800000);
+                for(int c = lane; c < TW; c += 32)
+                {
+                    const float zz = lds_depth(smem_addr(tile + r*TW + c));
+                    if(c < cols && zz < m) m = zz;                // a NaN depth never lets anything pass: no constraint
+                }
+#pragma unroll
+                for(int d = 16; d >= 1; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
+                if(lane == 0) s_rowmin[r] = (r < rows) ? m : __int_as_float(0x7f800000);
+            }
+        };
+        refresh_row_floor(warp_id, WARPS);
+        __syncthreads();
+
         // ---------------- rasterise the tile's span queue: persistent lanes --------------------
         {
-            constexpr int kRefill = 8;                     // idle lanes that trigger a refill
-            constexpr int kPend = 8;                       // parked lanes that trigger the update path
+            const int kRefill = p.refill_lanes;            // idle lanes that trigger a refill
+            const int kPend = p.pend_lanes;                // parked lanes that trigger the update path
             constexpr unsigned FULL = 0xffffffffu;
             const uint32_t tile_addr = smem_addr(tile);
             const int xlast = x0 + cols - 1;
@@ -212,8 +238,10 @@ raster_kernel(const RasterParams p)
                     // ---- idle lanes take the next spans of the queue: one ticket per warp ----
                     const int leader = __ffs(need_mask) - 1;
                     unsigned base = 0;
-                    if(lane == leader) base = atomicAdd(&s_ticket, (unsigned)__popc(need_mask));
+                    const unsigned take = (unsigned)__popc(need_mask);
+                    if(lane == leader) base = atomicAdd(&s_ticket, take);
                     base = __shfl_sync(FULL, base, leader);
+                    if(base/kFloorEvery != (base + take)/kFloorEvery && base < cnt) refresh_row_floor(0, 1);
                     if(need)
                     {
                         const unsigned idx = base + (unsigned)__popc(need_mask & ((1u << lane) - 1u));
@@ -232,6 +260,7 @@ raster_kernel(const RasterParams p)
                             const int xe = min(maxx, xlast);
                             x = minx;
                             n_left = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
+                            if(q3.w < s_rowmin[y - ys0]) n_left = 0;          // cannot win or tie anywhere in its row
                             rowaddr = tile_addr + (uint32_t)(((y - ys0)*TW - x0)*16);
                         }
                         else

@@ -21,6 +21,8 @@
 #include "raster_device.cuh"
 #include "edge_walk.cuh"
 
+#include <algorithm>
+
 namespace b200r {
 
 constexpr int kSetupThreads = 128;
@@ -81,6 +83,63 @@ __device__ __forceinline__ void light_vertex(V3 cam, V3 nrm, const float col[4],
     }
 #pragma unroll
     for(int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+// Upper bound of every depth value of a span: z_k = fl(z_{k-1} + zi), k <= n.  Each add rounds by
+// at most half an ulp of a value no larger than |z0| + n|zi| (plus the bound itself), so
+//   z_k <= max(z0, z0 + n*zi) + n * 2^-23 * (|z0| + n*|zi|)        (2x the worst case),
+// evaluated with every operation rounded towards +inf.  NaN / Inf input gives +inf or NaN: the
+// raster kernel culls only on a strict, ordered "bound < row minimum", so such spans are kept.
+__device__ __forceinline__ float span_depth_bound(float z0, float zi, int n)
+{
+    const float fn = (float)max(n, 0);
+    const float end = __fadd_ru(z0, __fmul_ru(fn, zi));
+    const float mag = __fadd_ru(fabsf(z0), __fmul_ru(fn, fabsf(zi)));
+    const float slack = __fmul_ru(__fmul_ru(fn, 1.1920929e-7f), mag);
+    return __fadd_ru(__fadd_ru(fmaxf(z0, end), slack), 1.0e-30f);    // absolute term: subnormal rounding
+}
+
+// ---- z range of a frame's vertices (for the depth buckets): ordered-integer keys ----
+__device__ __forceinline__ unsigned float_key(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256)
+zrange_kernel(MeshParams m, unsigned *zkeys)
+{
+    // zkeys[0] = max key, zkeys[1] = max of ~key (i.e. ~min key) over camera z = vertex z + P.z
+    // (finite values only); both start at 0 so one memset initialises them
+    unsigned kmax = 0u, kmin = 0xffffffffu;
+    const size_t nv = (size_t)m.ntri*3;
+    for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x*blockDim.x)
+    {
+        const float z = __ldg(m.pos + i*3 + 2) + m.pz;
+        if(fabsf(z) < 3.0e38f) { const unsigned k = float_key(z); kmax = max(kmax, k); kmin = min(kmin, k); }
+    }
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    if((threadIdx.x & 31) == 0 && kmax != 0u) { atomicMax(&zkeys[0], kmax); atomicMax(&zkeys[1], ~kmin); }
+}
+
+__global__ void zrange_finish_kernel(unsigned *zkeys)
+{
+    const unsigned kmax = zkeys[0], kmin = ~zkeys[1];
+    float zmax = 0.0f, inv = 0.0f;
+    if(kmax != 0u && kmax >= kmin)
+    {
+        zmax = key_float(kmax);
+        const float range = zmax - key_float(kmin);
+        inv = (range > 0.0f) ? 1.0f/range : 0.0f;
+        if(!(fabsf(inv) < 3.0e38f)) inv = 0.0f;
+    }
+    reinterpret_cast<float *>(zkeys)[0] = zmax;
+    reinterpret_cast<float *>(zkeys)[1] = inv;
 }
 
 __global__ void __launch_bounds__(kSetupThreads)
@@ -333,6 +392,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         unsigned seg_span0 = 0;
         unsigned pairs = 0;
         const unsigned prim = m.prim_base + base + t;
+        // depth bucket of the whole triangle: 0 = nearest (largest camera z, projekt.cpp:525)
+        unsigned bucket = 0;
+        {
+            const float ztri = fmaxf(fmaxf(s_pos[t*9 + 2], s_pos[t*9 + 5]), s_pos[t*9 + 8]) + m.pz;
+            const float f = (out.zrange[0] - ztri)*out.zrange[1]*(float)kDepthBuckets;
+            if(f > 0.0f) bucket = (unsigned)min((int)f, kDepthBuckets - 1);
+        }
 
         auto close_segment = [&]()
         {
@@ -340,12 +406,14 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             int tx0 = 1, tx1 = 0;
             if(seg_minx <= seg_maxx) { tx0 = seg_minx/v.tile_w; tx1 = seg_maxx/v.tile_w; }
             SegInfo si;
-            si.tile_row = (unsigned)((seg_y0 - v.band_y0)/v.tile_h);
+            const unsigned trow = (unsigned)((seg_y0 - v.band_y0)/v.tile_h);
+            si.tile_row = trow | (bucket << 24);
             si.tx = (unsigned)tx0 | ((unsigned)tx1 << 16);
             si.span_base = seg_span0;
             si.nrows = span - seg_span0;
             out.segs[seg] = si;
-            for(int tx = tx0; tx <= tx1; ++tx) atomicAdd(&out.tile_count[si.tile_row*v.tiles_x + tx], si.nrows);
+            for(int tx = tx0; tx <= tx1; ++tx)
+                atomicAdd(&out.tile_count[(trow*v.tiles_x + tx)*kDepthBuckets + bucket], si.nrows);
             if(tx0 <= tx1) pairs += (unsigned)(tx1 - tx0 + 1)*si.nrows;
             ++seg; open = false;
         };
@@ -408,11 +476,12 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                                 Q[0] = make_float4(__uint_as_float(prim), __int_as_float(ay), __int_as_float(0), __int_as_float(0));
                                 Q[1] = make_float4(az, a0, a1, a2);
                                 Q[2] = make_float4(a3, 0.0f, 0.0f, 0.0f);
-                                Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), 0.0f);
+                                Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), az);
                                 SegInfo si;
-                                si.tile_row = (unsigned)((ay - v.band_y0)/v.tile_h); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
+                                const unsigned trow = (unsigned)((ay - v.band_y0)/v.tile_h);
+                                si.tile_row = trow | (bucket << 24); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
                                 out.segs[asg] = si;
-                                atomicAdd(&out.tile_count[si.tile_row*v.tiles_x], 1u);
+                                atomicAdd(&out.tile_count[(trow*v.tiles_x)*kDepthBuckets + bucket], 1u);
                                 pairs += 1u;
                             }
                         }
@@ -424,7 +493,8 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
                         Q[1] = make_float4(z, c0, c1, c2);
                         Q[2] = make_float4(c3, zi, i0, i1);
-                        Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), 0.0f);
+                        Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u),
+                                           span_depth_bound(z, zi, maxx - minx));
                         ++span;
                         if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
                     }
@@ -466,6 +536,18 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         atomicAdd(&out.counters[0], (unsigned long long)s_binned);
         atomicAdd(&out.counters[1], (unsigned long long)s_pairs);
     }
+}
+
+void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s)
+{
+    if(m.ntri == 0) return;
+    unsigned blocks = (unsigned)std::min<size_t>(((size_t)m.ntri*3 + 255)/256, 148*8);
+    zrange_kernel<<<blocks, 256, 0, s>>>(m, zkeys);
+}
+
+void launch_zrange_finish(unsigned *zkeys, cudaStream_t s)
+{
+    zrange_finish_kernel<<<1, 1, 0, s>>>(zkeys);
 }
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s)
