@@ -36,7 +36,13 @@ sys.path.insert(0, ROOT)
 METRICS = {
     "c2": ("Mtriangles/s", "C2: 1M ~10px triangles, 1920x1080, depth-tested Gouraud (setup/binning bound)"),
     "c3": ("Mpixels/s", "C3: 50k large overlapping triangles, 3840x2160, ~35x overdraw (fill bound)"),
+    "c4": ("Mpixels/s", "C4: 20M triangles, 16384x16384, screen-space tile bands across the GPUs, NCCL gather"),
+    "c5": ("Mtriangles/s", "C5: 256 views of a 2M-triangle mesh (ConstructSphere, StepCount 708), 1920x1080, frame-parallel"),
 }
+# c2/c3: every rank renders its own frame (weak).  c4: one frame split in row bands, c5: a fixed
+# set of 256 views split over the ranks (strong: the total work does not grow with N).
+SCALING = {"c2": "weak", "c3": "weak", "c4": "strong", "c5": "strong"}
+C5_VIEWS = 256
 
 
 def log(*a):
@@ -53,12 +59,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(config):
-    """dram bytes per raster_kernel launch from the committed ncu capture, if any."""
+def ncu_traffic(config, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture, if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(config)
+            return json.load(open(p)).get(config, {}).get(kernel)
         except Exception:
             return None
     return None
@@ -113,11 +119,27 @@ class ClockSampler:
         return out
 
 
-def build_scene(config, rank):
+def build_scene(config, rank, scale=1.0):
     from cpu_renderer_b200 import scene as sc
+    if config == "c5":
+        step = max(4, int(round(708 * scale ** 0.5)))
+        pos, col, nrm, uvs = sc.construct_sphere(step)
+        return sc.sphere_scene(pos, col, nrm, uvs, 1920, 1080, 500.0, name="c5")
     cfg = dict(sc.CONFIGS[config])
-    cfg["seed"] = cfg["seed"] + 0x1000 * rank       # every rank renders its own frame
+    cfg["count"] = max(1, int(round(cfg["count"] * scale)))
+    if config in ("c2", "c3"):
+        cfg["seed"] = cfg["seed"] + 0x1000 * rank   # every rank renders its own frame
     return sc.triangle_soup(config, **cfg)
+
+
+def c5_view(i):
+    """View i of config C5: the reference API has no camera rotation, only Object->P and the
+    pin-hole distance (projekt.cpp:3900, 74-93), so a view is a (P, DistanceAboveTarget) pair on a
+    fixed spiral."""
+    import math
+    a = 2.0 * math.pi * i / 32.0
+    r = 0.15 + 0.45 * i / C5_VIEWS
+    return (r * math.cos(a), 0.6 * r * math.sin(a), 0.0), 3.0 + 1.5 * i / C5_VIEWS
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -129,12 +151,8 @@ def run_reference(args):
     import oracle_lib as ol
     from cpu_renderer_b200 import scene as sc
     unit, workload = METRICS[args.config]
-    scene = build_scene(args.config, 0)
-    # bounded sample: a prefix of the frame's triangle list
-    sample = min(scene.triangle_count, args.ref_sample or (250_000 if args.config == "c2" else 4000))
-    s = sc.Scene(scene.name, scene.width, scene.height, scene.transform, scene.positions[:sample * 3],
-                 scene.colors[:sample * 3], scene.normals[:sample * 3], scene.uvs[:sample * 3])
-    threads = args.ref_threads or (os.cpu_count() or 1)
+    scene = build_scene(args.config, 0, args.scale)
+    s, sample, threads = cpu_sample(args.config, scene, sc, args.ref_sample, args.ref_threads)
     kind = "reference" if ol.ref_available() else "port"
     res = time_cpu(ol, s, threads, args.steps, args.warmup, kind)
     ms = res["ms_per_step"]
@@ -143,7 +161,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": unit, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": SCALING[args.config], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "triangles_per_step": sample, "width": scene.width,
                    "height": scene.height},
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind,
@@ -152,6 +170,29 @@ def run_reference(args):
         "host": {"cpu_count": os.cpu_count(), "model": cpu_model()},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_sample(config, scene, sc, sample=0, threads=0):
+    """Bounded CPU sample of a config: a prefix of the frame's triangle list (for c5: of view 0)."""
+    import copy
+    default = {"c2": 250_000, "c3": 4000, "c4": 250_000, "c5": 250_000}[config]
+    sample = min(scene.triangle_count, sample or default)
+    if config == "c5":
+        # a mesh is ordered: take every k-th triangle so the sample covers the whole sphere
+        k = max(1, scene.triangle_count // sample)
+        pick = (np.arange(sample) * k)[:, None] * 3 + np.arange(3)[None, :]
+        pick = pick.reshape(-1)
+        arrays = [np.ascontiguousarray(a[pick]) for a in (scene.positions, scene.colors, scene.normals, scene.uvs)]
+    else:
+        arrays = [a[:sample * 3] for a in (scene.positions, scene.colors, scene.normals, scene.uvs)]
+    s = sc.Scene(scene.name, scene.width, scene.height, copy.copy(scene.transform), *arrays,
+                 scene.object_p, scene.ambient, scene.lights)
+    if config == "c5":
+        s.object_p, s.transform.distance_above_target = c5_view(0)
+    # every worker owns a private colour/depth pair: 2 GiB each at 16384^2, so c4 uses few workers
+    cap = 4 if config == "c4" else 1 << 30
+    threads = threads or min(os.cpu_count() or 1, cap)
+    return s, sample, threads
 
 
 def cpu_model():
@@ -228,34 +269,65 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    from cpu_renderer_b200 import shard
+    import copy
     unit, workload = METRICS[args.config]
-    scene = build_scene(args.config, rank)
+    cfgname = args.config
+    scene = build_scene(cfgname, rank, args.scale)
     ntri, W, H = scene.triangle_count, scene.width, scene.height
     K, Wm = args.steps, args.warmup
     wpad = (W + 63) // 64 * 64
 
     stream = torch.cuda.Stream(device=dev)
     r = api.Renderer(local_rank)
-    if args.tile:
-        tw, th = (int(x) for x in args.tile.split("x"))
-        r.set_tile(tw, th)
+    tile = args.tile or {"c3": "128x16", "c4": "64x32"}.get(cfgname, "64x32")
+    tw, th = (int(x) for x in tile.split("x"))
+    r.set_tile(tw, th)
     r.set_stream(stream.cuda_stream)
 
     d_pos = torch.from_numpy(scene.positions).to(dev)
     d_col = torch.from_numpy(scene.colors).to(dev)
     d_nrm = torch.from_numpy(scene.normals).to(dev)
-    mesh = api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*scene.object_p))
-    cmd, keep = api.make_commands(scene)
-    nsets = max(K, Wm, 1)
-    colors = [torch.empty((H, wpad), dtype=torch.int32, device=dev) for _ in range(nsets)]
-    depths = [torch.empty((H, wpad), dtype=torch.float32, device=dev) for _ in range(nsets)]
-    targets = [api.device_target(c.data_ptr(), z.data_ptr(), W, H, wpad * 4, wpad, 0, H)
+
+    # ---- the frames this rank renders in one step ------------------------------------------
+    band_first, band_rows = 0, H
+    frames = []                                   # (device_mesh, game_render_commands, keepalive)
+    if cfgname == "c4":
+        band_first, band_rows = shard.band_rows(H, world, rank, th)
+    if cfgname == "c5":
+        for vi in shard.frame_range(C5_VIEWS, world, rank):
+            P, D = c5_view(vi)
+            sv = copy.copy(scene)
+            sv.transform = copy.copy(scene.transform)
+            sv.transform.distance_above_target = D
+            cmd_v, keep_v = api.make_commands(sv)
+            frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*P)),
+                           cmd_v, keep_v))
+    else:
+        cmd0, keep0 = api.make_commands(scene)
+        frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri,
+                                       api.v3(*scene.object_p)), cmd0, keep0))
+    mesh, cmd, keep = frames[0]
+    # c2/c3: one pre-cleared target pair per timed frame (clear outside the timed region).
+    # c4/c5: one pair, cleared inside the step (a 16K^2 pair is 2 GiB; a real frame clears anyway).
+    clear_in_step = cfgname in ("c4", "c5")
+    nsets = 1 if clear_in_step else max(K, Wm, 1)
+    colors = [torch.empty((band_rows, wpad), dtype=torch.int32, device=dev) for _ in range(nsets)]
+    depths = [torch.empty((band_rows, wpad), dtype=torch.float32, device=dev) for _ in range(nsets)]
+    targets = [api.device_target(c.data_ptr(), z.data_ptr(), W, H, wpad * 4, wpad, band_first, band_rows)
                for c, z in zip(colors, depths)]
 
     def clear_all():
         for c, z in zip(colors, depths):
             c.fill_(scene.clear_color); z.fill_(scene.clear_depth)
         torch.cuda.synchronize()
+
+    def step(i):
+        t = targets[i % nsets]
+        for (m_, c_, _) in frames:
+            if clear_in_step:
+                r.clear_device(t, scene.clear_color, scene.clear_depth)
+            r.render_device([m_], c_, t)
 
     def barrier():
         if world > 1:
@@ -267,7 +339,7 @@ def run_ours(args):
     clear_all()
     with torch.cuda.stream(stream):
         for i in range(Wm):
-            r.render_device([mesh], cmd, targets[i % nsets])
+            step(i)
         r.sync()
     clear_all()                                   # every timed frame starts from cleared targets
     launches0 = r.stats()["KernelLaunches"]
@@ -276,7 +348,7 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for i in range(K):
-            r.render_device([mesh], cmd, targets[i])
+            step(i)
         ev1.record(stream)
         r.sync()
     torch.cuda.synchronize(); barrier()
@@ -295,10 +367,11 @@ def run_ours(args):
     t_end = time.time() + 1.0
     with torch.cuda.stream(stream):
         i = 0
-        while i < K or (time.time() < t_end and i < 64 * K):
+        while i < min(K, 8) or (time.time() < t_end and i < 64 * K):
             if i % nsets == 0 and i:
                 clear_all()
-            r.render_device([mesh], cmd, targets[i % nsets])
+            m_, c_, _ = frames[i % len(frames)]
+            r.render_device([m_], c_, targets[i % nsets])
             for k, v in r.stage_ms().items():
                 stage[k].append(v)
             i += 1
@@ -310,45 +383,83 @@ def run_ours(args):
     with_gather = None
     if world > 1:
         clear_all()
-        gl = [torch.empty_like(colors[0]) for _ in range(world)] if rank == 0 else None
+        if cfgname == "c4":
+            gather = lambda t: shard.gather_bands(t, H, world, rank, th, dst=0)      # noqa: E731
+        else:
+            gl = [torch.empty_like(colors[0]) for _ in range(world)] if rank == 0 else None
+            gather = lambda t: dist.gather(t, gl, dst=0)                             # noqa: E731
         with torch.cuda.stream(stream):
-            for _ in range(3):                         # communicator set-up and warm-up, untimed
-                dist.gather(colors[0], gl, dst=0)
+            for _ in range(2):                         # communicator set-up and warm-up, untimed
+                gather(colors[0])
         barrier(); torch.cuda.synchronize()
+        kg = min(K, 10)
         with torch.cuda.stream(stream):
             ev0.record(stream)
-            for i in range(K):
-                r.render_device([mesh], cmd, targets[i])
-                dist.gather(colors[i], gl, dst=0)     # stream-ordered after this frame's kernels
+            for i in range(kg):
+                step(i)
+                gather(colors[i % nsets])              # stream-ordered after this step's kernels
             ev1.record(stream)
         torch.cuda.synchronize(); barrier()
-        g = torch.tensor([ev0.elapsed_time(ev1) / K], dtype=torch.float64, device=dev)
+        g = torch.tensor([ev0.elapsed_time(ev1) / kg], dtype=torch.float64, device=dev)
         dist.all_reduce(g, op=dist.ReduceOp.MAX)
-        with_gather = {"ms_per_step": float(g.item()), "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1))}
+        with_gather = {"ms_per_step": float(g.item()), "what": "NCCL gather of the finished colour image(s) to rank 0 after every step",
+                       "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1))}
 
-    # ---- end to end through the host-pointer C ABI (pinned host buffers) --------------------
-    r.set_stream(0)
-    e2e_steps = min(K, 10)
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()      # noqa: E731
+    # ---- end to end: host buffers in, host buffers out, copies inside the timed region ---------
+    pin = lambda a: torch.from_numpy(a).pin_memory()              # noqa: E731
     from cpu_renderer_b200 import scene as sc
-    hs = sc.Scene(scene.name, W, H, scene.transform, pin(scene.positions), pin(scene.colors),
-                  pin(scene.normals), scene.uvs, scene.object_p, scene.ambient, scene.lights)
-    hcol = [torch.full((H, W), scene.clear_color, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-            for _ in range(e2e_steps + 1)]
-    hz = [torch.full((H, W), scene.clear_depth, dtype=torch.float32).pin_memory().numpy()
-          for _ in range(e2e_steps + 1)]
-    r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps])       # warm-up (allocations)
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        r.render_scene_host(hs, hcol[i], hz[i])
-    torch.cuda.synchronize()
-    e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
+    if not clear_in_step:
+        # c2/c3: the reference-facing call b200r_render_objects (H2D vertices + targets, kernels, D2H targets)
+        r.set_stream(0)
+        e2e_steps = min(K, 10)
+        hs = sc.Scene(scene.name, W, H, scene.transform, pin(scene.positions).numpy(), pin(scene.colors).numpy(),
+                      pin(scene.normals).numpy(), scene.uvs, scene.object_p, scene.ambient, scene.lights)
+        hcol = [torch.full((H, W), scene.clear_color, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                for _ in range(e2e_steps + 1)]
+        hz = [torch.full((H, W), scene.clear_depth, dtype=torch.float32).pin_memory().numpy()
+              for _ in range(e2e_steps + 1)]
+        r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps])       # warm-up (allocations)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            r.render_scene_host(hs, hcol[i], hz[i])
+        torch.cuda.synchronize()
+        e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
+        covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
+        e2e_api = "b200r_render_objects (host pointers, pinned)"
+        h2d_bytes, d2h_bytes = int(ntri * 120 + 2 * W * H * 4), int(2 * W * H * 4)
+    else:
+        # c4/c5: vertices from pinned host memory every step, b200r_clear_device + b200r_render_device
+        # per frame (band / view), colour and depth of every frame read back to pinned host memory
+        e2e_steps = min(K, 3)
+        h_pos, h_col, h_nrm = pin(scene.positions), pin(scene.colors), pin(scene.normals)
+        h_c = torch.empty((band_rows, wpad), dtype=torch.int32).pin_memory()
+        h_z = torch.empty((band_rows, wpad), dtype=torch.float32).pin_memory()
+
+        def e2e_once():
+            with torch.cuda.stream(stream):
+                d_pos.copy_(h_pos, non_blocking=True); d_col.copy_(h_col, non_blocking=True)
+                d_nrm.copy_(h_nrm, non_blocking=True)
+                for (m_, c_, _) in frames:
+                    r.clear_device(targets[0], scene.clear_color, scene.clear_depth)
+                    r.render_device([m_], c_, targets[0])
+                    h_c.copy_(colors[0], non_blocking=True); h_z.copy_(depths[0], non_blocking=True)
+                r.sync()
+            stream.synchronize()
+        e2e_once()
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_once()
+        torch.cuda.synchronize()
+        e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
+        covered = int((h_z.numpy()[:, :W] != np.float32(scene.clear_depth)).sum())
+        e2e_api = "pinned H2D of the vertex streams + b200r_clear_device/b200r_render_device per frame + D2H of colour and depth"
+        h2d_bytes, d2h_bytes = int(ntri * 120), int(len(frames) * 2 * band_rows * wpad * 4)
     e_t = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e_t.item())
-    covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
 
     clocks = sampler.stop() if sampler else None
     if rank != 0:
@@ -357,33 +468,44 @@ def run_ours(args):
         return
 
     def to_value(ms_step, n_ranks):
-        units = ntri if unit == "Mtriangles/s" else W * H
-        return n_ranks * units / (ms_step * 1e-3) / 1e6
+        if cfgname == "c2":
+            units = n_ranks * ntri                      # every rank: its own 1M-triangle frame
+        elif cfgname == "c3":
+            units = n_ranks * W * H
+        elif cfgname == "c4":
+            units = W * H                               # one frame, its bands spread over the ranks
+        else:
+            units = C5_VIEWS * ntri                     # 256 views in total, whatever the rank count
+        return units / (ms_step * 1e-3) / 1e6
 
     peak, peak_src = measured_peak()
-    a_frame = 120.0 * ntri + 16.0 * W * H
-    own_bytes = {"setup_kernel": 120.0 * ntri, "raster_kernel": 16.0 * W * H,
+    nframes = len(frames)
+    # algorithmic bytes of what THIS rank does in one step: read every vertex
+    # attribute once per frame, load + store colour and depth once per pixel of its target
+    a_frame = nframes * (120.0 * ntri + 16.0 * W * band_rows)
+    own_bytes = {"setup_kernel": 120.0 * ntri, "raster_kernel": 16.0 * W * band_rows,
                  "tile_scan_kernel": 0.0, "scatter_kernel": 0.0}[dominant]
     achieved = own_bytes / (stage_ms[dominant] * 1e-3) / 1e9
     frame_achieved = a_frame / (ms * 1e-3) / 1e9
-    traffic = ncu_traffic(args.config)
+    traffic = ncu_traffic(args.config, dominant)
     line = {
         "metric": unit, "value": to_value(ms, world), "unit": unit, "n_gpus": world, "steps": K,
-        "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING[cfgname],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "triangles": ntri, "width": W, "height": H,
-                   "parallelism": f"frame-parallel x{world}" if world > 1 else "1 GPU",
-                   "tile": args.tile or "64x32",
+                   "parallelism": ({"c4": f"screen-space row bands x{world}", "c5": f"{C5_VIEWS} views over {world} ranks"}
+                                   .get(cfgname, f"frame-parallel x{world}") if world > 1 else "1 GPU"),
+                   "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": args.scale,
+                   "tile": tile,
                    "l2": "each timed frame streams >126 MB (vertices + records + pair lists + its own "
                          "pre-cleared target), i.e. inputs larger than L2; no explicit flush",
-                   "targets": "one pre-cleared colour/depth pair per timed frame (clear outside the timed region)"},
-        "mpixels_per_s": world * W * H / (ms * 1e-3) / 1e6,
-        "mtriangles_per_s": world * ntri / (ms * 1e-3) / 1e6,
-        "frame_ms": ms,
+                   "targets": ("one target pair, b200r_clear_device inside every timed frame" if clear_in_step else
+                               "one pre-cleared colour/depth pair per timed frame (clear outside the timed region)")},
+        "frame_ms": ms / nframes,
         "gpu_launches": int(launches),
         "stage_ms": stage_ms,
-        "binner": {"binned_triangles": stats["Binned"], "tile_pairs": stats["TilePairs"], "tiles": stats["Tiles"],
-                   "reruns": stats["Reruns"]},
+        "binner": {"binned_triangles": stats["Binned"], "segments": stats["Segments"], "spans": stats["Spans"],
+                   "queue_entries": stats["TilePairs"], "tiles": stats["Tiles"], "reruns": stats["Reruns"]},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": own_bytes,
@@ -392,9 +514,8 @@ def run_ours(args):
                      "frame": {"algorithmic_bytes": a_frame, "achieved": frame_achieved,
                                "frac": frame_achieved / peak}},
         "e2e": {"value": to_value(e2e_ms, world), "unit": unit, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(ntri * 120 + 2 * W * H * 4), "d2h_bytes_per_step": int(2 * W * H * 4),
-                "steps": e2e_steps, "covered_pixels": covered,
-                "api": "b200r_render_objects (host pointers, pinned)"},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "steps": e2e_steps, "covered_pixels": covered, "api": e2e_api},
         "clocks": clocks,
     }
     if with_gather:
@@ -405,10 +526,7 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as ol
             from cpu_renderer_b200 import scene as sc2
-            sample = min(ntri, 250_000 if args.config == "c2" else 4000)
-            s = sc2.Scene(scene.name, W, H, scene.transform, scene.positions[:sample * 3], scene.colors[:sample * 3],
-                          scene.normals[:sample * 3], scene.uvs[:sample * 3])
-            threads = os.cpu_count() or 1
+            s, sample, threads = cpu_sample(cfgname, scene, sc2)
             kind = "reference" if ol.ref_available() else "port"
             res = time_cpu(ol, s, threads, 3, 1, kind)
             units = sample if unit == "Mtriangles/s" else W * H * (sample / ntri)
@@ -429,6 +547,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c2", choices=sorted(METRICS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the triangle count (smoke runs only)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", default=None, help="WxH: 64x32 (default), 32x32, 128x16, 64x16")
     ap.add_argument("--no-cpu-baseline", action="store_true")

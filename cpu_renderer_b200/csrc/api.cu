@@ -176,7 +176,7 @@ static int issue_frame(b200r_context *c)
         if(m.ntri) c->stats.KernelLaunches += 1;
     }
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[1], c->stream));
-    launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, c->stream);
+    launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, tile_offset + nbins + 1, c->stream);
     c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[2], c->stream));
     CU(cudaMemcpyAsync(c->h_words, words, sizeof(FrameWords), cudaMemcpyDeviceToHost, c->stream));
@@ -380,7 +380,8 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     // first guesses (2.5 segments, 6 spans, 8 queue entries per triangle); all lists grow on demand
     if(c->segs.bytes == 0) CU(c->segs.reserve((size_t)std::max<uint64_t>(total*5/2, 1u << 16)*sizeof(SegInfo)));
     if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*kSpanWords*sizeof(uint32_t)));
-    CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1)*sizeof(unsigned)));
+    // counts, cursors, offsets (+1 end entry), and the scan's chunk scratch
+    CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1 + 2*((size_t)ntiles*kDepthBuckets/8192 + 2))*sizeof(unsigned)));
     if(c->pairs.bytes == 0)
         CU(c->pairs.reserve((size_t)std::max<uint64_t>(total*8, 1u << 16)*sizeof(unsigned)));
 

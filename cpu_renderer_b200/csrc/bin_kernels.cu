@@ -82,10 +82,71 @@ scatter_kernel(const ScatterParams p)
     }
 }
 
-void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
-                      unsigned *pair_total, cudaStream_t s)
+// Large bin counts (16K^2 targets: 1 M bins) use a three-step scan: per-CTA scans of 8192-element
+// chunks, the single-CTA scan over the chunk totals, then a uniform add.
+constexpr unsigned kChunk = kScanThreads*8;
+
+__global__ void __launch_bounds__(kScanThreads)
+chunk_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offset, unsigned n,
+                  unsigned *__restrict__ chunk_sums)
 {
-    tile_scan_kernel<<<1, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, pair_total);
+    __shared__ unsigned warp_sums[kScanThreads/32];
+    const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned lo = min(blockIdx.x*kChunk + t*8, n), hi = min(lo + 8, n);
+    unsigned v[8], sum = 0;
+#pragma unroll
+    for(int i = 0; i < 8; ++i) { v[i] = (lo + i < hi) ? count[lo + i] : 0u; sum += v[i]; }
+    unsigned incl = sum;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1)
+    {
+        unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+        if(lane >= (unsigned)d) incl += up;
+    }
+    if(lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if(warp == 0)
+    {
+        unsigned w = warp_sums[lane], wi = w;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1)
+        {
+            unsigned up = __shfl_up_sync(0xffffffffu, wi, d);
+            if(lane >= (unsigned)d) wi += up;
+        }
+        warp_sums[lane] = wi - w;
+        if(lane == 31) chunk_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    unsigned run = warp_sums[warp] + (incl - sum);
+#pragma unroll
+    for(int i = 0; i < 8; ++i) { if(lo + i < hi) offset[lo + i] = run; run += v[i]; }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+chunk_add_kernel(unsigned *__restrict__ offset, unsigned n, const unsigned *__restrict__ chunk_offsets,
+                 const unsigned *__restrict__ total)
+{
+    const unsigned add = chunk_offsets[blockIdx.x];
+    const unsigned lo = blockIdx.x*kChunk;
+    for(unsigned i = lo + threadIdx.x; i < min(lo + kChunk, n); i += kScanThreads) offset[i] += add;
+    if(blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offset[n] = *total;
+}
+
+// scratch: 2*ceil(n/8192) + 1 words
+void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
+                      unsigned *pair_total, unsigned *scratch, cudaStream_t s)
+{
+    if(ntiles <= 4*kChunk)
+    {
+        tile_scan_kernel<<<1, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, pair_total);
+        return;
+    }
+    const unsigned chunks = (ntiles + kChunk - 1)/kChunk;
+    unsigned *chunk_sums = scratch, *chunk_offsets = scratch + chunks;
+    chunk_scan_kernel<<<chunks, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, chunk_sums);
+    tile_scan_kernel<<<1, kScanThreads, 0, s>>>(chunk_sums, chunk_offsets, chunks, pair_total);
+    chunk_add_kernel<<<chunks, kScanThreads, 0, s>>>(tile_offset, ntiles, chunk_offsets, pair_total);
 }
 
 void launch_scatter(const ScatterParams &p, cudaStream_t s)

@@ -197,7 +197,7 @@ void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &
 void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s);
 void launch_zrange_finish(unsigned *zkeys, cudaStream_t s);
 void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
-                      unsigned *pair_total, cudaStream_t s);
+                      unsigned *pair_total, unsigned *scratch, cudaStream_t s);
 struct ScatterParams
 {
     const SegInfo *segs;

@@ -312,13 +312,14 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         walk_end = min(max_y, v.band_y1);
         if(have_walk && !(first_row < walk_end && max_y > v.band_y0 - (v.alias_rows ? 1 : 0))) have_walk = false;
 
-        // Number of segments and spans, without walking: between consecutive list-change rows the
+        // Number of spans and segments, without walking: between consecutive list-change rows the
         // set of active edges {e : YMin <= row < YMax} is constant; a stretch with >= 2 of them
-        // yields one span per row and one segment per tile-row band it touches.  The walk below
-        // splits at exactly the same rows.
+        // yields one span per row.  A segment is the run of a triangle's spans inside one tile-row
+        // band (its span records are consecutive), so the segment count is the number of distinct
+        // bands those rows fall into.  The walk below opens segments by exactly the same rule.
         if(have_walk)
         {
-            int y = first_row;
+            int y = first_row, last_band = -1;
             while(y < walk_end)
             {
                 int nxt = walk_end, act = 0;
@@ -337,7 +338,9 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     const int a = max(y, v.band_y0);
                     if(a < nxt)
                     {
-                        my_segs += (nxt - 1 - v.band_y0)/v.tile_h - (a - v.band_y0)/v.tile_h + 1;
+                        const int b0 = (a - v.band_y0)/v.tile_h, b1 = (nxt - 1 - v.band_y0)/v.tile_h;
+                        my_segs += b1 - b0 + ((b0 == last_band) ? 0 : 1);
+                        last_band = b1;
                         my_spans += nxt - a;
                     }
                 }
@@ -376,24 +379,29 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         span_at = s_span_base + s_warp_sum2[warp] + (incl_p - (unsigned)my_spans);
     }
 
-    if((unsigned)t < n && have_walk &&
-       (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity &&
-       (unsigned long long)span_at + (unsigned)my_spans <= out.span_capacity)
+    // ---- the row walk.  All 32 lanes of a warp stay in the loops below (warp-wide trip counts,
+    //      predicated bodies): list events are handled for all lanes that have one at the same
+    //      time, then the rows up to each lane's next event run in lock step. ----
     {
+        const bool walking = (unsigned)t < n && have_walk &&
+                             (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity &&
+                             (unsigned long long)span_at + (unsigned)my_spans <= out.span_capacity;
         const uint32_t *rec = s_rec + t*kRecWords;
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
         ActiveEdge L, R;
         L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;
         L.ymax = 0; L.id = -1; R = L;
         int nact = 0, next_ev = first_row;
-        bool open = false;
+        int y = first_row;
+        int seg_band = -1;                                  // band of the open segment, -1: none
         unsigned seg = seg_at, span = span_at;
-        int seg_y0 = 0, seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
+        int seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
         unsigned seg_span0 = 0;
         unsigned pairs = 0;
         const unsigned prim = m.prim_base + base + t;
         // depth bucket of the whole triangle: 0 = nearest (largest camera z, projekt.cpp:525)
         unsigned bucket = 0;
+        if(walking)
         {
             const float ztri = fmaxf(fmaxf(s_pos[t*9 + 2], s_pos[t*9 + 5]), s_pos[t*9 + 8]) + m.pz;
             const float f = (out.zrange[0] - ztri)*out.zrange[1]*(float)kDepthBuckets;
@@ -402,125 +410,135 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 
         auto close_segment = [&]()
         {
-            if(!open) return;
+            if(seg_band < 0) return;
             int tx0 = 1, tx1 = 0;
             if(seg_minx <= seg_maxx) { tx0 = seg_minx/v.tile_w; tx1 = seg_maxx/v.tile_w; }
             SegInfo si;
-            const unsigned trow = (unsigned)((seg_y0 - v.band_y0)/v.tile_h);
-            si.tile_row = trow | (bucket << 24);
+            si.tile_row = (unsigned)seg_band | (bucket << 24);
             si.tx = (unsigned)tx0 | ((unsigned)tx1 << 16);
             si.span_base = seg_span0;
             si.nrows = span - seg_span0;
             out.segs[seg] = si;
             for(int tx = tx0; tx <= tx1; ++tx)
-                atomicAdd(&out.tile_count[(trow*v.tiles_x + tx)*kDepthBuckets + bucket], si.nrows);
+                atomicAdd(&out.tile_count[(seg_band*v.tiles_x + tx)*kDepthBuckets + bucket], si.nrows);
             if(tx0 <= tx1) pairs += (unsigned)(tx1 - tx0 + 1)*si.nrows;
-            ++seg; open = false;
+            ++seg; seg_band = -1;
         };
 
-        for(int y = first_row; y < walk_end; ++y)
+        while(__any_sync(0xffffffffu, walking && y < walk_end))
         {
-            bool brk = false;
-            if(y == next_ev) { active_list_event(y, rec, nedges, L, R, nact, next_ev); brk = true; }
-            if(nact == 2)
+            // (a) list events (projekt.cpp:202-296), together
+            if(walking && y < walk_end && y == next_ev) active_list_event(y, rec, nedges, L, R, nact, next_ev);
+            // (b) rows up to the next event
+            const int nrow = (walking && y < walk_end) ? (min(next_ev, walk_end) - y) : 0;
+            const int nrow_max = __reduce_max_sync(0xffffffffu, nrow);
+            for(int k = 0; k < nrow_max; ++k)
             {
-                const bool in_band = y >= v.band_y0;
-                if(in_band || (v.alias_rows && y == v.band_y0 - 1))
+                if(k >= nrow) continue;
+                if(nact == 2)
                 {
-                    if(in_band && (brk || !open || ((y - v.band_y0) % v.tile_h) == 0))
+                    const bool in_band = y >= v.band_y0;
+                    if(in_band || (v.alias_rows && y == v.band_y0 - 1))
                     {
-                        close_segment();
-                        open = true; seg_y0 = y; seg_span0 = span; seg_minx = 0x7fffffff; seg_maxx = (int)0x80000000;
-                    }
-                    // ---- span set-up, projekt.cpp:306-412, once per row ----
-                    const float xdiff = roundf(fsub(R.x, L.x));                   // :311-312
-                    float zi = 0.0f, i0 = 0.0f, i1 = 0.0f, i2 = 0.0f, i3 = 0.0f;
-                    if(xdiff != 0.0f)                                             // :333-363
-                    {
-                        i0 = fdiv(fsub(R.c0, L.c0), xdiff); i1 = fdiv(fsub(R.c1, L.c1), xdiff);
-                        i2 = fdiv(fsub(R.c2, L.c2), xdiff); i3 = fdiv(fsub(R.c3, L.c3), xdiff);
-                        zi = fdiv(fsub(R.z, L.z), xdiff);
-                    }
-                    float xoff = 0.0f, leftx = L.x;                               // :381-390
-                    if(leftx < 0.0f) { xoff = -leftx; leftx = 0.0f; }
-                    else if(leftx >= wf) { leftx = wf_m1; }
-                    float rightx = R.x;                                           // :392-400
-                    if(rightx < 0.0f) { rightx = 0.0f; }
-                    else if(rightx >= wf) { rightx = wf_m1; }
-                    const int minx = round_s32(leftx);                            // :402-406
-                    int maxx = round_s32(rightx);
-                    const float z = fadd(L.z, fmul(xoff, zi));                    // :375, :408
-                    const float c0 = fadd(L.c0, fmul(xoff, i0)), c1 = fadd(L.c1, fmul(xoff, i1));   // :379, :412
-                    const float c2 = fadd(L.c2, fmul(xoff, i2)), c3 = fadd(L.c3, fmul(xoff, i3));
-                    if(maxx >= v.width && minx <= maxx)
-                    {
-                        // An end in [Width-0.5, Width) is not clamped (:387, :397) and rounds up to
-                        // column == Width (:402-403); the reference's pointer arithmetic (:414-419)
-                        // puts that pixel into column 0 of the NEXT row when rows are contiguous, into
-                        // row padding otherwise, past the buffer on the last row.  The next-row write
-                        // is reproduced as a one-pixel span of its own; the others are dropped.
-                        const int ay = y + 1;
-                        if(v.alias_rows && ay < v.height && ay >= v.band_y0 && ay < v.band_y1)
+                        if(in_band)
                         {
-                            float az = z, a0 = c0, a1 = c1, a2 = c2, a3 = c3;
-                            for(int sx = minx; sx < v.width; ++sx)                // :534-535 up to that column
+                            const int band = (y - v.band_y0)/v.tile_h;
+                            if(band != seg_band)
                             {
-                                a0 = fadd(a0, i0); a1 = fadd(a1, i1); a2 = fadd(a2, i2); a3 = fadd(a3, i3);
-                                az = fadd(az, zi);
-                            }
-                            const unsigned ex = atomicAdd(out.extra_total, 1u);
-                            if(ex < out.span_capacity && ex < out.seg_capacity)
-                            {
-                                const unsigned asp = out.span_capacity - 1u - ex, asg = out.seg_capacity - 1u - ex;
-                                float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)asp*kSpanWords);
-                                Q[0] = make_float4(__uint_as_float(prim), __int_as_float(ay), __int_as_float(0), __int_as_float(0));
-                                Q[1] = make_float4(az, a0, a1, a2);
-                                Q[2] = make_float4(a3, 0.0f, 0.0f, 0.0f);
-                                Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), az);
-                                SegInfo si;
-                                const unsigned trow = (unsigned)((ay - v.band_y0)/v.tile_h);
-                                si.tile_row = trow | (bucket << 24); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
-                                out.segs[asg] = si;
-                                atomicAdd(&out.tile_count[(trow*v.tiles_x)*kDepthBuckets + bucket], 1u);
-                                pairs += 1u;
+                                close_segment();
+                                seg_band = band; seg_span0 = span; seg_minx = 0x7fffffff; seg_maxx = (int)0x80000000;
                             }
                         }
-                        maxx = v.width - 1;
+                        // ---- span set-up, projekt.cpp:306-412, once per row ----
+                        const float xdiff = roundf(fsub(R.x, L.x));                   // :311-312
+                        float zi = 0.0f, i0 = 0.0f, i1 = 0.0f, i2 = 0.0f, i3 = 0.0f;
+                        if(xdiff != 0.0f)                                             // :333-363
+                        {
+                            i0 = fdiv(fsub(R.c0, L.c0), xdiff); i1 = fdiv(fsub(R.c1, L.c1), xdiff);
+                            i2 = fdiv(fsub(R.c2, L.c2), xdiff); i3 = fdiv(fsub(R.c3, L.c3), xdiff);
+                            zi = fdiv(fsub(R.z, L.z), xdiff);
+                        }
+                        float xoff = 0.0f, leftx = L.x;                               // :381-390
+                        if(leftx < 0.0f) { xoff = -leftx; leftx = 0.0f; }
+                        else if(leftx >= wf) { leftx = wf_m1; }
+                        float rightx = R.x;                                           // :392-400
+                        if(rightx < 0.0f) { rightx = 0.0f; }
+                        else if(rightx >= wf) { rightx = wf_m1; }
+                        const int minx = round_s32(leftx);                            // :402-406
+                        int maxx = round_s32(rightx);
+                        const float z = fadd(L.z, fmul(xoff, zi));                    // :375, :408
+                        const float c0 = fadd(L.c0, fmul(xoff, i0)), c1 = fadd(L.c1, fmul(xoff, i1));   // :379, :412
+                        const float c2 = fadd(L.c2, fmul(xoff, i2)), c3 = fadd(L.c3, fmul(xoff, i3));
+                        if(maxx >= v.width && minx <= maxx)
+                        {
+                            // An end in [Width-0.5, Width) is not clamped (:387, :397) and rounds up to
+                            // column == Width (:402-403); the reference's pointer arithmetic (:414-419)
+                            // puts that pixel into column 0 of the NEXT row when rows are contiguous, into
+                            // row padding otherwise, past the buffer on the last row.  The next-row write
+                            // is reproduced as a one-pixel span of its own; the others are dropped.
+                            const int ay = y + 1;
+                            if(v.alias_rows && ay < v.height && ay >= v.band_y0 && ay < v.band_y1)
+                            {
+                                float az = z, a0 = c0, a1 = c1, a2 = c2, a3 = c3;
+                                for(int sx = minx; sx < v.width; ++sx)                // :534-535 up to that column
+                                {
+                                    a0 = fadd(a0, i0); a1 = fadd(a1, i1); a2 = fadd(a2, i2); a3 = fadd(a3, i3);
+                                    az = fadd(az, zi);
+                                }
+                                const unsigned ex = atomicAdd(out.extra_total, 1u);
+                                if(ex < out.span_capacity && ex < out.seg_capacity)
+                                {
+                                    const unsigned asp = out.span_capacity - 1u - ex, asg = out.seg_capacity - 1u - ex;
+                                    float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)asp*kSpanWords);
+                                    Q[0] = make_float4(__uint_as_float(prim), __int_as_float(ay), __int_as_float(0), __int_as_float(0));
+                                    Q[1] = make_float4(az, a0, a1, a2);
+                                    Q[2] = make_float4(a3, 0.0f, 0.0f, 0.0f);
+                                    Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), az);
+                                    SegInfo si;
+                                    const unsigned trow = (unsigned)((ay - v.band_y0)/v.tile_h);
+                                    si.tile_row = trow | (bucket << 24); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
+                                    out.segs[asg] = si;
+                                    atomicAdd(&out.tile_count[(trow*v.tiles_x)*kDepthBuckets + bucket], 1u);
+                                    pairs += 1u;
+                                }
+                            }
+                            maxx = v.width - 1;
+                        }
+                        if(in_band)
+                        {
+                            float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+                            Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
+                            Q[1] = make_float4(z, c0, c1, c2);
+                            Q[2] = make_float4(c3, zi, i0, i1);
+                            Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u),
+                                               span_depth_bound(z, zi, maxx - minx));
+                            ++span;
+                            if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
+                        }
                     }
-                    if(in_band)
-                    {
-                        float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
-                        Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
-                        Q[1] = make_float4(z, c0, c1, c2);
-                        Q[2] = make_float4(c3, zi, i0, i1);
-                        Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u),
-                                           span_depth_bound(z, zi, maxx - minx));
-                        ++span;
-                        if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
-                    }
+                    step_edge(L); step_edge(R);                                   // :542-549
+                    if(L.x > R.x) { ActiveEdge tmp = L; L = R; R = tmp; }          // :562-572
                 }
-                step_edge(L); step_edge(R);                                   // :542-549
-                if(L.x > R.x) { ActiveEdge tmp = L; L = R; R = tmp; }          // :562-572
+                ++y;
             }
-            else
+        }
+        if(walking)
+        {
+            close_segment();
+            // slots promised by the counts but not produced (cannot happen for finite input) are blanked
+            for(; span < span_at + (unsigned)my_spans; ++span)
             {
-                close_segment();
+                float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+                Q[0] = make_float4(__uint_as_float(prim), 0.0f, __int_as_float(1), __int_as_float(0));
+                Q[1] = Q[2] = Q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
+            for(; seg < seg_at + (unsigned)my_segs; ++seg)
+            {
+                SegInfo si; si.tile_row = 0; si.tx = 1u; si.span_base = 0; si.nrows = 0;
+                out.segs[seg] = si;
+            }
+            if(pairs) { atomicAdd(&s_binned, 1u); atomicAdd(&s_pairs, pairs); }
         }
-        close_segment();
-        // slots promised by the counts but not produced (cannot happen for finite input) are blanked
-        for(; span < span_at + (unsigned)my_spans; ++span)
-        {
-            float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
-            Q[0] = make_float4(__uint_as_float(prim), 0.0f, __int_as_float(1), __int_as_float(0));
-            Q[1] = Q[2] = Q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
-        for(; seg < seg_at + (unsigned)my_segs; ++seg)
-        {
-            SegInfo si; si.tile_row = 0; si.tx = 1u; si.span_base = 0; si.nrows = 0;
-            out.segs[seg] = si;
-        }
-        if(pairs) { atomicAdd(&s_binned, 1u); atomicAdd(&s_pairs, pairs); }
     }
     __syncthreads();
 
