@@ -63,7 +63,7 @@ struct b200r_context
     cudaEvent_t total_ready = nullptr;
     std::string error;
     int tile_w = 64, tile_h = 32;
-    int refill_lanes = 8, pend_lanes = 8;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
+    int refill_lanes = 8, pend_lanes = 4;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned

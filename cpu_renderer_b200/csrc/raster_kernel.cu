@@ -15,8 +15,8 @@
 //     with ONE warp-aggregated ticket (ballot + popc + shuffle) on a shared-memory counter;
 //   * lanes with pixels advance in lock step, one pixel per iteration; pixels left of the tile
 //     are the same iteration with the memory part predicated off (adds only, in registers);
-//   * a pixel whose depth test may pass parks its lane; when kPend lanes are parked they run the
-//     update together: pack ARGB (:520-523) and one 128-bit compare-and-swap (ATOMS.CAS.128)
+//   * a pixel whose depth test may pass parks its lane; as soon as kPend lanes are parked they run
+//     the update together: pack ARGB (:520-523) and one 128-bit compare-and-swap (ATOMS.CAS.128)
 //     under the rule   z > zold || (z == zold && prim < primold)
 //     which is the reference's strict '>' with first-submitted-wins (:525) made order
 //     independent.  Depth, owner and colour change together, so no ordering between lanes or
@@ -206,30 +206,32 @@ raster_kernel(const RasterParams p)
                 const unsigned pend_mask = __ballot_sync(FULL, pending);
                 if((need_mask | busy_mask | pend_mask) == 0) break;
 
-                if(pend_mask && (busy_mask == 0 || __popc(pend_mask) >= kPend))
+                // depth-test passes, projekt.cpp:520-529: pack + one 128-bit compare-and-swap
+                auto resolve_pending = [&]()
                 {
-                    // ---- depth-test passes, projekt.cpp:520-529, for all parked lanes at once ----
-                    if(pending)
+                    const uint32_t pa = rowaddr + (uint32_t)x*16u;
+                    Pixel mine;
+                    mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
+                    mine.color = pack_argb(c0, c1, c2, c3, guarded); mine.pad = 0;
+                    Pixel old = lds_pixel(pa);
+                    while(true)
                     {
-                        const uint32_t pa = rowaddr + (uint32_t)x*16u;
-                        Pixel mine;
-                        mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
-                        mine.color = pack_argb(c0, c1, c2, c3, guarded); mine.pad = 0;
-                        Pixel old = lds_pixel(pa);
-                        while(true)
-                        {
-                            const float oz = __uint_as_float(old.z);
-                            const int op = (int)old.prim;
-                            if(!(z > oz || (z == oz && prim < op))) break;            // :525 + tie rule
-                            const Pixel prev = cas_pixel(pa, old, mine);
-                            if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
-                            old = prev;
-                        }
-                        c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
-                        z = fadd(z, zi);                                                              // :535
-                        ++x; --n_left;
-                        pending = false;
+                        const float oz = __uint_as_float(old.z);
+                        const int op = (int)old.prim;
+                        if(!(z > oz || (z == oz && prim < op))) break;            // :525 + tie rule
+                        const Pixel prev = cas_pixel(pa, old, mine);
+                        if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
+                        old = prev;
                     }
+                    c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
+                    z = fadd(z, zi);                                                              // :535
+                    ++x; --n_left;
+                    pending = false;
+                };
+
+                if(pend_mask && busy_mask == 0)
+                {
+                    if(pending) resolve_pending();          // nobody else can make progress: flush the parked lanes
                     continue;
                 }
 
@@ -272,22 +274,27 @@ raster_kernel(const RasterParams p)
                 }
 
                 // ---- pixel steps, projekt.cpp:423-425, 525, 534-535 (a few per ballot round) ----
+                // A lane whose depth test may pass parks; as soon as kPend lanes of the warp are
+                // parked they run the update together, right here (low-overdraw scenes pass on
+                // nearly every pixel, high-overdraw scenes rarely: both stay converged).
 #pragma unroll
                 for(int u = 0; u < 4; ++u)
                 {
-                    if(n_left > 0 && !pending)
+                    if(n_left > 0 && !pending && x >= x0)
                     {
-                        if(x >= x0)
-                        {
-                            const float zo = lds_depth(rowaddr + (uint32_t)x*16u);
-                            pending = (z >= zo);                              // may pass: park
-                        }
-                        if(!pending)
-                        {
-                            c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
-                            z = fadd(z, zi);                                                              // :535
-                            ++x; --n_left;
-                        }
+                        const float zo = lds_depth(rowaddr + (uint32_t)x*16u);
+                        pending = (z >= zo);
+                    }
+                    const bool flush = __popc(__ballot_sync(FULL, pending)) >= kPend;
+                    if(pending)
+                    {
+                        if(flush) resolve_pending();
+                    }
+                    else if(n_left > 0)
+                    {
+                        c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
+                        z = fadd(z, zi);                                                              // :535
+                        ++x; --n_left;
                     }
                 }
             }

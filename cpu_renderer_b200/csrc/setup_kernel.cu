@@ -517,7 +517,11 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         }
                     }
                     step_edge(L); step_edge(R);                                   // :542-549
-                    if(L.x > R.x) { ActiveEdge tmp = L; L = R; R = tmp; }          // :562-572
+                    if(L.x > R.x)                                                 // :562-572 (rare: keep it a branch)
+                    {
+                        asm volatile("" ::: "memory");
+                        ActiveEdge tmp = L; L = R; R = tmp;
+                    }
                 }
                 ++y;
             }
