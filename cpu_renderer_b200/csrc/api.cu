@@ -44,12 +44,13 @@ struct FrameWords
 {
     unsigned pair_total;
     unsigned work_counter;
-    unsigned seg_total;
-    unsigned span_total;
     unsigned extra_total;
-    unsigned pad;
+    unsigned overflow;                  // finalize_kernel: some list did not fit
+    unsigned seg_max, span_max;         // finalize_kernel: largest region fill (incl. alias entries)
     unsigned zkeys[2];                  // z range of the frame: ordered keys, then {zmax, 1/range} as floats
-    unsigned long long counters[2];     // binned triangles, tile pairs
+    unsigned long long counters[4];     // binned triangles, queue entries, segments, spans
+    unsigned seg_fill[kSubAllocators];
+    unsigned span_fill[kSubAllocators];
 };
 
 } // namespace
@@ -127,6 +128,8 @@ static int fill_view(b200r_context *c, const game_render_commands *cmd, const b2
     v.width = t->Width; v.height = t->Height;
     v.band_y0 = t->BandFirstRow; v.band_y1 = t->BandFirstRow + t->BandRows;
     v.tile_w = c->tile_w; v.tile_h = c->tile_h;
+    v.tile_w_shift = 0; while((1 << v.tile_w_shift) < v.tile_w) ++v.tile_w_shift;
+    v.tile_h_shift = 0; while((1 << v.tile_h_shift) < v.tile_h) ++v.tile_h_shift;
     v.tiles_x = (t->Width + c->tile_w - 1)/c->tile_w;
     v.tiles_y = (t->BandRows + c->tile_h - 1)/c->tile_h;
     v.alias_rows = (t->ColorPitch == t->Width*4 && t->DepthStride == t->Width) ? 1 : 0;
@@ -154,8 +157,8 @@ static int issue_frame(b200r_context *c)
     so.recs = nullptr;
     so.spans = (uint32_t *)c->spans.ptr;
     so.segs = (SegInfo *)c->segs.ptr;
-    so.seg_total = &words->seg_total;
-    so.span_total = &words->span_total;
+    so.seg_fill = words->seg_fill;
+    so.span_fill = words->span_fill;
     so.extra_total = &words->extra_total;
     so.seg_capacity = seg_cap;
     so.span_capacity = span_cap;
@@ -178,6 +181,14 @@ static int issue_frame(b200r_context *c)
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[1], c->stream));
     launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, tile_offset + nbins + 1, c->stream);
     c->stats.KernelLaunches += 1;
+    const unsigned pair_cap_f = (unsigned)(c->pairs.bytes/sizeof(unsigned));
+    FinalizeParams fp;
+    fp.seg_fill = words->seg_fill; fp.span_fill = words->span_fill;
+    fp.extra_total = &words->extra_total; fp.pair_total = &words->pair_total;
+    fp.seg_capacity = seg_cap; fp.span_capacity = span_cap; fp.pair_capacity = pair_cap_f;
+    fp.overflow = &words->overflow; fp.seg_max = &words->seg_max; fp.span_max = &words->span_max;
+    launch_finalize(fp, c->stream);
+    c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[2], c->stream));
     CU(cudaMemcpyAsync(c->h_words, words, sizeof(FrameWords), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->total_ready, c->stream));
@@ -185,9 +196,8 @@ static int issue_frame(b200r_context *c)
     const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
     ScatterParams sp;
     sp.segs = so.segs;
-    sp.seg_total = &words->seg_total; sp.span_total = &words->span_total; sp.extra_total = &words->extra_total;
-    sp.pair_total = &words->pair_total;
-    sp.seg_capacity = seg_cap; sp.span_capacity = span_cap; sp.pair_capacity = pair_cap;
+    sp.seg_fill = words->seg_fill; sp.extra_total = &words->extra_total; sp.overflow = &words->overflow;
+    sp.seg_capacity = seg_cap;
     sp.tiles_x = v.tiles_x;
     sp.tile_offset = tile_offset; sp.tile_fill = tile_fill; sp.pair_list = (unsigned *)c->pairs.ptr;
     launch_scatter(sp, c->stream);
@@ -197,9 +207,7 @@ static int issue_frame(b200r_context *c)
     RasterParams rp;
     rp.v = v;
     rp.spans = so.spans;
-    rp.seg_total = &words->seg_total;
-    rp.span_total = &words->span_total;
-    rp.extra_total = &words->extra_total;
+    rp.overflow = &words->overflow;
     rp.seg_capacity = seg_cap;
     rp.span_capacity = span_cap;
     rp.tile_offset = tile_offset;
@@ -232,27 +240,32 @@ static int settle_pending(b200r_context *c)
     while(c->pending)
     {
         CU(cudaEventSynchronize(c->total_ready));
-        const unsigned total = c->h_words->pair_total;
-        const unsigned nextra = c->h_words->extra_total;
-        const uint64_t nseg = (uint64_t)c->h_words->seg_total + nextra, nspan = (uint64_t)c->h_words->span_total + nextra;
+        const FrameWords &hw = *c->h_words;
+        const unsigned total = hw.pair_total;
         const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
-        const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
-        const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(kSpanWords*sizeof(uint32_t)), 0xffffffffu);
-        c->stats.Binned = c->h_words->counters[0];
-        c->stats.TilePairs = c->h_words->counters[1];
+        uint64_t nseg = hw.extra_total, nspan = hw.extra_total;
+        for(int r = 0; r < kSubAllocators; ++r) { nseg += hw.seg_fill[r]; nspan += hw.span_fill[r]; }
+        c->stats.Binned = hw.counters[0];
+        c->stats.TilePairs = hw.counters[1];
         c->stats.Segments = nseg;
         c->stats.Spans = nspan;
-        c->stats.AliasPixels = nextra;
+        c->stats.AliasPixels = hw.extra_total;
         c->pending = false;
-        if(total > pair_cap || nseg > seg_cap || nspan > span_cap)
+        if(hw.overflow)
         {
-            // the scatter and raster kernels of that frame saw the same totals and did nothing
+            // the scatter and raster kernels of that frame saw the same verdict and did nothing.
+            // Every region must hold the fullest region's fill (plus slack for run-to-run jitter
+            // in which CTA lands in which region).
             CU(cudaStreamSynchronize(c->stream));
-            const bool truncated = nseg > seg_cap || nspan > span_cap;
-            if(nseg > seg_cap) CU(c->segs.reserve((size_t)nseg*sizeof(SegInfo)));
-            if(nspan > span_cap) CU(c->spans.reserve((size_t)nspan*kSpanWords*sizeof(uint32_t)));
-            // with truncated lists the pair total was an under-count: leave headroom
-            CU(c->pairs.reserve((size_t)std::max<uint64_t>(total, truncated ? (uint64_t)nspan*2 : 0)*sizeof(unsigned)));
+            const unsigned seg_region = (unsigned)(c->segs.bytes/sizeof(SegInfo))/kSubAllocators;
+            const unsigned span_region = (unsigned)(c->spans.bytes/(kSpanWords*sizeof(uint32_t)))/kSubAllocators;
+            const bool truncated = hw.seg_max > seg_region || hw.span_max > span_region;
+            if(hw.seg_max > seg_region)
+                CU(c->segs.reserve(((size_t)hw.seg_max + hw.seg_max/8 + 64)*kSubAllocators*sizeof(SegInfo)));
+            if(hw.span_max > span_region)
+                CU(c->spans.reserve(((size_t)hw.span_max + hw.span_max/8 + 64)*kSubAllocators*kSpanWords*sizeof(uint32_t)));
+            // with truncated lists the queue total was an under-count: leave headroom
+            CU(c->pairs.reserve((size_t)std::max<uint64_t>(total, truncated ? nspan*2 : 0)*sizeof(unsigned)));
             c->stats.Reruns += 1;
             int rc = issue_frame(c);
             if(rc != B200R_OK) return rc;
@@ -564,7 +577,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     ViewParams v;
     rc = fill_view(c, cmd, &t, v);
     if(rc != B200R_OK) return rc;
-    v.tiles_x = 1; v.tiles_y = 1; v.tile_w = 1 << 21; v.tile_h = 1 << 21;
+    v.tiles_x = 1; v.tiles_y = 1; v.tile_w = 1 << 21; v.tile_h = 1 << 21; v.tile_w_shift = v.tile_h_shift = 21;
     CU(c->recs.reserve((size_t)tris*kRecWords*sizeof(uint32_t)));
     CU(c->tiles.reserve(((size_t)kDepthBuckets*3 + 1)*sizeof(unsigned)));
     unsigned *tile_count = (unsigned *)c->tiles.ptr;
@@ -573,7 +586,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
     SetupOutputs so;
     so.recs = (uint32_t *)c->recs.ptr; so.spans = nullptr; so.segs = nullptr;
-    so.seg_total = &words->seg_total; so.span_total = &words->span_total; so.extra_total = &words->extra_total;
+    so.seg_fill = words->seg_fill; so.span_fill = words->span_fill; so.extra_total = &words->extra_total;
     so.seg_capacity = 0; so.span_capacity = 0;
     so.tile_count = tile_count; so.counters = words->counters;
     so.zrange = reinterpret_cast<const float *>(words->zkeys);

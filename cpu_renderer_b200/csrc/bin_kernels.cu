@@ -64,12 +64,15 @@ tile_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offs
 __global__ void __launch_bounds__(256)
 scatter_kernel(const ScatterParams p)
 {
-    const unsigned nseg = *p.seg_total, nextra = *p.extra_total;
-    if(lists_overflowed(nseg, *p.span_total, nextra, *p.pair_total, p.seg_capacity, p.span_capacity, p.pair_capacity)) return;
-    // ordinary segments occupy [0, nseg); alias-pixel segments the last nextra slots
+    if(*p.overflow) return;                              // host grows the lists and re-issues the frame
+    // blockIdx.y = region of the segment array; the alias-pixel segments sit at the very end
+    const unsigned region = blockIdx.y;
+    const unsigned region_size = p.seg_capacity/kSubAllocators;
+    const unsigned nseg = p.seg_fill[region];
+    const unsigned nextra = (region == kSubAllocators - 1) ? *p.extra_total : 0u;
     for(unsigned i = blockIdx.x*blockDim.x + threadIdx.x; i < nseg + nextra; i += gridDim.x*blockDim.x)
     {
-        const unsigned seg = (i < nseg) ? i : p.seg_capacity - 1u - (i - nseg);
+        const unsigned seg = (i < nseg) ? region*region_size + i : p.seg_capacity - 1u - (i - nseg);
         const SegInfo si = p.segs[seg];
         const int tx0 = si.tx & 0xffff, tx1 = si.tx >> 16;
         const unsigned trow = si.tile_row & 0xffffffu, bucket = si.tile_row >> 24;
@@ -79,6 +82,27 @@ scatter_kernel(const ScatterParams p)
             const unsigned slot = p.tile_offset[tile] + atomicAdd(&p.tile_fill[tile], si.nrows);
             for(unsigned r = 0; r < si.nrows; ++r) p.pair_list[slot + r] = si.span_base + r;
         }
+    }
+}
+
+__global__ void finalize_kernel(const FinalizeParams p)
+{
+    // one warp: largest region fills, then the overflow verdict every later kernel obeys
+    const unsigned lane = threadIdx.x;
+    unsigned g = 0, s = 0;
+    for(unsigned r = lane; r < (unsigned)kSubAllocators; r += 32) { g = max(g, p.seg_fill[r]); s = max(s, p.span_fill[r]); }
+    g = __reduce_max_sync(0xffffffffu, g);
+    s = __reduce_max_sync(0xffffffffu, s);
+    if(lane == 0)
+    {
+        const unsigned nextra = *p.extra_total;
+        const unsigned seg_region = p.seg_capacity/kSubAllocators, span_region = p.span_capacity/kSubAllocators;
+        const unsigned long long last_g = (unsigned long long)p.seg_fill[kSubAllocators - 1] + nextra;
+        const unsigned long long last_s = (unsigned long long)p.span_fill[kSubAllocators - 1] + nextra;
+        *p.seg_max = (unsigned)min(max((unsigned long long)g, last_g), 0xffffffffull);
+        *p.span_max = (unsigned)min(max((unsigned long long)s, last_s), 0xffffffffull);
+        *p.overflow = (g > seg_region || s > span_region || last_g > seg_region || last_s > span_region ||
+                       *p.pair_total > p.pair_capacity) ? 1u : 0u;
     }
 }
 
@@ -152,10 +176,16 @@ void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigne
 void launch_scatter(const ScatterParams &p, cudaStream_t s)
 {
     if(p.seg_capacity == 0) return;
-    // the segment count lives on the device: size the grid for the capacity, grid-stride inside
-    unsigned blocks = (p.seg_capacity + 255)/256;
-    if(blocks > 148*16) blocks = 148*16;
-    scatter_kernel<<<blocks, 256, 0, s>>>(p);
+    // the fill counts live on the device: size the grid for a region's capacity, grid-stride inside
+    unsigned blocks = (p.seg_capacity/kSubAllocators + 255)/256;
+    if(blocks > 64) blocks = 64;
+    if(blocks < 1) blocks = 1;
+    scatter_kernel<<<dim3(blocks, kSubAllocators), 256, 0, s>>>(p);
+}
+
+void launch_finalize(const FinalizeParams &p, cudaStream_t s)
+{
+    finalize_kernel<<<1, 32, 0, s>>>(p);
 }
 
 } // namespace b200r

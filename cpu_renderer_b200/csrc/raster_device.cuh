@@ -18,6 +18,11 @@ constexpr int kMaxLights = 8;
 // owning triangle, nearest first.  Processing order never changes the image (the depth rule is
 // order independent); near-to-far order only makes the cheap early depth test fail more often.
 constexpr int kDepthBuckets = 8;
+// The span and segment arrays are carved into kSubAllocators equal regions, each with its own
+// fill counter; CTA b of the set-up kernel allocates from region b % kSubAllocators.  One global
+// counter pair was the set-up kernel's bottleneck: every CTA does one returning atomicAdd on it
+// and waits for the answer at a barrier (C4: 156 k CTAs on two addresses).
+constexpr int kSubAllocators = 64;
 
 struct DevLight { float px, py, pz; float ir, ig, ib, ia; };
 
@@ -31,7 +36,8 @@ struct ViewParams
     DevLight lights[kMaxLights];
     int width, height;          // logical screen (loaded_bitmap Width/Height)
     int band_y0, band_y1;       // screen rows owned by this target
-    int tile_w, tile_h;
+    int tile_w, tile_h;         // powers of two
+    int tile_w_shift, tile_h_shift;
     int tiles_x, tiles_y;
     int alias_rows;             // rows are contiguous (Pitch == Width*4, depth stride == Width): a pixel the
                                 // reference writes at column == Width lands in column 0 of the next row
@@ -79,9 +85,7 @@ struct RasterParams
 {
     ViewParams v;
     const uint32_t *spans;      // kSpanWords per span
-    const unsigned *seg_total;  // device words: segments / spans / next-row alias pixels this frame
-    const unsigned *span_total;
-    const unsigned *extra_total;
+    const unsigned *overflow;   // device word set by finalize_kernel: some list did not fit, skip the frame
     unsigned seg_capacity, span_capacity;
     const unsigned *tile_offset;    // [tile*kDepthBuckets + bucket], plus one end entry
     const unsigned *pair_list;
@@ -97,15 +101,6 @@ struct RasterParams
     int refill_lanes;           // idle lanes of a warp that trigger a refill from the span queue
     int pend_lanes;             // parked lanes of a warp that trigger the depth-pass path
 };
-
-// Every consumer of the lists uses the same test, so a frame whose lists overflowed is skipped
-// consistently and re-issued by the host after growing them.
-__device__ __forceinline__ bool lists_overflowed(unsigned nseg, unsigned nspan, unsigned nextra, unsigned npair,
-                                                 unsigned seg_cap, unsigned span_cap, unsigned pair_cap)
-{
-    return (unsigned long long)nseg + nextra > seg_cap || (unsigned long long)nspan + nextra > span_cap ||
-           npair > pair_cap;
-}
 
 // ---------------------------------------------------------------- exact binary32 helpers
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
@@ -181,11 +176,11 @@ struct SetupOutputs
     uint32_t *recs;             // optional (b200r_fill_edge_table): kRecWords per triangle
     uint32_t *spans;            // kSpanWords per span (null: no row walk, records only)
     SegInfo *segs;
-    unsigned *seg_total;        // device counters
-    unsigned *span_total;
+    unsigned *seg_fill;         // [kSubAllocators] device counters, one per region of the arrays
+    unsigned *span_fill;        // [kSubAllocators]
     unsigned *extra_total;      // alias pixels: one-pixel span + segment each, allocated downwards
-                                // from the END of the span / segment arrays
-    unsigned seg_capacity, span_capacity;
+                                // from the END of the span / segment arrays (i.e. of the last region)
+    unsigned seg_capacity, span_capacity;   // whole arrays; a region holds capacity / kSubAllocators
     unsigned *tile_count;       // [tile*kDepthBuckets + bucket]
     const float *zrange;        // device: {largest camera z, 1/(largest - smallest)} of this frame's vertices
     unsigned long long *counters;   // [0] binned triangles, [1] tile pairs
@@ -201,14 +196,25 @@ void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigne
 struct ScatterParams
 {
     const SegInfo *segs;
-    const unsigned *seg_total, *span_total, *extra_total, *pair_total;
-    unsigned seg_capacity, span_capacity, pair_capacity;
+    const unsigned *seg_fill;   // [kSubAllocators]
+    const unsigned *extra_total;
+    const unsigned *overflow;
+    unsigned seg_capacity;
     int tiles_x;
     const unsigned *tile_offset;
     unsigned *tile_fill;
     unsigned *pair_list;        // per tile: span indices
 };
 void launch_scatter(const ScatterParams &p, cudaStream_t s);
+// After the scan: one word that tells scatter and raster whether every list fitted.
+struct FinalizeParams
+{
+    const unsigned *seg_fill, *span_fill, *extra_total, *pair_total;
+    unsigned seg_capacity, span_capacity, pair_capacity;
+    unsigned *overflow;
+    unsigned *seg_max, *span_max;   // largest region fill, for the host's growth decision
+};
+void launch_finalize(const FinalizeParams &p, cudaStream_t s);
 cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s);
 void launch_clear(uint32_t *color, int color_pitch_words, float *depth, int depth_stride,
                   int width, int rows, uint32_t cval, float dval, cudaStream_t s);

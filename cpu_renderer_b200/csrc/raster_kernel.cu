@@ -89,8 +89,7 @@ raster_kernel(const RasterParams p)
     __shared__ unsigned s_tile, s_ticket;
     __shared__ float s_rowmin[TH];                        // lower bound of the depth of each tile row
 
-    if(lists_overflowed(*p.seg_total, *p.span_total, *p.extra_total, *p.pair_total, p.seg_capacity, p.span_capacity,
-                        p.pair_capacity)) return;                          // host grows the lists and re-issues
+    if(*p.overflow) return;                                // host grows the lists and re-issues the frame
 
     const int tid = threadIdx.x, lane = tid & 31;
     Pixel *tile = reinterpret_cast<Pixel *>(smem_raw);

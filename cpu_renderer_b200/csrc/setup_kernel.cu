@@ -26,6 +26,7 @@
 namespace b200r {
 
 constexpr int kSetupThreads = 128;
+constexpr int kSortBins = 64;        // walkers are sorted by min(rows, 63); 3 bins per lane of one warp >= 65
 
 struct V3 { float x, y, z; };
 
@@ -145,11 +146,15 @@ __global__ void zrange_finish_kernel(unsigned *zkeys)
 __global__ void __launch_bounds__(kSetupThreads)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
-    __shared__ float s_pos[kSetupThreads*9];
+    __shared__ __align__(16) float s_pos[kSetupThreads*9];
     __shared__ __align__(16) float s_col[kSetupThreads*12];
-    __shared__ float s_nrm[kSetupThreads*9];
+    __shared__ __align__(16) float s_nrm[kSetupThreads*9];
     __shared__ __align__(16) uint32_t s_rec[kSetupThreads*kRecWords];
-    __shared__ unsigned s_binned, s_pairs, s_seg_base, s_span_base;
+    __shared__ unsigned s_binned, s_pairs, s_seg_base, s_span_base, s_fits;
+    __shared__ unsigned s_hist[kSortBins + 2 + 32], s_order[kSetupThreads], s_alive[kSetupThreads];
+    __shared__ int s_w_tri[kSetupThreads];
+    __shared__ int s_w_first[kSetupThreads], s_w_end[kSetupThreads];
+    __shared__ unsigned s_w_info[kSetupThreads], s_w_spans[kSetupThreads], s_w_seg_at[kSetupThreads], s_w_span_at[kSetupThreads];
     __shared__ unsigned s_warp_sum[kSetupThreads/32], s_warp_sum2[kSetupThreads/32];
 
     const unsigned base = blockIdx.x*kSetupThreads;
@@ -159,30 +164,67 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     int my_segs = 0, my_spans = 0, walk_end = 0, first_row = 0, max_y = 0, nedges = 0, nonfinite = 0;
     bool have_walk = false;
     unsigned seg_at = 0, span_at = 0;
+    int nalive = 0;
 
-    // coalesced attribute fetch: consecutive lanes read consecutive words
+    // Coalesced attribute fetch.  Full CTAs with 16-byte aligned streams issue all nine 128-bit
+    // loads of a thread back to back and only then store to shared memory: one DRAM round trip
+    // per CTA.  (A load->store loop costs one round trip per iteration -- measured: the kernel's
+    // time was CTA waves x ~30 us of serialized loads, whatever the arithmetic did.)
     {
         const float *gp = m.pos + (size_t)base*9;
         const float *gc = m.col + (size_t)base*12;
         const float *gn = m.nrm + (size_t)base*9;
-        for(unsigned i = t; i < n*9; i += kSetupThreads) { s_pos[i] = __ldg(gp + i); s_nrm[i] = __ldg(gn + i); }
-        for(unsigned i = t; i < n*12; i += kSetupThreads) s_col[i] = __ldg(gc + i);
+        const bool aligned = ((((uintptr_t)gp) | ((uintptr_t)gc) | ((uintptr_t)gn)) & 15) == 0;
+        if(n == (unsigned)kSetupThreads && aligned)
+        {
+            constexpr int kPos4 = kSetupThreads*9/4, kCol4 = kSetupThreads*12/4;     // 288, 384 float4
+            const float4 *gp4 = reinterpret_cast<const float4 *>(gp);
+            const float4 *gc4 = reinterpret_cast<const float4 *>(gc);
+            const float4 *gn4 = reinterpret_cast<const float4 *>(gn);
+            float4 rp[3], rc[3], rn[3];
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+            {
+                const int i = t + k*kSetupThreads;
+                rp[k] = (i < kPos4) ? __ldg(gp4 + i) : make_float4(0, 0, 0, 0);
+                rc[k] = (i < kCol4) ? __ldg(gc4 + i) : make_float4(0, 0, 0, 0);
+                rn[k] = (i < kPos4) ? __ldg(gn4 + i) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+            {
+                const int i = t + k*kSetupThreads;
+                if(i < kPos4) { reinterpret_cast<float4 *>(s_pos)[i] = rp[k]; reinterpret_cast<float4 *>(s_nrm)[i] = rn[k]; }
+                if(i < kCol4) reinterpret_cast<float4 *>(s_col)[i] = rc[k];
+            }
+        }
+        else
+        {
+            for(unsigned i = t; i < n*9; i += kSetupThreads) { s_pos[i] = __ldg(gp + i); s_nrm[i] = __ldg(gn + i); }
+            for(unsigned i = t; i < n*12; i += kSetupThreads) s_col[i] = __ldg(gc + i);
+        }
     }
     __syncthreads();
 
-    if((unsigned)t < n)
+    // ---- phase 1 (thread per triangle): project, back-face test (projekt.cpp:3926-3927, :3943,
+    //      Eye = (0,0,-1)) and, for multi-GPU row bands, a conservative "can it reach my band" test.
+    //      Survivors are compacted so that the expensive phases below run on dense warps. ----
+    auto project_triangle = [&](int tri_, V3 cam[3], V3 prj[3])
     {
-        uint32_t *rec = s_rec + t*kRecWords;
-        V3 cam[3], prj[3];
 #pragma unroll
         for(int k = 0; k < 3; ++k)
         {
-            cam[k].x = fadd(s_pos[t*9 + 3*k + 0], m.px);    // :3900
-            cam[k].y = fadd(s_pos[t*9 + 3*k + 1], m.py);
-            cam[k].z = fadd(s_pos[t*9 + 3*k + 2], m.pz);
-            prj[k] = project_vertex(cam[k], v);             // :3907
+            cam[k].x = fadd(s_pos[tri_*9 + 3*k + 0], m.px);    // :3900
+            cam[k].y = fadd(s_pos[tri_*9 + 3*k + 1], m.py);
+            cam[k].z = fadd(s_pos[tri_*9 + 3*k + 2], m.pz);
+            prj[k] = project_vertex(cam[k], v);                // :3907
         }
-        // back-face test, :3926-3927, :3943, Eye = (0,0,-1)
+    };
+    bool alive = false;
+    if((unsigned)t < n)
+    {
+        V3 cam[3], prj[3];
+        project_triangle(t, cam, prj);
         V3 d1 = { fsub(prj[1].x, prj[0].x), fsub(prj[1].y, prj[0].y), fsub(prj[1].z, prj[0].z) };
         V3 d2 = { fsub(prj[2].x, prj[0].x), fsub(prj[2].y, prj[0].y), fsub(prj[2].z, prj[0].z) };
         V3 n1 = normalize3(d1), n2 = normalize3(d2);
@@ -190,12 +232,45 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         float cry = fsub(fmul(n1.z, n2.x), fmul(n1.x, n2.z));
         float crz = fsub(fmul(n1.x, n2.y), fmul(n1.y, n2.x));
         float facing = fadd(fadd(fmul(0.0f, crx), fmul(0.0f, cry)), fmul(-1.0f, crz));
+        // A triangle whose projected rows cannot reach this GPU's band (nor the row just above it,
+        // which may drop an alias pixel into the band) needs nothing more here.  Rows lie in
+        // [Round(min y), Round(max y)), so two rows of margin are conservative; NaN compares false
+        // and keeps the triangle.
+        const float ymin_p = fminf(prj[0].y, fminf(prj[1].y, prj[2].y));
+        const float ymax_p = fmaxf(prj[0].y, fmaxf(prj[1].y, prj[2].y));
+        const bool off_band = out.recs == nullptr &&
+                              (ymax_p < (float)(v.band_y0 - 2) || ymin_p > (float)(v.band_y1 + 1));
+        alive = facing > 0.0f && !off_band;
+        // default record header: no edges (overwritten in phase 2 for survivors)
+        uint32_t *rec0 = s_rec + t*kRecWords;
+        rec0[R_NEDGES] = 0; rec0[R_FIRSTROW] = 0; rec0[R_MAXY] = 0; rec0[R_PRIM] = m.prim_base + base + t;
+        rec0[R_EDGE0 + 3*kEdgeWords] = 0; rec0[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec0[R_EDGE0 + 3*kEdgeWords + 2] = 0;
+    }
+    {
+        const unsigned lane = t & 31, warp = t >> 5;
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if(lane == 0) s_warp_sum[warp] = __popc(bal);
+        __syncthreads();
+        unsigned before = 0;
+        for(unsigned w = 0; w < warp; ++w) before += s_warp_sum[w];
+        if(alive) s_alive[before + __popc(bal & ((1u << lane) - 1u))] = (unsigned)t;
+        unsigned total = 0;
+        for(unsigned w = 0; w < kSetupThreads/32; ++w) total += s_warp_sum[w];
+        nalive = (int)total;
+        __syncthreads();
+    }
 
+    // ---- phase 2 (thread per surviving triangle): edges, lighting, MergeSort order, counts ----
+    const int tri = (t < nalive) ? (int)s_alive[t] : -1;
+    if(tri >= 0)
+    {
+        uint32_t *rec = s_rec + tri*kRecWords;
+        V3 cam[3], prj[3];
+        project_triangle(tri, cam, prj);
         uint32_t emit = 0;                                  // slot of the k-th edge FillEdgeTable emits, 2 bits each
         int slot_of[3] = {-1, -1, -1};
         int mn[3], mx[3];                                   // per edge: index of upper / lower end
 
-        if(facing > 0.0f)
         {
             // pass 1: which edges survive and where MergeSort puts them (needs only y)
             int key[3];
@@ -240,9 +315,9 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 #pragma unroll
                 for(int q = 0; q < 3; ++q)
                 {
-                    float4 c4 = *reinterpret_cast<const float4 *>(&s_col[t*12 + 4*q]);
+                    float4 c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
                     float col[4] = { c4.x, c4.y, c4.z, c4.w };
-                    V3 nr = { s_nrm[t*9 + 3*q + 0], s_nrm[t*9 + 3*q + 1], s_nrm[t*9 + 3*q + 2] };
+                    V3 nr = { s_nrm[tri*9 + 3*q + 0], s_nrm[tri*9 + 3*q + 1], s_nrm[tri*9 + 3*q + 2] };
                     light_vertex(cam[q], nr, col, v, lit[q]);
                 }
                 int max_row = (int)0x80000000;
@@ -284,7 +359,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             }
         }
         rec[R_NEDGES] = (uint32_t)nedges; rec[R_FIRSTROW] = (uint32_t)first_row;
-        rec[R_MAXY] = (uint32_t)max_y; rec[R_PRIM] = m.prim_base + base + t;
+        rec[R_MAXY] = (uint32_t)max_y; rec[R_PRIM] = m.prim_base + base + (unsigned)tri;
         rec[R_EDGE0 + 3*kEdgeWords] = emit; rec[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec[R_EDGE0 + 3*kEdgeWords + 2] = 0;
 
         have_walk = (nedges >= 2) && out.spans != nullptr;
@@ -338,7 +413,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     const int a = max(y, v.band_y0);
                     if(a < nxt)
                     {
-                        const int b0 = (a - v.band_y0)/v.tile_h, b1 = (nxt - 1 - v.band_y0)/v.tile_h;
+                        const int b0 = (a - v.band_y0) >> v.tile_h_shift, b1 = (nxt - 1 - v.band_y0) >> v.tile_h_shift;
                         my_segs += b1 - b0 + ((b0 == last_band) ? 0 : 1);
                         last_band = b1;
                         my_spans += nxt - a;
@@ -371,22 +446,71 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                 unsigned cg = s_warp_sum[w], cp = s_warp_sum2[w];
                 s_warp_sum[w] = run_g; s_warp_sum2[w] = run_p; run_g += cg; run_p += cp;
             }
-            s_seg_base = run_g ? atomicAdd(out.seg_total, run_g) : 0u;
-            s_span_base = run_p ? atomicAdd(out.span_total, run_p) : 0u;
+            // region-relative bases; fits == false marks the whole CTA as overflowed (host re-issues)
+            const unsigned region = blockIdx.x % kSubAllocators;
+            const unsigned seg_region = out.seg_capacity/kSubAllocators, span_region = out.span_capacity/kSubAllocators;
+            const unsigned g0 = run_g ? atomicAdd(out.seg_fill + region, run_g) : 0u;
+            const unsigned p0 = run_p ? atomicAdd(out.span_fill + region, run_p) : 0u;
+            s_fits = ((unsigned long long)g0 + run_g <= seg_region && (unsigned long long)p0 + run_p <= span_region) ? 1u : 0u;
+            s_seg_base = region*seg_region + g0;
+            s_span_base = region*span_region + p0;
         }
         __syncthreads();
         seg_at = s_seg_base + s_warp_sum[warp] + (incl_g - (unsigned)my_segs);
         span_at = s_span_base + s_warp_sum2[warp] + (incl_p - (unsigned)my_spans);
     }
 
+    // ---- hand the walks out again: compact the triangles that have rows to walk and sort them by
+    //      row count (counting sort in shared memory), so that warps are dense and hold triangles of
+    //      similar height.  Lanes of a warp walk in lock step, so a warp costs its tallest triangle;
+    //      without this, culled / off-band / short triangles leave most lanes idle. ----
+    {
+        const bool mine_walks = tri >= 0 && have_walk && s_fits != 0u;
+        const int my_rows = mine_walks ? (walk_end - first_row) : 0;
+        const int key = mine_walks ? (kSortBins - 1 - min(my_rows, kSortBins - 1)) : kSortBins;   // tall first, idle last
+        if(t <= kSortBins) s_hist[t] = 0;
+        __syncthreads();
+        const unsigned rank = atomicAdd(&s_hist[key], 1u);
+        s_w_first[t] = first_row; s_w_end[t] = walk_end;
+        s_w_info[t] = (unsigned)nedges | ((unsigned)nonfinite << 8) | (mine_walks ? 0x8000u : 0u) | ((unsigned)my_segs << 16);
+        s_w_spans[t] = (unsigned)my_spans;
+        s_w_seg_at[t] = seg_at; s_w_span_at[t] = span_at; s_w_tri[t] = tri;
+        __syncthreads();
+        if(t < 32)
+        {
+            // exclusive scan of the kSortBins + 1 bin counts by one warp (three bins per lane)
+            unsigned a = s_hist[3*t], b = (3*t + 1 <= kSortBins) ? s_hist[3*t + 1] : 0u, c3 = (3*t + 2 <= kSortBins) ? s_hist[3*t + 2] : 0u;
+            unsigned sum = a + b + c3, incl = sum;
+#pragma unroll
+            for(int d = 1; d < 32; d <<= 1)
+            {
+                unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+                if(t >= d) incl += up;
+            }
+            unsigned run = incl - sum;
+            s_hist[3*t] = run; run += a;
+            if(3*t + 1 <= kSortBins) { s_hist[3*t + 1] = run; run += b; }
+            if(3*t + 2 <= kSortBins) { s_hist[3*t + 2] = run; }
+        }
+        __syncthreads();
+        s_order[s_hist[key] + rank] = (unsigned)t;          // order inside a bin is irrelevant
+        __syncthreads();
+    }
+
     // ---- the row walk.  All 32 lanes of a warp stay in the loops below (warp-wide trip counts,
     //      predicated bodies): list events are handled for all lanes that have one at the same
     //      time, then the rows up to each lane's next event run in lock step. ----
     {
-        const bool walking = (unsigned)t < n && have_walk &&
-                             (unsigned long long)seg_at + (unsigned)my_segs <= out.seg_capacity &&
-                             (unsigned long long)span_at + (unsigned)my_spans <= out.span_capacity;
-        const uint32_t *rec = s_rec + t*kRecWords;
+        const int slot = (int)s_order[t];                   // whose phase-2 results this thread walks
+        const int tri = max(s_w_tri[slot], 0);              // that triangle's index inside the CTA
+        const unsigned info = s_w_info[slot];
+        const int nedges = (int)(info & 0xffu);
+        const int nonfinite = (int)((info >> 8) & 0x7fu);
+        const int my_segs = (int)(info >> 16), my_spans = (int)s_w_spans[slot];
+        const int first_row = s_w_first[slot], walk_end = s_w_end[slot];
+        const unsigned seg_at = s_w_seg_at[slot], span_at = s_w_span_at[slot];
+        const bool walking = (info & 0x8000u) != 0;
+        const uint32_t *rec = s_rec + tri*kRecWords;
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
         ActiveEdge L, R;
         L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;
@@ -398,12 +522,12 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         int seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
         unsigned seg_span0 = 0;
         unsigned pairs = 0;
-        const unsigned prim = m.prim_base + base + t;
+        const unsigned prim = m.prim_base + base + (unsigned)tri;
         // depth bucket of the whole triangle: 0 = nearest (largest camera z, projekt.cpp:525)
         unsigned bucket = 0;
         if(walking)
         {
-            const float ztri = fmaxf(fmaxf(s_pos[t*9 + 2], s_pos[t*9 + 5]), s_pos[t*9 + 8]) + m.pz;
+            const float ztri = fmaxf(fmaxf(s_pos[tri*9 + 2], s_pos[tri*9 + 5]), s_pos[tri*9 + 8]) + m.pz;
             const float f = (out.zrange[0] - ztri)*out.zrange[1]*(float)kDepthBuckets;
             if(f > 0.0f) bucket = (unsigned)min((int)f, kDepthBuckets - 1);
         }
@@ -412,7 +536,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         {
             if(seg_band < 0) return;
             int tx0 = 1, tx1 = 0;
-            if(seg_minx <= seg_maxx) { tx0 = seg_minx/v.tile_w; tx1 = seg_maxx/v.tile_w; }
+            if(seg_minx <= seg_maxx) { tx0 = seg_minx >> v.tile_w_shift; tx1 = seg_maxx >> v.tile_w_shift; }
             SegInfo si;
             si.tile_row = (unsigned)seg_band | (bucket << 24);
             si.tx = (unsigned)tx0 | ((unsigned)tx1 << 16);
@@ -442,7 +566,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     {
                         if(in_band)
                         {
-                            const int band = (y - v.band_y0)/v.tile_h;
+                            const int band = (y - v.band_y0) >> v.tile_h_shift;
                             if(band != seg_band)
                             {
                                 close_segment();
@@ -495,7 +619,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                                     Q[2] = make_float4(a3, 0.0f, 0.0f, 0.0f);
                                     Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), az);
                                     SegInfo si;
-                                    const unsigned trow = (unsigned)((ay - v.band_y0)/v.tile_h);
+                                    const unsigned trow = (unsigned)((ay - v.band_y0) >> v.tile_h_shift);
                                     si.tile_row = trow | (bucket << 24); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
                                     out.segs[asg] = si;
                                     atomicAdd(&out.tile_count[(trow*v.tiles_x)*kDepthBuckets + bucket], 1u);
