@@ -26,6 +26,7 @@
 namespace b200r {
 
 constexpr int kSetupThreads = 128;
+constexpr int kEdgeRec = 3*kEdgeWords;   // 45 words of edge data per triangle in shared memory
 constexpr int kSortBins = 64;        // walkers are sorted by min(rows, 63); 3 bins per lane of one warp >= 65
 
 struct V3 { float x, y, z; };
@@ -143,13 +144,15 @@ __global__ void zrange_finish_kernel(unsigned *zkeys)
     reinterpret_cast<float *>(zkeys)[1] = inv;
 }
 
-__global__ void __launch_bounds__(kSetupThreads)
+__global__ void __launch_bounds__(kSetupThreads, 5)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
     __shared__ __align__(16) float s_pos[kSetupThreads*9];
     __shared__ __align__(16) float s_col[kSetupThreads*12];
     __shared__ __align__(16) float s_nrm[kSetupThreads*9];
-    __shared__ __align__(16) uint32_t s_rec[kSetupThreads*kRecWords];
+    // per triangle only the 3 x 15 edge words live in shared memory (odd stride: conflict-free);
+    // `rec` pointers below are biased by -R_EDGE0 so that rec[R_EDGE0 + ...] addresses them.
+    __shared__ __align__(16) uint32_t s_edge[kSetupThreads*kEdgeRec];
     __shared__ unsigned s_binned, s_pairs, s_seg_base, s_span_base, s_fits;
     __shared__ unsigned s_hist[kSortBins + 2 + 32], s_order[kSetupThreads], s_alive[kSetupThreads];
     __shared__ int s_w_tri[kSetupThreads];
@@ -241,10 +244,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const bool off_band = out.recs == nullptr &&
                               (ymax_p < (float)(v.band_y0 - 2) || ymin_p > (float)(v.band_y1 + 1));
         alive = facing > 0.0f && !off_band;
-        // default record header: no edges (overwritten in phase 2 for survivors)
-        uint32_t *rec0 = s_rec + t*kRecWords;
-        rec0[R_NEDGES] = 0; rec0[R_FIRSTROW] = 0; rec0[R_MAXY] = 0; rec0[R_PRIM] = m.prim_base + base + t;
-        rec0[R_EDGE0 + 3*kEdgeWords] = 0; rec0[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec0[R_EDGE0 + 3*kEdgeWords + 2] = 0;
+        // b200r_fill_edge_table only: default record header (no edges), overwritten in phase 2
+        if(out.recs)
+        {
+            uint32_t *g = out.recs + (size_t)(m.prim_base + base + t)*kRecWords;
+            g[R_NEDGES] = 0; g[R_FIRSTROW] = 0; g[R_MAXY] = 0; g[R_PRIM] = m.prim_base + base + t;
+            g[R_EDGE0 + 3*kEdgeWords] = 0;
+        }
     }
     {
         const unsigned lane = t & 31, warp = t >> 5;
@@ -264,7 +270,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     const int tri = (t < nalive) ? (int)s_alive[t] : -1;
     if(tri >= 0)
     {
-        uint32_t *rec = s_rec + tri*kRecWords;
+        uint32_t *rec = s_edge + tri*kEdgeRec - R_EDGE0;
         V3 cam[3], prj[3];
         project_triangle(tri, cam, prj);
         uint32_t emit = 0;                                  // slot of the k-th edge FillEdgeTable emits, 2 bits each
@@ -358,9 +364,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                 max_y = (max_row > v.height) ? v.height : max_row;                                   // :187-196
             }
         }
-        rec[R_NEDGES] = (uint32_t)nedges; rec[R_FIRSTROW] = (uint32_t)first_row;
-        rec[R_MAXY] = (uint32_t)max_y; rec[R_PRIM] = m.prim_base + base + (unsigned)tri;
-        rec[R_EDGE0 + 3*kEdgeWords] = emit; rec[R_EDGE0 + 3*kEdgeWords + 1] = 0; rec[R_EDGE0 + 3*kEdgeWords + 2] = 0;
+        if(out.recs)                                        // b200r_fill_edge_table only
+        {
+            uint32_t *g = out.recs + (size_t)(m.prim_base + base + (unsigned)tri)*kRecWords;
+            g[R_NEDGES] = (uint32_t)nedges; g[R_FIRSTROW] = (uint32_t)first_row; g[R_MAXY] = (uint32_t)max_y;
+            g[R_EDGE0 + 3*kEdgeWords] = emit;
+            for(int w = 0; w < nedges*kEdgeWords; ++w) g[R_EDGE0 + w] = rec[R_EDGE0 + w];
+        }
 
         have_walk = (nedges >= 2) && out.spans != nullptr;
         nonfinite = 0;
@@ -510,7 +520,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const int first_row = s_w_first[slot], walk_end = s_w_end[slot];
         const unsigned seg_at = s_w_seg_at[slot], span_at = s_w_span_at[slot];
         const bool walking = (info & 0x8000u) != 0;
-        const uint32_t *rec = s_rec + tri*kRecWords;
+        const uint32_t *rec = s_edge + tri*kEdgeRec - R_EDGE0;
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
         ActiveEdge L, R;
         L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;
@@ -670,13 +680,6 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     }
     __syncthreads();
 
-    // coalesced 128-bit record store (only b200r_fill_edge_table asks for the records)
-    if(out.recs)
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(s_rec);
-        float4 *dst = reinterpret_cast<float4 *>(out.recs) + (size_t)(m.prim_base + base)*kRecVec4;
-        for(unsigned i = t; i < n*kRecVec4; i += kSetupThreads) dst[i] = src[i];
-    }
     if(t == 0 && s_binned)
     {
         atomicAdd(&out.counters[0], (unsigned long long)s_binned);
