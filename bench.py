@@ -221,14 +221,14 @@ def time_cpu(ol, s, threads, steps, warmup, kind):
             ol.RefLoadedBitmap(s.width, s.height, c.strides[0], c.ctypes.data) for c in colors])
         zptrs = (ol.f32p * threads)(*[z.ctypes.data_as(ol.f32p) for z in zs])
         cmd = os_.ref_commands(zs[0])
-        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc))
+        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc), 0)
         fb = C.cast(lib_o.orc_ref_fallback, C.c_void_p)
         user = C.cast(C.pointer(ctx), C.c_void_p)
         for i in range(warmup + steps):
             colors[0].fill(s.clear_color); zs[0].fill(s.clear_depth)
             t0 = time.perf_counter()
             lib.ref_render_triangles_mt(os_.pos_p, os_.col_p, os_.nrm_p, os_.uvs_p, n, os_.P,
-                                        C.byref(cmd), bmps, zptrs, threads, skip.ctypes.data, fb, user)
+                                        C.byref(cmd), bmps, zptrs, threads, skip.ctypes.data, fb, user, 0)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)

@@ -99,8 +99,16 @@ int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm
                             uint32_t VertexCount, const float P[3], const orc_scene *Scene,
                             orc_edge *Edges, orc_edge *Temp)
 {
+    return orc_fill_edge_table_ex(Pos, Col, Nrm, VertexCount, P, Scene, 0, Edges, Temp);
+}
+
+/* projekt.cpp:3882-4121, Object->Bitmap == 0; Phong selects :4012-4019 instead of :4020-4064. */
+int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *Nrm,
+                               uint32_t VertexCount, const float P[3], const orc_scene *Scene,
+                               int32_t Phong, orc_edge *Edges, orc_edge *Temp)
+{
     static const uint32_t Indices[3][2] = { {0, 1}, {1, 2}, {2, 0} };   /* :3936-3941 */
-    if(Scene->LightCount == 0) return -1;
+    if(Scene->LightCount == 0 && !Phong) return -1;
     uint32_t TriangleCount = VertexCount/3;                      /* :3886 */
     uint32_t Visible = 0;
     for(uint32_t Tri = 0; Tri < TriangleCount; ++Tri)
@@ -125,7 +133,14 @@ int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm
 
         for(int v = 0; v < 3; ++v)
         {
-            light_vertex(Cam[v], Nrm + 9*(size_t)Tri + 3*v, Col + 12*(size_t)Tri + 4*v, Scene, Lit[v]);
+            if(Phong)                                            /* :4014-4015: colours stay unlit */
+            {
+                for(int i = 0; i < 4; ++i) Lit[v][i] = Col[12*(size_t)Tri + 4*v + i];
+            }
+            else
+            {
+                light_vertex(Cam[v], Nrm + 9*(size_t)Tri + 3*v, Col + 12*(size_t)Tri + 4*v, Scene, Lit[v]);
+            }
         }
 
         for(uint32_t e = 0; e < 3; ++e)                          /* :3947 */
@@ -163,6 +178,12 @@ int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm
                 {
                     E->ColorGradient[i] = (Lit[MaxI][i] - E->MinColor[i])/YDiff;
                 }
+                for(int i = 0; i < 3; ++i)                       /* :4017-4018, :4104-4109 */
+                {
+                    /* the start normal is NOT advanced by the top clip (only colour is, :4091) */
+                    E->MinNormal[i] = Phong ? Nrm[9*(size_t)Tri + 3*MinI + i] : 0.0f;
+                    E->NormalGradient[i] = Phong ? (Nrm[9*(size_t)Tri + 3*MaxI + i] - E->MinNormal[i])/YDiff : 0.0f;
+                }
                 E->Triangle = (int32_t)Tri;
                 ++Visible;                                       /* :4068 */
             }
@@ -175,6 +196,7 @@ int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm
 /* Running state of one edge while it is in the active list. */
 typedef struct active_edge {
     float X, Z, C[4];
+    float N[3];                                                  /* Phong only */
     const orc_edge *E;
 } active_edge;
 
@@ -188,21 +210,65 @@ static int edge_before(const active_edge *New, const active_edge *Old)
 }
 
 /* projekt.cpp:306-425 (span set-up) and 510-538 (Gouraud pixel loop). */
+/* UnprojectVertex, projekt.cpp:147-160 */
+static void unproject_vertex(float X, float Y, float Z, const orc_transform *T, float Out[3])
+{
+    float Dist = T->DistanceAboveTarget - Z;                     /* :152 */
+    float Inv = 1.0f/T->MetersToPixels;
+    float Ax = Inv*(X - T->ScreenCenterX), Ay = Inv*(Y - T->ScreenCenterY);   /* :154 */
+    float S = Dist/T->FocalLength;                               /* :155 */
+    Out[0] = S*Ax; Out[1] = S*Ay; Out[2] = Z;
+}
+
+/* Per-pixel Phong colour, projekt.cpp:452-483.  pow(x,16) is the C++ pow(float,int) overload:
+ * double precision, then narrowed to r32 (:478). */
+static void phong_shade(const float Color[4], const float Normal[3], float X, float Row, float Z,
+                        const orc_scene *Scene, float Out[4])
+{
+    float Final[4] = {0, 0, 0, 0};                               /* :448 */
+    float Pw[3];
+    unproject_vertex(X, Row, Z, &Scene->Transform, Pw);          /* :455-458 */
+    for(uint32_t Li = 0; Li < Scene->LightCount; ++Li)
+    {
+        const orc_light *Light = Scene->Lights + Li;
+        if(Li == 0) for(int i = 0; i < 4; ++i) Final[i] = Color[i]*Scene->Ambient[i];   /* :466 */
+        float ToLight[3] = { Light->P[0] - Pw[0], Light->P[1] - Pw[1], Light->P[2] - Pw[2] };
+        float Ld[3], Vd[3], Hd[3];
+        normalize3(ToLight, Ld);                                 /* :471 */
+        float Cos = clamp01(inner3(Normal, Ld));                 /* :474 */
+        float Neg[3] = { -Pw[0], -Pw[1], -Pw[2] };
+        normalize3(Neg, Vd);                                     /* :475 */
+        float Sum[3] = { Ld[0] + Vd[0], Ld[1] + Vd[1], Ld[2] + Vd[2] };
+        normalize3(Sum, Hd);                                     /* :476 */
+        float Term = clamp01(inner3(Normal, Hd));                /* :477 */
+        Term = (float)pow((double)Term, 16.0);                   /* :478 */
+        for(int i = 0; i < 4; ++i)                               /* :480 */
+        {
+            Final[i] = Final[i] + (Cos*(Color[i]*Light->Intensity[i]) + Term*(1.0f*Light->Intensity[i]));
+        }
+    }
+    for(int i = 0; i < 4; ++i) Out[i] = clamp01(Final[i]);       /* :483 */
+}
+
 static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Row,
-                          int32_t PrimIndex, orc_target *T, orc_stats *Stats)
+                          int32_t PrimIndex, orc_target *T, orc_stats *Stats,
+                          const orc_scene *Scene, int32_t Phong)
 {
     float XDiff = roundf(R->X - L->X);                           /* :311-312 */
-    float CInc[4], ZInc;
+    float CInc[4], ZInc, NInc[3];
     if(XDiff != 0.0f)                                            /* :333-363 */
     {
         for(int i = 0; i < 4; ++i) CInc[i] = (R->C[i] - L->C[i])/XDiff;
+        for(int i = 0; i < 3; ++i) NInc[i] = (R->N[i] - L->N[i])/XDiff;      /* :344-349 */
         ZInc = (R->Z - L->Z)/XDiff;
     }
     else
     {
         for(int i = 0; i < 4; ++i) CInc[i] = 0.0f;
+        for(int i = 0; i < 3; ++i) NInc[i] = 0.0f;
         ZInc = 0.0f;
     }
+    float N[3] = { L->N[0], L->N[1], L->N[2] };                  /* :378 */
     float Z = L->Z;                                              /* :375 */
     float C[4] = { L->C[0], L->C[1], L->C[2], L->C[3] };         /* :379 */
     float XOffset = 0.0f;
@@ -215,6 +281,7 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
     int32_t MinX = (int32_t)(float)round_s32(LeftX);             /* :402-406 */
     int32_t MaxX = (int32_t)(float)round_s32(RightX);
     Z += XOffset*ZInc;                                           /* :408 */
+    for(int i = 0; i < 3; ++i) N[i] += XOffset*NInc[i];          /* :411 */
     for(int i = 0; i < 4; ++i) C[i] += XOffset*CInc[i];          /* :412 */
 
     uint32_t *Pixel = (uint32_t *)((uint8_t *)T->Color + (size_t)MinX*4 + (size_t)Row*T->Pitch);  /* :414 */
@@ -233,13 +300,16 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
         if(X >= T->Width && !(Contiguous && Row + 1 < T->Height))
         {
             ++ZPixel; ++Pixel; if(Prim) ++Prim;
+            if(Phong) { float Tn[3] = { N[0] + NInc[0], N[1] + NInc[1], N[2] + NInc[2] }; normalize3(Tn, N); }
             for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];
             Z += ZInc;
             continue;
         }
+        float F[4] = { C[0], C[1], C[2], C[3] };                 /* :513 */
+        if(Phong) phong_shade(C, N, (float)X, (float)Row, Z, Scene, F);     /* :450-483 */
         /* colour is r,g,b,a = C[0..3]; packed A R G B (:520-523) */
-        uint32_t Color32 = (round_u32(C[3]*255.0f) << 24) | (round_u32(C[0]*255.0f) << 16) |
-                           (round_u32(C[1]*255.0f) << 8) | (round_u32(C[2]*255.0f) << 0);
+        uint32_t Color32 = (round_u32(F[3]*255.0f) << 24) | (round_u32(F[0]*255.0f) << 16) |
+                           (round_u32(F[1]*255.0f) << 8) | (round_u32(F[2]*255.0f) << 0);
         if(Stats) Stats->Fragments += 1;
         if(Z > *ZPixel)                                          /* :525 */
         {
@@ -249,8 +319,9 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
             if(Stats) Stats->DepthPasses += 1;
         }
         ++ZPixel; ++Pixel; if(Prim) ++Prim;
-        for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];        /* :534 */
-        Z += ZInc;                                               /* :535 */
+        if(Phong) { float Tn[3] = { N[0] + NInc[0], N[1] + NInc[1], N[2] + NInc[2] }; normalize3(Tn, N); }   /* :504 */
+        for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];        /* :534 / :505 */
+        Z += ZInc;                                               /* :535 / :506 */
     }
 }
 
@@ -264,6 +335,12 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
  *     :274-278): bit 2 of the result reports that case. */
 int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
                           orc_target *T, orc_stats *Stats)
+{
+    return orc_draw_triangle_ex(Edges, EdgeCount, PrimIndex, T, Stats, 0, 0);
+}
+
+int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
+                             orc_target *T, orc_stats *Stats, const orc_scene *Scene, int32_t Phong)
 {
     if(EdgeCount == 0) return 0;
     if(EdgeCount > 3) EdgeCount = 3;
@@ -284,6 +361,7 @@ int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t Pri
             active_edge New;
             New.X = Edges[e].XMin; New.Z = Edges[e].ZMin; New.E = Edges + e;
             for(int i = 0; i < 4; ++i) New.C[i] = Edges[e].MinColor[i];
+            for(int i = 0; i < 3; ++i) New.N[i] = Edges[e].MinNormal[i];
             uint32_t At = Count;
             for(uint32_t k = 0; k < Count; ++k)
             {
@@ -303,7 +381,7 @@ int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t Pri
         if(Count < 2) continue;                                  /* defined: nothing happens */
 
         active_edge *L = &List[0], *R = &List[1];                /* :300-303, first pair only */
-        orc_fill_span(L, R, Row, PrimIndex, T, Stats);           /* Row >= 0 always (:308) */
+        orc_fill_span(L, R, Row, PrimIndex, T, Stats, Scene, Phong);   /* Row >= 0 always (:308) */
         Result |= 1;
         L->X += L->E->Gradient;      R->X += R->E->Gradient;     /* :542-543 */
         L->Z += L->E->ZGradient;     R->Z += R->E->ZGradient;    /* :545-546 */
@@ -311,6 +389,13 @@ int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t Pri
         {
             L->C[i] += L->E->ColorGradient[i];
             R->C[i] += R->E->ColorGradient[i];
+        }
+        if(Phong)                                                /* :551-552 */
+        {
+            float Tl[3], Tr[3];
+            for(int i = 0; i < 3; ++i) { Tl[i] = L->N[i] + L->E->NormalGradient[i]; Tr[i] = R->N[i] + R->E->NormalGradient[i]; }
+            normalize3(Tl, L->N);
+            normalize3(Tr, R->N);
         }
         if(L->X > R->X)                                          /* :562-572 */
         {
@@ -322,18 +407,25 @@ int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t Pri
 }
 
 /* One triangle = one object: FillEdgeTable on the 3-vertex object, then the level-1 walk. */
+static int32_t render_one_ex(const float *Pos, const float *Col, const float *Nrm, uint32_t Tri,
+                             const float P[3], const orc_scene *Scene, int32_t Phong, orc_target *T,
+                             int32_t PrimIndex, orc_stats *Stats)
+{
+    orc_edge Edges[3], Temp[3];
+    int32_t Count = orc_fill_edge_table_ex(Pos + 9*(size_t)Tri, Col + 12*(size_t)Tri, Nrm + 9*(size_t)Tri,
+                                           3, P, Scene, Phong, Edges, Temp);
+    if(Count < 0) return Count;
+    if(Stats) { Stats->Triangles += 1; if(Count > 0) Stats->Visible += 1; }
+    int32_t R = orc_draw_triangle_ex(Edges, (uint32_t)Count, PrimIndex, T, Stats, Scene, Phong);
+    if(Stats && (R & 2)) Stats->RefWouldCrash += 1;
+    return R;
+}
+
 static int32_t render_one(const float *Pos, const float *Col, const float *Nrm, uint32_t Tri,
                           const float P[3], const orc_scene *Scene, orc_target *T,
                           int32_t PrimIndex, orc_stats *Stats)
 {
-    orc_edge Edges[3], Temp[3];
-    int32_t Count = orc_fill_edge_table(Pos + 9*(size_t)Tri, Col + 12*(size_t)Tri, Nrm + 9*(size_t)Tri,
-                                        3, P, Scene, Edges, Temp);
-    if(Count < 0) return Count;
-    if(Stats) { Stats->Triangles += 1; if(Count > 0) Stats->Visible += 1; }
-    int32_t R = orc_draw_triangle(Edges, (uint32_t)Count, PrimIndex, T, Stats);
-    if(Stats && (R & 2)) Stats->RefWouldCrash += 1;
-    return R;
+    return render_one_ex(Pos, Col, Nrm, Tri, P, Scene, 0, T, PrimIndex, Stats);
 }
 
 int32_t orc_render_triangles(const float *Pos, const float *Col, const float *Nrm,
@@ -341,10 +433,18 @@ int32_t orc_render_triangles(const float *Pos, const float *Col, const float *Nr
                              orc_target *Target, int32_t PrimBase, uint8_t *WouldCrash,
                              orc_stats *Stats)
 {
-    if(Scene->LightCount == 0) return -1;
+    return orc_render_triangles_ex(Pos, Col, Nrm, TriangleCount, P, Scene, 0, Target, PrimBase, WouldCrash, Stats);
+}
+
+int32_t orc_render_triangles_ex(const float *Pos, const float *Col, const float *Nrm,
+                                uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
+                                int32_t Phong, orc_target *Target, int32_t PrimBase, uint8_t *WouldCrash,
+                                orc_stats *Stats)
+{
+    if(Scene->LightCount == 0 && !Phong) return -1;
     for(uint32_t Tri = 0; Tri < TriangleCount; ++Tri)
     {
-        int32_t R = render_one(Pos, Col, Nrm, Tri, P, Scene, Target, PrimBase + (int32_t)Tri, Stats);
+        int32_t R = render_one_ex(Pos, Col, Nrm, Tri, P, Scene, Phong, Target, PrimBase + (int32_t)Tri, Stats);
         if(WouldCrash) WouldCrash[Tri] = (uint8_t)((R & 2) ? 1 : 0);
     }
     return 0;
@@ -446,6 +546,6 @@ void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
     orc_target T;
     T.Width = B->Width; T.Height = B->Height; T.Pitch = B->Pitch;
     T.Color = (uint32_t *)B->Memory; T.Z = C->ZBuffer; T.ZStride = C->Width; T.Prim = 0;
-    render_one(Ctx->Pos, Ctx->Col, Ctx->Nrm, TriangleIndex, Ctx->P, Ctx->Scene, &T,
-               (int32_t)TriangleIndex, 0);
+    render_one_ex(Ctx->Pos, Ctx->Col, Ctx->Nrm, TriangleIndex, Ctx->P, Ctx->Scene, Ctx->Phong, &T,
+                  (int32_t)TriangleIndex, 0);
 }

@@ -9,7 +9,8 @@
  *   orc_draw_triangle       projekt.cpp:198-303, 542-597 active-edge walk, "level 1":
  *                           one triangle = one object, defined behaviour where the reference
  *                           dereferences a null list pointer
- *   orc_fill_span           projekt.cpp:306-425, 510-538 span set-up + Gouraud pixel loop
+ *   orc_fill_span           projekt.cpp:306-425, 510-538 span set-up + Gouraud pixel loop;
+ *                           450-509 per-pixel Phong loop (UnprojectVertex 147-160)
  *
  * Pinning: the missing math layer is pinned by oracle/ref_shim.h, so
  * with respect to upstream this path is PARITY UNPINNED (the reference ships no tests, golden
@@ -54,6 +55,8 @@ typedef struct orc_edge {
     float ColorGradient[4];
     int32_t Left;
     int32_t Triangle;                   /* provenance only (not in the reference) */
+    float MinNormal[3];                 /* Phong only (projekt.cpp:4017, 4104-4109) */
+    float NormalGradient[3];
 } orc_edge;
 
 typedef struct orc_target {
@@ -83,6 +86,10 @@ void orc_project_vertex(const float Cam[3], const orc_transform *T, float Out[3]
 int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm,
                             uint32_t VertexCount, const float P[3], const orc_scene *Scene,
                             orc_edge *Edges, orc_edge *Temp);
+/* Same with PhongShading != 0 (projekt.cpp:4012-4019, 4104-4109): unlit colours, vertex normals. */
+int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *Nrm,
+                               uint32_t VertexCount, const float P[3], const orc_scene *Scene,
+                               int32_t Phong, orc_edge *Edges, orc_edge *Temp);
 
 void orc_merge_sort(uint32_t Count, orc_edge *First, orc_edge *Temp);
 
@@ -90,6 +97,9 @@ void orc_merge_sort(uint32_t Count, orc_edge *First, orc_edge *Temp);
  * Returns a bit mask: 1 = drew at least one span, 2 = the verbatim reference would crash. */
 int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
                           orc_target *Target, orc_stats *Stats);
+/* Same with per-pixel Phong shading (projekt.cpp:450-509, 551-552); Scene gives lights + transform. */
+int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
+                             orc_target *Target, orc_stats *Stats, const orc_scene *Scene, int32_t Phong);
 
 /* Per-triangle semantics over a soup, in submission order.  PrimBase is added to the
  * triangle index stored in Target->Prim.  WouldCrash (optional, one byte per triangle). */
@@ -97,6 +107,10 @@ int32_t orc_render_triangles(const float *Pos, const float *Col, const float *Nr
                              uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
                              orc_target *Target, int32_t PrimBase, uint8_t *WouldCrash,
                              orc_stats *Stats);
+int32_t orc_render_triangles_ex(const float *Pos, const float *Col, const float *Nrm,
+                                uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
+                                int32_t Phong, orc_target *Target, int32_t PrimBase, uint8_t *WouldCrash,
+                                orc_stats *Stats);
 
 /* Same result, Threads workers with private targets folded in submission order. */
 int32_t orc_render_triangles_mt(const float *Pos, const float *Col, const float *Nrm,
@@ -109,6 +123,7 @@ typedef struct orc_fallback_ctx {
     const float *Pos, *Col, *Nrm;
     float P[3];
     const orc_scene *Scene;
+    int32_t Phong;
 } orc_fallback_ctx;
 void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
                       void *RefGameRenderCommands);

@@ -118,6 +118,30 @@ def main():
         out[f"{name}_ref_crashes"] = np.int64(o["would_crash"].sum())
         out[f"{name}_covered"] = np.int64((r["z"] != np.float32(s.clear_depth)).sum())
 
+    # ---- per-pixel Phong path (projekt.cpp:450-509, 4012-4019): verbatim images and hashes -----
+    phong = {}
+    for name, s in kat_scenes.all_scenes().items():
+        o = ol.oracle_render(s, phong=True)
+        r = ol.ref_render_triangles(s, skip=o["would_crash"], use_fallback=True, phong=True)
+        phong[f"kat_{name}_color"] = r["color"]
+        phong[f"kat_{name}_z"] = r["z"].view(np.uint32)
+    for name, kw in {"soup_small": dict(seed=0xB2000002, count=30_000, width=1280, height=720, rmin=1.5, rmax=6.0),
+                     "soup_large": dict(seed=0xB2000003, count=1_500, width=1280, height=720, rmin=32.0, rmax=96.0)}.items():
+        s = sc.triangle_soup(name, **kw)
+        o = ol.oracle_render(s, phong=True)
+        r = ol.ref_render_triangles(s, skip=o["would_crash"], use_fallback=True, phong=True)
+        phong[f"{name}_color_hash"] = np.array(ol.fnv1a64_words(r["color"]))
+        phong[f"{name}_z_hash"] = np.array(ol.fnv1a64_words(r["z"]))
+    s = sc.sphere_scene(pos, col, nrm, uvs, 960, 540, 135.0)
+    e, n = ol.ref_edge_table(s, phong=True)
+    cols = [np.ascontiguousarray(e[f]).view(np.uint32).reshape(len(e), -1) for f in ol.PHONG_FIELDS]
+    phong["sphere_540p_edges"] = np.concatenate(cols, axis=1)
+    o = ol.oracle_render(s, phong=True)
+    r = ol.ref_render_triangles(s, skip=o["would_crash"], use_fallback=True, phong=True)
+    phong["sphere_540p_color"] = r["color"]
+    phong["sphere_540p_z_hash"] = np.array(ol.fnv1a64_words(r["z"]))
+    np.savez_compressed(os.path.join(HERE, "reference_vectors_phong.npz"), **phong)
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     for k in sorted(out):
         v = out[k]

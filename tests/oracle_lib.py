@@ -44,12 +44,14 @@ class OrcEdge(C.Structure):
     _fields_ = [("YMin", C.c_int32), ("YMax", C.c_int32), ("XMin", C.c_float),
                 ("Gradient", C.c_float), ("ZMin", C.c_float), ("ZGradient", C.c_float),
                 ("MinColor", C.c_float * 4), ("ColorGradient", C.c_float * 4),
-                ("Left", C.c_int32), ("Triangle", C.c_int32)]
+                ("Left", C.c_int32), ("Triangle", C.c_int32),
+                ("MinNormal", C.c_float * 3), ("NormalGradient", C.c_float * 3)]
 
 
 ORC_EDGE_DTYPE = np.dtype([("YMin", "<i4"), ("YMax", "<i4"), ("XMin", "<f4"), ("Gradient", "<f4"),
                            ("ZMin", "<f4"), ("ZGradient", "<f4"), ("MinColor", "<f4", 4),
-                           ("ColorGradient", "<f4", 4), ("Left", "<i4"), ("Triangle", "<i4")])
+                           ("ColorGradient", "<f4", 4), ("Left", "<i4"), ("Triangle", "<i4"),
+                           ("MinNormal", "<f4", 3), ("NormalGradient", "<f4", 3)])
 
 
 class OrcTarget(C.Structure):
@@ -69,7 +71,7 @@ class OrcStats(C.Structure):
 
 class OrcFallbackCtx(C.Structure):
     _fields_ = [("Pos", f32p), ("Col", f32p), ("Nrm", f32p), ("P", C.c_float * 3),
-                ("Scene", C.POINTER(OrcScene))]
+                ("Scene", C.POINTER(OrcScene)), ("Phong", C.c_int32)]
 
 
 # ------------------------------------------------------------------ reference structs
@@ -121,6 +123,8 @@ REF_EDGE_DTYPE = np.dtype({
 # The fields FillEdgeTable defines in Gouraud mode (SURVEY.md 8b "Ownership").
 GOURAUD_FIELDS = ["YMin", "YMax", "XMin", "Gradient", "ZMin", "ZGradient", "MinColor",
                   "ColorGradient", "Left"]
+# Phong mode additionally defines the normals (projekt.cpp:4017, 4104-4109)
+PHONG_FIELDS = GOURAUD_FIELDS + ["MinNormal", "NormalGradient"]
 
 REF_FALLBACK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
 
@@ -157,6 +161,13 @@ def oracle():
                                              C.POINTER(OrcTarget), C.c_int32, C.c_void_p,
                                              C.POINTER(OrcStats)]
         lib.orc_render_triangles.restype = C.c_int32
+        lib.orc_render_triangles_ex.argtypes = [f32p, f32p, f32p, C.c_uint32, f32p, C.POINTER(OrcScene),
+                                                C.c_int32, C.POINTER(OrcTarget), C.c_int32, C.c_void_p,
+                                                C.POINTER(OrcStats)]
+        lib.orc_render_triangles_ex.restype = C.c_int32
+        lib.orc_fill_edge_table_ex.argtypes = [f32p, f32p, f32p, C.c_uint32, f32p, C.POINTER(OrcScene),
+                                               C.c_int32, C.c_void_p, C.c_void_p]
+        lib.orc_fill_edge_table_ex.restype = C.c_int32
         lib.orc_render_triangles_mt.argtypes = [f32p, f32p, f32p, C.c_uint32, f32p,
                                                 C.POINTER(OrcScene), C.POINTER(OrcTarget),
                                                 C.c_uint32, C.POINTER(OrcStats)]
@@ -194,11 +205,11 @@ def ref():
         lib.ref_render_object.restype = C.c_int32
         lib.ref_render_triangles.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p,
                                              C.POINTER(RefCommands), C.POINTER(RefLoadedBitmap),
-                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         lib.ref_render_triangles_mt.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p,
                                                 C.POINTER(RefCommands), C.POINTER(RefLoadedBitmap),
                                                 C.POINTER(f32p), C.c_uint32, C.c_void_p,
-                                                C.c_void_p, C.c_void_p]
+                                                C.c_void_p, C.c_void_p, C.c_int32]
         _ref = lib
     return _ref
 
@@ -265,7 +276,7 @@ def _orc_target(color, z, prim):
     return t
 
 
-def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0):
+def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0, phong=False):
     """Level-1 (one triangle = one object) render.  Returns dict(color, z, prim, stats, would_crash)."""
     lib = oracle()
     s = OracleScene(scene)
@@ -274,7 +285,10 @@ def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0):
     stats = OrcStats()
     n = scene.triangle_count
     crash = np.zeros(n, dtype=np.uint8)
-    if threads > 1:
+    if phong:
+        rc = lib.orc_render_triangles_ex(s.pos_p, s.col_p, s.nrm_p, n, s.P, C.byref(s.orc), 1, C.byref(t),
+                                         prim_base, crash.ctypes.data, C.byref(stats))
+    elif threads > 1:
         rc = lib.orc_render_triangles_mt(s.pos_p, s.col_p, s.nrm_p, n, s.P, C.byref(s.orc),
                                          C.byref(t), threads, C.byref(stats))
     else:
@@ -284,7 +298,7 @@ def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0):
     return dict(color=color, z=z, prim=prim, stats=stats.as_dict(), would_crash=crash)
 
 
-def oracle_edge_table(scene, first_vertex=0, vertex_count=None):
+def oracle_edge_table(scene, first_vertex=0, vertex_count=None, phong=False):
     """orc_fill_edge_table over (a slice of) the scene's vertex arrays as ONE object."""
     lib = oracle()
     s = OracleScene(scene)
@@ -293,13 +307,13 @@ def oracle_edge_table(scene, first_vertex=0, vertex_count=None):
     edges = np.zeros(max(vertex_count, 1), dtype=ORC_EDGE_DTYPE)
     tmp = np.zeros(max(vertex_count, 1), dtype=ORC_EDGE_DTYPE)
     off = first_vertex
-    n = lib.orc_fill_edge_table(s.pos[off:].ctypes.data_as(f32p), s.col[off:].ctypes.data_as(f32p),
-                                s.nrm[off:].ctypes.data_as(f32p), vertex_count, s.P,
-                                C.byref(s.orc), edges.ctypes.data, tmp.ctypes.data)
+    n = lib.orc_fill_edge_table_ex(s.pos[off:].ctypes.data_as(f32p), s.col[off:].ctypes.data_as(f32p),
+                                   s.nrm[off:].ctypes.data_as(f32p), vertex_count, s.P,
+                                   C.byref(s.orc), 1 if phong else 0, edges.ctypes.data, tmp.ctypes.data)
     return edges[:max(n, 0)].copy(), n
 
 
-def ref_edge_table(scene, first_vertex=0, vertex_count=None):
+def ref_edge_table(scene, first_vertex=0, vertex_count=None, phong=False):
     """Verbatim FillEdgeTable (projekt.cpp:3882) over (a slice of) the scene as ONE object."""
     lib = ref()
     s = OracleScene(scene)
@@ -318,11 +332,12 @@ def ref_edge_table(scene, first_vertex=0, vertex_count=None):
     obj.NormalData = s.nrm.ctypes.data + first_vertex * 12
     obj.UVData = s.uvs.ctypes.data + first_vertex * 8
     obj.EdgeMemory = edges.ctypes.data
-    n = lib.ref_fill_edge_table(C.byref(obj), C.byref(cmd), 0)
+    obj.PhongShading = 1 if phong else 0
+    n = lib.ref_fill_edge_table(C.byref(obj), C.byref(cmd), 1 if phong else 0)
     return edges[:max(n, 0)].copy(), n
 
 
-def ref_render_object(scene, targets=None):
+def ref_render_object(scene, targets=None, phong=False):
     """Level 0: the whole scene as ONE object through verbatim FillEdgeTable + DrawModel."""
     lib = ref()
     s = OracleScene(scene)
@@ -338,11 +353,12 @@ def ref_render_object(scene, targets=None):
     obj.VertexData, obj.ColorData = s.pos.ctypes.data, s.col.ctypes.data
     obj.NormalData, obj.UVData = s.nrm.ctypes.data, s.uvs.ctypes.data
     obj.EdgeMemory = edges.ctypes.data
+    obj.PhongShading = 1 if phong else 0
     rc = lib.ref_render_object(C.byref(obj), C.byref(cmd), C.byref(bmp))
     return dict(color=color, z=z, status=rc)
 
 
-def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, targets=None):
+def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, targets=None, phong=False):
     """One triangle = one object through the verbatim call pair.  ``skip`` marks triangles the
     reference would crash on; with ``use_fallback`` they are drawn by the oracle port."""
     lib = ref()
@@ -356,12 +372,12 @@ def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, target
     fb, user = None, None
     ctx = None
     if use_fallback:
-        ctx = OrcFallbackCtx(s.pos_p, s.col_p, s.nrm_p, s.P, C.pointer(s.orc))
+        ctx = OrcFallbackCtx(s.pos_p, s.col_p, s.nrm_p, s.P, C.pointer(s.orc), 1 if phong else 0)
         fb = C.cast(oracle().orc_ref_fallback, C.c_void_p)
         user = C.cast(C.pointer(ctx), C.c_void_p)
     if threads <= 1:
         lib.ref_render_triangles(s.pos_p, s.col_p, s.nrm_p, s.uvs_p, n, s.P, C.byref(cmd),
-                                 C.byref(bmp), skip_p, status.ctypes.data, fb, user)
+                                 C.byref(bmp), skip_p, status.ctypes.data, fb, user, 1 if phong else 0)
     else:
         colors = [color] + [color.copy() for _ in range(threads - 1)]
         zs = [z] + [z.copy() for _ in range(threads - 1)]
@@ -369,7 +385,7 @@ def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, target
             RefLoadedBitmap(scene.width, scene.height, c.strides[0], c.ctypes.data) for c in colors])
         zptrs = (f32p * threads)(*[zz.ctypes.data_as(f32p) for zz in zs])
         lib.ref_render_triangles_mt(s.pos_p, s.col_p, s.nrm_p, s.uvs_p, n, s.P, C.byref(cmd), bmps,
-                                    zptrs, threads, skip_p, fb, user)
+                                    zptrs, threads, skip_p, fb, user, 1 if phong else 0)
     return dict(color=color, z=z, status=status)
 
 
