@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libb200raster.so")
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM, E_NO_DEVICE = 0, -1, -2, -3, -4, -5
 WHOLE_OBJECT_AEL = 1
+MESH_PHONG = 1
 
 EXPORTS = [
     "b200r_create", "b200r_destroy", "b200r_last_error", "b200r_set_stream", "b200r_sync",
@@ -72,7 +73,7 @@ class render_entry_3d_object(C.Structure):
 
 class device_mesh(C.Structure):
     _fields_ = [("Positions", C.c_void_p), ("Colors", C.c_void_p), ("Normals", C.c_void_p),
-                ("TriangleCount", C.c_uint32), ("P", v3)]
+                ("TriangleCount", C.c_uint32), ("P", v3), ("Flags", C.c_uint32)]
 
 
 class device_target(C.Structure):
@@ -214,9 +215,10 @@ class Renderer:
         return s.as_dict()
 
     # ---- host-pointer drop-in (FillEdgeTable + DrawModel pair, projekt.cpp:3882 + 162) ----
-    def render_scene_host(self, scene, color: np.ndarray, depth: np.ndarray, splits=None, flags=0):
+    def render_scene_host(self, scene, color: np.ndarray, depth: np.ndarray, splits=None, flags=0, phong=False):
         """Render ``scene`` into host arrays color[H,W] u32 / depth[H,W] f32 in place.
-        ``splits``: optional list of vertex counts to submit the scene as several objects."""
+        ``splits``: optional list of vertex counts to submit the scene as several objects.
+        ``phong``: bool, or one bool per split (render_entry_3d_object::PhongShading)."""
         assert color.dtype == np.uint32 and depth.dtype == np.float32
         nv = scene.positions.shape[0]
         splits = splits or [nv]
@@ -227,6 +229,7 @@ class Renderer:
             o = objs[i]
             o.P = v3(*scene.object_p)
             o.VertexCount = cnt
+            o.PhongShading = int(phong[i] if isinstance(phong, (list, tuple)) else phong)
             o.VertexData = scene.positions.ctypes.data + at * 12
             o.ColorData = scene.colors.ctypes.data + at * 16
             o.NormalData = scene.normals.ctypes.data + at * 12
@@ -238,7 +241,7 @@ class Renderer:
                                                   C.byref(bmp), flags))
         del keep
 
-    def fill_edge_table(self, scene, first_vertex=0, vertex_count=None):
+    def fill_edge_table(self, scene, first_vertex=0, vertex_count=None, phong=False):
         """b200r_fill_edge_table over (a slice of) the scene as ONE object -> edge_info array."""
         if vertex_count is None:
             vertex_count = scene.positions.shape[0] - first_vertex
@@ -252,7 +255,8 @@ class Renderer:
         o.UVData = scene.uvs.ctypes.data + first_vertex * 8
         o.EdgeMemory = edges.ctypes.data
         cmd, keep = make_commands(scene)
-        n = self._check(self.lib.b200r_fill_edge_table(self.ctx, C.byref(o), C.byref(cmd), 0))
+        o.PhongShading = 1 if phong else 0
+        n = self._check(self.lib.b200r_fill_edge_table(self.ctx, C.byref(o), C.byref(cmd), 1 if phong else 0))
         del keep
         return edges[:n].copy()
 

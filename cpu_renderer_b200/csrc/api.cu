@@ -64,6 +64,7 @@ struct b200r_context
     cudaEvent_t total_ready = nullptr;
     std::string error;
     int tile_w = 64, tile_h = 32;
+    int span_words = kSpanWords;        // of the last issued frame (kSpanWordsPhong if it had a Phong mesh)
     int refill_lanes = 8, pend_lanes = 4;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
@@ -97,12 +98,15 @@ static int fail(b200r_context *c, int code, const char *what, cudaError_t e = cu
 
 #define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(c, B200R_E_CUDA, #call, e_); } while(0)
 
-static int fill_view(b200r_context *c, const game_render_commands *cmd, const b200r_device_target *t, ViewParams &v)
+static int fill_view(b200r_context *c, const game_render_commands *cmd, const b200r_device_target *t, ViewParams &v,
+                     bool all_phong = false)
 {
     if(!cmd || !t) return fail(c, B200R_E_INVALID, "null Commands / Target");
     const light_data &ld = cmd->LightData;
-    if(ld.LightCount == 0 || ld.LightCount > (u32)kMaxLights || !ld.Lights)
-        return fail(c, B200R_E_UNSUPPORTED, "LightCount must be 1..8 (0 lights leaves MinColor undefined in the reference, projekt.cpp:4022)");
+    // Gouraud: 0 lights leaves MinColor uninitialised in the reference (projekt.cpp:4022-4045).
+    // Phong: 0 lights is defined (FinalColor stays 0, :448).
+    if((ld.LightCount == 0 && !all_phong) || ld.LightCount > (u32)kMaxLights || (ld.LightCount && !ld.Lights))
+        return fail(c, B200R_E_UNSUPPORTED, "LightCount must be 1..8 (0 only when every object is Phong shaded)");
     if(t->Width <= 0 || t->Height <= 0 || t->BandRows <= 0 || t->BandFirstRow < 0 ||
        t->BandFirstRow + t->BandRows > t->Height || !t->Color || !t->Depth)
         return fail(c, B200R_E_INVALID, "bad target geometry");
@@ -152,10 +156,11 @@ static int issue_frame(b200r_context *c)
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
 
     const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
-    const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(kSpanWords*sizeof(uint32_t)), 0xffffffffu);
+    const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(c->span_words*sizeof(uint32_t)), 0xffffffffu);
     SetupOutputs so;
     so.recs = nullptr;
     so.spans = (uint32_t *)c->spans.ptr;
+    so.span_words = c->span_words;
     so.segs = (SegInfo *)c->segs.ptr;
     so.seg_fill = words->seg_fill;
     so.span_fill = words->span_fill;
@@ -207,6 +212,7 @@ static int issue_frame(b200r_context *c)
     RasterParams rp;
     rp.v = v;
     rp.spans = so.spans;
+    rp.span_words = c->span_words;
     rp.overflow = &words->overflow;
     rp.seg_capacity = seg_cap;
     rp.span_capacity = span_cap;
@@ -258,12 +264,12 @@ static int settle_pending(b200r_context *c)
             // in which CTA lands in which region).
             CU(cudaStreamSynchronize(c->stream));
             const unsigned seg_region = (unsigned)(c->segs.bytes/sizeof(SegInfo))/kSubAllocators;
-            const unsigned span_region = (unsigned)(c->spans.bytes/(kSpanWords*sizeof(uint32_t)))/kSubAllocators;
+            const unsigned span_region = (unsigned)(c->spans.bytes/(c->span_words*sizeof(uint32_t)))/kSubAllocators;
             const bool truncated = hw.seg_max > seg_region || hw.span_max > span_region;
             if(hw.seg_max > seg_region)
                 CU(c->segs.reserve(((size_t)hw.seg_max + hw.seg_max/8 + 64)*kSubAllocators*sizeof(SegInfo)));
             if(hw.span_max > span_region)
-                CU(c->spans.reserve(((size_t)hw.span_max + hw.span_max/8 + 64)*kSubAllocators*kSpanWords*sizeof(uint32_t)));
+                CU(c->spans.reserve(((size_t)hw.span_max + hw.span_max/8 + 64)*kSubAllocators*c->span_words*sizeof(uint32_t)));
             // with truncated lists the queue total was an under-count: leave headroom
             CU(c->pairs.reserve((size_t)std::max<uint64_t>(total, truncated ? nspan*2 : 0)*sizeof(unsigned)));
             c->stats.Reruns += 1;
@@ -367,8 +373,14 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     int rc = settle_pending(c);                 // the previous frame must be complete in the stream
     if(rc != B200R_OK) return rc;
 
+    bool any_phong = false, all_phong = mesh_count > 0;
+    for(u32 i = 0; i < mesh_count; ++i)
+    {
+        const bool ph = (meshes[i].Flags & B200R_MESH_PHONG) != 0;
+        any_phong |= ph; all_phong &= ph;
+    }
     ViewParams v;
-    rc = fill_view(c, cmd, target, v);
+    rc = fill_view(c, cmd, target, v, all_phong);
     if(rc != B200R_OK) return rc;
 
     uint64_t total = 0;
@@ -384,6 +396,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
         mp.ntri = m.TriangleCount;
         mp.px = m.P.x; mp.py = m.P.y; mp.pz = m.P.z;
         mp.prim_base = (unsigned)total;
+        mp.phong = (m.Flags & B200R_MESH_PHONG) ? 1 : 0;
         total += m.TriangleCount;
         ms.push_back(mp);
     }
@@ -392,7 +405,9 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
     // first guesses (2.5 segments, 6 spans, 8 queue entries per triangle); all lists grow on demand
     if(c->segs.bytes == 0) CU(c->segs.reserve((size_t)std::max<uint64_t>(total*5/2, 1u << 16)*sizeof(SegInfo)));
-    if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*kSpanWords*sizeof(uint32_t)));
+    // a frame with a Phong mesh uses the wider span record for all its spans
+    c->span_words = any_phong ? kSpanWordsPhong : kSpanWords;
+    if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*c->span_words*sizeof(uint32_t)));
     // counts, cursors, offsets (+1 end entry), and the scan's chunk scratch
     CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1 + 2*((size_t)ntiles*kDepthBuckets/8192 + 2))*sizeof(unsigned)));
     if(c->pairs.bytes == 0)
@@ -457,7 +472,7 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
     for(u32 i = 0; i < n; ++i)
     {
         const render_entry_3d_object &o = objs[i];
-        if(o.PhongShading || o.Bitmap) return fail(c, B200R_E_UNSUPPORTED, "Phong / textured objects are not implemented (SURVEY.md 8f rows 1-2)");
+        if(o.Bitmap) return fail(c, B200R_E_UNSUPPORTED, "textured objects are not implemented (SURVEY.md 8f row 2)");
         u32 tris = o.VertexCount/3;                          // projekt.cpp:3886
         if(tris && (!o.VertexData || !o.ColorData || !o.NormalData)) return fail(c, B200R_E_INVALID, "object with null vertex stream");
         verts += (uint64_t)tris*3;
@@ -477,6 +492,7 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
         m.Normals = (const r32 *)c->d_nrm.ptr + at*3;
         m.TriangleCount = tris;
         m.P = o.P;
+        m.Flags = o.PhongShading ? B200R_MESH_PHONG : 0u;
         if(nv)
         {
             CU(cudaMemcpyAsync((void *)m.Positions, o.VertexData, nv*12, cudaMemcpyHostToDevice, c->stream));
@@ -556,7 +572,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
 {
     if(!c) return B200R_E_INVALID;
     if(!obj || !cmd) return fail(c, B200R_E_INVALID, "null argument");
-    if(phong || obj->PhongShading || obj->Bitmap) return fail(c, B200R_E_UNSUPPORTED, "Phong / textured edge tables are not implemented");
+    if(obj->Bitmap) return fail(c, B200R_E_UNSUPPORTED, "textured edge tables are not implemented");
     if(!obj->EdgeMemory) return fail(c, B200R_E_INVALID, "null EdgeMemory");
     CU(cudaSetDevice(c->device));
     int rc = settle_pending(c);
@@ -575,7 +591,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     t.ColorPitch = t.Width*4; t.DepthStride = t.Width;
     t.Color = (u32 *)16; t.Depth = (r32 *)16;    // never dereferenced: raster is not launched
     ViewParams v;
-    rc = fill_view(c, cmd, &t, v);
+    rc = fill_view(c, cmd, &t, v, phong != 0);
     if(rc != B200R_OK) return rc;
     v.tiles_x = 1; v.tiles_y = 1; v.tile_w = 1 << 21; v.tile_h = 1 << 21; v.tile_w_shift = v.tile_h_shift = 21;
     CU(c->recs.reserve((size_t)tris*kRecWords*sizeof(uint32_t)));
@@ -587,12 +603,13 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     SetupOutputs so;
     so.recs = (uint32_t *)c->recs.ptr; so.spans = nullptr; so.segs = nullptr;
     so.seg_fill = words->seg_fill; so.span_fill = words->span_fill; so.extra_total = &words->extra_total;
-    so.seg_capacity = 0; so.span_capacity = 0;
+    so.seg_capacity = 0; so.span_capacity = 0; so.span_words = kSpanWords;
     so.tile_count = tile_count; so.counters = words->counters;
     so.zrange = reinterpret_cast<const float *>(words->zkeys);
     MeshParams mp;
     mp.pos = meshes[0].Positions; mp.col = meshes[0].Colors; mp.nrm = meshes[0].Normals;
     mp.ntri = tris; mp.px = obj->P.x; mp.py = obj->P.y; mp.pz = obj->P.z; mp.prim_base = 0;
+    mp.phong = phong ? 1 : 0;
     launch_setup(v, mp, so, c->stream);
     c->stats.KernelLaunches += 1;
     CU(cudaGetLastError());
@@ -602,7 +619,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
 
     // Host side of FillEdgeTable's tail: append each triangle's edges in the reference's
     // emission order (edge 0-1, 1-2, 2-0; projekt.cpp:3947) and apply MergeSort's permutation.
-    struct Ref { uint64_t key; const uint32_t *edge; };
+    struct Ref { uint64_t key; const uint32_t *edge; u32 tri; };
     std::vector<Ref> order;
     order.reserve((size_t)tris*3);
     for(u32 tri = 0; tri < tris; ++tri)
@@ -613,7 +630,7 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
         for(int k = 0; k < ne; ++k)
         {
             int slot = (emit >> (2*k)) & 3;
-            order.push_back({0, rec + R_EDGE0 + slot*kEdgeWords});
+            order.push_back({0, rec + R_EDGE0 + slot*kEdgeWords, tri});
         }
     }
     const uint32_t n = (uint32_t)order.size();
@@ -639,8 +656,21 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
         o.MinColor.x = f(E_C + 0); o.MinColor.y = f(E_C + 1); o.MinColor.z = f(E_C + 2); o.MinColor.w = f(E_C + 3);
         o.ColorGradient.x = f(E_DC + 0); o.ColorGradient.y = f(E_DC + 1);
         o.ColorGradient.z = f(E_DC + 2); o.ColorGradient.w = f(E_DC + 3);
-        o.Left = (b32)E[E_LEFT];
+        o.Left = (b32)(E[E_LEFT] & 1u);
         o.Next = nullptr;
+        if(phong)
+        {
+            // projekt.cpp:4017-4018, 4104-4109: MinNormal = the upper vertex's normal (not advanced by
+            // the top clip), NormalGradient = (MaxNormal - MinNormal)/YDifference -- one IEEE
+            // subtraction and division each, done here on the host from the caller's NormalData
+            const float *N = (const float *)obj->NormalData + (size_t)order[i].tri*9;
+            const int mn = (int)((E[E_LEFT] >> 8) & 3u), mx = (int)((E[E_LEFT] >> 16) & 3u);
+            const volatile float ydiff = (float)o.YMax - (float)o.YMin;
+            const float *a = N + 3*mn, *b = N + 3*mx;
+            o.MinNormal.x = a[0]; o.MinNormal.y = a[1]; o.MinNormal.z = a[2];
+            volatile float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+            o.NormalGradient.x = dx/ydiff; o.NormalGradient.y = dy/ydiff; o.NormalGradient.z = dz/ydiff;
+        }
     }
     return (int)n;
 }

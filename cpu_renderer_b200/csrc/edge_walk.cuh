@@ -14,11 +14,13 @@ struct ActiveEdge
 {
     float x, z, c0, c1, c2, c3;         // running XMin, ZMin, MinColor
     float dx, dz, d0, d1, d2, d3;       // Gradient, ZGradient, ColorGradient
+    float n0, n1, n2, g0, g1, g2;       // Phong: running MinNormal, NormalGradient
     int ymax;
     int id;                             // slot in the triangle record
 };
 
-__device__ __forceinline__ void load_edge(ActiveEdge &a, const uint32_t *rec, int id)
+// nrm: the triangle's three staged vertex normals (Phong), or nullptr
+__device__ __forceinline__ void load_edge(ActiveEdge &a, const uint32_t *rec, int id, const float *nrm)
 {
     const uint32_t *E = rec + R_EDGE0 + id*kEdgeWords;
     a.ymax = (int)E[E_YMAX];
@@ -29,14 +31,38 @@ __device__ __forceinline__ void load_edge(ActiveEdge &a, const uint32_t *rec, in
     a.d0 = __uint_as_float(E[E_DC + 0]);  a.d1 = __uint_as_float(E[E_DC + 1]);
     a.d2 = __uint_as_float(E[E_DC + 2]);  a.d3 = __uint_as_float(E[E_DC + 3]);
     a.id = id;
+    if(nrm)
+    {
+        // projekt.cpp:4017-4018, 4104-4109: MinNormal = upper vertex normal (not advanced by the
+        // top clip), NormalGradient = (MaxNormal - MinNormal)/YDifference
+        const int mn = (int)((E[E_LEFT] >> 8) & 3u), mx = (int)((E[E_LEFT] >> 16) & 3u);
+        const float ydiff = fsub(__int2float_rn((int)E[E_YMAX]), __int2float_rn((int)E[E_YMIN]));
+        a.n0 = nrm[3*mn + 0]; a.n1 = nrm[3*mn + 1]; a.n2 = nrm[3*mn + 2];
+        a.g0 = fdiv(fsub(nrm[3*mx + 0], a.n0), ydiff);
+        a.g1 = fdiv(fsub(nrm[3*mx + 1], a.n1), ydiff);
+        a.g2 = fdiv(fsub(nrm[3*mx + 2], a.n2), ydiff);
+    }
 }
 
-// projekt.cpp:542-549: one row down an edge.
+// Normalize(a) = a * (1/sqrt(a.a)) on three scalars (SURVEY.md Appendix A pin)
+__device__ __forceinline__ void normalize3f(float &x, float &y, float &z)
+{
+    const float s = fdiv(1.0f, __fsqrt_rn(fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z))));
+    x = fmul(s, x); y = fmul(s, y); z = fmul(s, z);
+}
+
+// projekt.cpp:542-552: one row down an edge.
+template<bool PHONG>
 __device__ __forceinline__ void step_edge(ActiveEdge &a)
 {
     a.x = fadd(a.x, a.dx);   a.z = fadd(a.z, a.dz);
     a.c0 = fadd(a.c0, a.d0); a.c1 = fadd(a.c1, a.d1);
     a.c2 = fadd(a.c2, a.d2); a.c3 = fadd(a.c3, a.d3);
+    if(PHONG)                                               // :551-552
+    {
+        a.n0 = fadd(a.n0, a.g0); a.n1 = fadd(a.n1, a.g1); a.n2 = fadd(a.n2, a.g2);
+        normalize3f(a.n0, a.n1, a.n2);
+    }
 }
 
 // The active list at row y (projekt.cpp:202-296): insert, in record order, every edge whose
@@ -46,7 +72,8 @@ __device__ __forceinline__ void step_edge(ActiveEdge &a)
 // at most two edges survive a row (a triangle's upper and lower short edges never share a row);
 // a third survivor is ignored.  next_ev = the next row at which the list can change.
 __device__ __forceinline__ void active_list_event(int y, const uint32_t *rec, int nedges,
-                                                  ActiveEdge &L, ActiveEdge &R, int &nact, int &next_ev)
+                                                  ActiveEdge &L, ActiveEdge &R, int &nact, int &next_ev,
+                                                  const float *nrm)
 {
     int ids[3] = {0, 0, 0};
     float xs[3] = {0.0f, 0.0f, 0.0f};
@@ -60,7 +87,7 @@ __device__ __forceinline__ void active_list_event(int y, const uint32_t *rec, in
         const uint32_t *E = rec + R_EDGE0 + e*kEdgeWords;
         if((int)E[E_YMIN] != y || n >= 3) continue;
         const float nx = __uint_as_float(E[E_X]), ng = __uint_as_float(E[E_DX]);
-        const int nl = (int)E[E_LEFT];
+        const int nl = (int)(E[E_LEFT] & 1u);
         int at = n;
 #pragma unroll
         for(int k = 2; k >= 0; --k)
@@ -68,7 +95,7 @@ __device__ __forceinline__ void active_list_event(int y, const uint32_t *rec, in
             if(k >= n) continue;
             const uint32_t *O = rec + R_EDGE0 + ids[k]*kEdgeWords;
             const float ox = xs[k], og = __uint_as_float(O[E_DX]);
-            const int ol = (int)O[E_LEFT];
+            const int ol = (int)(O[E_LEFT] & 1u);
             if(nx < ox || (nx == ox && (ng < og || (ng == og && nl < ol)))) at = k;   // ends as the first such k
         }
 #pragma unroll
@@ -96,13 +123,13 @@ __device__ __forceinline__ void active_list_event(int y, const uint32_t *rec, in
     {
         if(oldn >= 1 && kid0 == oldL.id) L = oldL;
         else if(oldn >= 2 && kid0 == oldR.id) L = oldR;
-        else load_edge(L, rec, kid0);
+        else load_edge(L, rec, kid0, nrm);
     }
     if(kept >= 2)
     {
         if(oldn >= 1 && kid1 == oldL.id) R = oldL;
         else if(oldn >= 2 && kid1 == oldR.id) R = oldR;
-        else load_edge(R, rec, kid1);
+        else load_edge(R, rec, kid1, nrm);
     }
     nact = (kept > 2) ? 2 : kept;
     int ev = 0x7fffffff;

@@ -51,6 +51,7 @@ struct MeshParams
     unsigned ntri;
     float px, py, pz;           // render_entry_3d_object::P
     unsigned prim_base;         // submission index of this mesh's first triangle
+    int phong;                  // render_entry_3d_object::PhongShading
 };
 
 // Compact per-triangle record written by the setup kernel and read by the raster kernel:
@@ -60,16 +61,21 @@ constexpr int kEdgeWords = 15;      // ymin ymax x dx z dz c[4] dc[4] left
 constexpr int kRecWords = 52;       // 4 header + 3*15 + 3 pad  = 208 bytes = 13 float4
 constexpr int kRecVec4 = kRecWords/4;
 enum { E_YMIN = 0, E_YMAX = 1, E_X = 2, E_DX = 3, E_Z = 4, E_DZ = 5, E_C = 6, E_DC = 10, E_LEFT = 14 };
+// E_LEFT word: bit 0 = edge_info::Left; bits 8-9 / 16-17 = index (0..2) of the edge's upper / lower
+// vertex in the triangle (Phong: normals are re-read from the staged vertex normals)
 enum { R_NEDGES = 0, R_FIRSTROW = 1, R_MAXY = 2, R_PRIM = 3, R_EDGE0 = 4 };
 
 // Span record: one row of one triangle, fully set up (projekt.cpp:306-412 done once, in the
 // set-up kernel): the inclusive column range, the values at the first column and the per-pixel
 // increments.  The raster kernel only replays the per-pixel adds and depth-tests.
-constexpr int kSpanWords = 16;      // 64 bytes = 4 float4
+constexpr int kSpanWords = 16;      // Gouraud frame: 64 bytes = 4 float4
+constexpr int kSpanWordsPhong = 24; // frame with a Phong mesh: + normal at the first column, per-pixel normal increment
 constexpr int kSpanVec4 = kSpanWords/4;
 enum { P_PRIM = 0, P_Y = 1, P_MINX = 2, P_MAXX = 3, P_Z = 4, P_C = 5, P_ZI = 9, P_CI = 10, P_FLAGS = 14, P_ZUB = 15 };
 // P_ZUB: an upper bound of every depth value the span can produce (see span_depth_bound)
 constexpr unsigned kSpanNonFinite = 1u;   // colours may be NaN/Inf/huge -> guarded pack
+constexpr unsigned kSpanAlias = 4u;       // Phong alias pixel: shade at X = word 19, Row = word 20 (not at its own column/row)
+constexpr unsigned kSpanPhong = 2u;       // per-pixel Phong shading (projekt.cpp:450-509): words 16..21 hold the normals
 
 // Segment: the consecutive spans of one triangle that share one pair of active edges and lie in
 // one tile-row band; the unit the binner scatters (its spans are contiguous in the span array).
@@ -84,7 +90,8 @@ struct SegInfo
 struct RasterParams
 {
     ViewParams v;
-    const uint32_t *spans;      // kSpanWords per span
+    const uint32_t *spans;      // span_words per span
+    int span_words;             // kSpanWords, or kSpanWordsPhong when any mesh of the frame is Phong
     const unsigned *overflow;   // device word set by finalize_kernel: some list did not fit, skip the frame
     unsigned seg_capacity, span_capacity;
     const unsigned *tile_offset;    // [tile*kDepthBuckets + bucket], plus one end entry
@@ -174,7 +181,8 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 struct SetupOutputs
 {
     uint32_t *recs;             // optional (b200r_fill_edge_table): kRecWords per triangle
-    uint32_t *spans;            // kSpanWords per span (null: no row walk, records only)
+    uint32_t *spans;            // span_words per span (null: no row walk, records only)
+    int span_words;
     SegInfo *segs;
     unsigned *seg_fill;         // [kSubAllocators] device counters, one per region of the arrays
     unsigned *span_fill;        // [kSubAllocators]

@@ -70,6 +70,55 @@ __device__ __forceinline__ uint32_t pack_argb(float r, float g, float b, float a
            ((uint32_t)__float2int_rn(fg) << 8) | ((uint32_t)__float2int_rn(fb) << 0);
 }
 
+// ---- per-pixel Phong shading, projekt.cpp:450-483 (UnprojectVertex :147-160) -----------------
+__device__ __forceinline__ void normalize3r(float &x, float &y, float &z)
+{
+    const float s = fdiv(1.0f, __fsqrt_rn(fadd(fadd(fmul(x, x), fmul(y, y)), fmul(z, z))));
+    x = fmul(s, x); y = fmul(s, y); z = fmul(s, z);
+}
+
+// c: interpolated (unlit) colour, n: interpolated normal, (X, Row, Z): the pixel's screen position
+// and depth.  pow(x, 16) is a double-precision pow narrowed to r32 in the reference (:478); x^16
+// by four double squarings differs from it by at most 3 double roundings, far inside the +-1 LSB
+// colour tolerance of this path.  The pack is always the guarded one: a degenerate normal or half
+// vector yields NaN, which cvtss2si turns into 0x80000000 (:490-493).
+__device__ __noinline__ uint32_t phong_pixel(const ViewParams &v, float c0, float c1, float c2, float c3,
+                                             float n0, float n1, float n2, float X, float Row, float Z, bool guarded)
+{
+    const float dist = fsub(v.dist, Z);                                     // :152
+    const float inv = fdiv(1.0f, v.m2p);
+    const float ax = fmul(inv, fsub(X, v.cx)), ay = fmul(inv, fsub(Row, v.cy));   // :154
+    const float sc = fdiv(dist, v.focal);                                   // :155
+    const float px = fmul(sc, ax), py = fmul(sc, ay), pz = Z;
+    const float c[4] = { c0, c1, c2, c3 };
+    float f[4] = { 0.0f, 0.0f, 0.0f, 0.0f };                                // :448
+    for(int l = 0; l < v.nlights; ++l)
+    {
+        const DevLight &L = v.lights[l];
+        if(l == 0)                                                          // :464-467
+        {
+#pragma unroll
+            for(int i = 0; i < 4; ++i) f[i] = fmul(c[i], v.amb[i]);
+        }
+        float lx = fsub(L.px, px), ly = fsub(L.py, py), lz = fsub(L.pz, pz);
+        normalize3r(lx, ly, lz);                                            // :471
+        const float cosi = clamp01(fadd(fadd(fmul(n0, lx), fmul(n1, ly)), fmul(n2, lz)));   // :474
+        float vx = -px, vy = -py, vz = -pz;
+        normalize3r(vx, vy, vz);                                            // :475
+        float hx = fadd(lx, vx), hy = fadd(ly, vy), hz = fadd(lz, vz);
+        normalize3r(hx, hy, hz);                                            // :476
+        float term = clamp01(fadd(fadd(fmul(n0, hx), fmul(n1, hy)), fmul(n2, hz)));         // :477
+        double d = (double)term;
+        d = __dmul_rn(d, d); d = __dmul_rn(d, d); d = __dmul_rn(d, d); d = __dmul_rn(d, d);
+        term = __double2float_rn(d);                                        // :478
+        const float I[4] = { L.ir, L.ig, L.ib, L.ia };
+#pragma unroll
+        for(int i = 0; i < 4; ++i)                                          // :480
+            f[i] = fadd(f[i], fadd(fmul(cosi, fmul(c[i], I[i])), fmul(term, fmul(1.0f, I[i]))));
+    }
+    return pack_argb(clamp01(f[0]), clamp01(f[1]), clamp01(f[2]), clamp01(f[3]), guarded);   // :483-493
+}
+
 template<int TW, int TH>
 struct TileLayout
 {
@@ -77,7 +126,8 @@ struct TileLayout
     static constexpr int kBytes = kPix*16 + 16;     // pixels + mbarrier
 };
 
-template<int TW, int TH, int WARPS>
+// PHONG: the frame contains Phong meshes (24-word span records; per-span flag selects the shading)
+template<int TW, int TH, int WARPS, bool PHONG>
 __global__ void __launch_bounds__(WARPS*32)
 raster_kernel(const RasterParams p)
 {
@@ -194,6 +244,9 @@ raster_kernel(const RasterParams p)
             const uint32_t tile_addr = smem_addr(tile);
             const int xlast = x0 + cols - 1;
             float z = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, zi = 0, i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+            float n0 = 0, n1 = 0, n2 = 0, ni0 = 0, ni1 = 0, ni2 = 0;       // Phong: normal and its per-pixel increment
+            float shade_dx = 0, shade_row = 0;                             // Phong: X = x + shade_dx, Row for UnprojectVertex
+            bool phong_span = false;
             int prim = 0, n_left = 0, x = 0;
             uint32_t rowaddr = tile_addr;                  // shared address of column 0 of the span's row
             bool guarded = false, exhausted = false, pending = false;
@@ -211,7 +264,10 @@ raster_kernel(const RasterParams p)
                     const uint32_t pa = rowaddr + (uint32_t)x*16u;
                     Pixel mine;
                     mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
-                    mine.color = pack_argb(c0, c1, c2, c3, guarded); mine.pad = 0;
+                    mine.color = (PHONG && phong_span)
+                                 ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
+                                 : pack_argb(c0, c1, c2, c3, guarded);
+                    mine.pad = 0;
                     Pixel old = lds_pixel(pa);
                     while(true)
                     {
@@ -222,6 +278,7 @@ raster_kernel(const RasterParams p)
                         if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
                         old = prev;
                     }
+                    if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
                     c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
                     z = fadd(z, zi);                                                              // :535
                     ++x; --n_left;
@@ -249,7 +306,7 @@ raster_kernel(const RasterParams p)
                         if(idx < cnt)
                         {
                             const unsigned sp = __ldg(p.pair_list + off + idx);
-                            const float4 *S = reinterpret_cast<const float4 *>(p.spans + (size_t)sp*kSpanWords);
+                            const float4 *S = reinterpret_cast<const float4 *>(p.spans + (size_t)sp*(PHONG ? kSpanWordsPhong : kSpanWords));
                             const float4 q0 = __ldg(S), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
                             prim = __float_as_int(q0.x);
                             const int y = __float_as_int(q0.y);
@@ -258,6 +315,18 @@ raster_kernel(const RasterParams p)
                             c3 = q2.x; zi = q2.y; i0 = q2.z; i1 = q2.w;
                             i2 = q3.x; i3 = q3.y;
                             guarded = (__float_as_uint(q3.z) & kSpanNonFinite) != 0;
+                            if(PHONG)
+                            {
+                                const unsigned fl = __float_as_uint(q3.z);
+                                phong_span = (fl & kSpanPhong) != 0;
+                                shade_dx = 0.0f; shade_row = (float)y;
+                                if(phong_span)
+                                {
+                                    const float4 q4 = __ldg(S + 4), q5 = __ldg(S + 5);
+                                    n0 = q4.x; n1 = q4.y; n2 = q4.z; ni0 = q4.w; ni1 = q5.x; ni2 = q5.y;
+                                    if(fl & kSpanAlias) { shade_dx = q4.w; shade_row = q5.x; ni0 = ni1 = ni2 = 0.0f; }
+                                }
+                            }
                             const int xe = min(maxx, xlast);
                             x = minx;
                             n_left = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
@@ -291,6 +360,7 @@ raster_kernel(const RasterParams p)
                     }
                     else if(n_left > 0)
                     {
+                        if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
                         c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
                         z = fadd(z, zi);                                                              // :535
                         ++x; --n_left;
@@ -336,11 +406,11 @@ raster_kernel(const RasterParams p)
     bulk_wait_read();
 }
 
-template<int TW, int TH, int WARPS>
+template<int TW, int TH, int WARPS, bool PHONG>
 static cudaError_t launch_one(const RasterParams &p, int sm_count, cudaStream_t s)
 {
     const int smem = TileLayout<TW, TH>::kBytes;
-    auto kern = raster_kernel<TW, TH, WARPS>;
+    auto kern = raster_kernel<TW, TH, WARPS, PHONG>;
     static bool configured = false;
     static int per_sm = 1;
     if(!configured)
@@ -358,15 +428,21 @@ static cudaError_t launch_one(const RasterParams &p, int sm_count, cudaStream_t 
     return cudaGetLastError();
 }
 
-cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s)
+template<bool PHONG>
+static cudaError_t launch_mode(const RasterParams &p, int sm_count, cudaStream_t s)
 {
     const int tw = p.v.tile_w, th = p.v.tile_h;
-    if(tw == 64 && th == 32) return launch_one<64, 32, 8>(p, sm_count, s);     // 32 KB tile
-    if(tw == 32 && th == 32) return launch_one<32, 32, 8>(p, sm_count, s);     // 16 KB
-    if(tw == 128 && th == 16) return launch_one<128, 16, 8>(p, sm_count, s);   // 32 KB
-    if(tw == 64 && th == 16) return launch_one<64, 16, 8>(p, sm_count, s);     // 16 KB
-    if(tw == 128 && th == 32) return launch_one<128, 32, 8>(p, sm_count, s);   // 64 KB
+    if(tw == 64 && th == 32) return launch_one<64, 32, 8, PHONG>(p, sm_count, s);     // 32 KB tile
+    if(tw == 32 && th == 32) return launch_one<32, 32, 8, PHONG>(p, sm_count, s);     // 16 KB
+    if(tw == 128 && th == 16) return launch_one<128, 16, 8, PHONG>(p, sm_count, s);   // 32 KB
+    if(tw == 64 && th == 16) return launch_one<64, 16, 8, PHONG>(p, sm_count, s);     // 16 KB
+    if(tw == 128 && th == 32) return launch_one<128, 32, 8, PHONG>(p, sm_count, s);   // 64 KB
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s)
+{
+    return (p.span_words == kSpanWordsPhong) ? launch_mode<true>(p, sm_count, s) : launch_mode<false>(p, sm_count, s);
 }
 
 } // namespace b200r

@@ -144,6 +144,9 @@ __global__ void zrange_finish_kernel(unsigned *zkeys)
     reinterpret_cast<float *>(zkeys)[1] = inv;
 }
 
+// PHONG: the mesh is drawn with per-pixel Phong shading (render_entry_3d_object::PhongShading,
+// projekt.cpp:4012-4019): edge colours stay unlit, edges and spans carry interpolated normals.
+template<bool PHONG>
 __global__ void __launch_bounds__(kSetupThreads, 5)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
@@ -324,7 +327,8 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     float4 c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
                     float col[4] = { c4.x, c4.y, c4.z, c4.w };
                     V3 nr = { s_nrm[tri*9 + 3*q + 0], s_nrm[tri*9 + 3*q + 1], s_nrm[tri*9 + 3*q + 2] };
-                    light_vertex(cam[q], nr, col, v, lit[q]);
+                    if(PHONG) { lit[q][0] = col[0]; lit[q][1] = col[1]; lit[q][2] = col[2]; lit[q][3] = col[3]; }   // :4014-4015
+                    else light_vertex(cam[q], nr, col, v, lit[q]);
                 }
                 int max_row = (int)0x80000000;
 #pragma unroll
@@ -357,7 +361,8 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         E[E_C + i] = __float_as_uint(c0);
                         E[E_DC + i] = __float_as_uint(fdiv(fsub(lit[mx[e]][i], c0), ydiff));         // :4096
                     }
-                    E[E_LEFT] = (ymin == round_s32(prj[e].y)) ? 1u : 0u;                             // :4093
+                    E[E_LEFT] = ((ymin == round_s32(prj[e].y)) ? 1u : 0u) |                           // :4093
+                                ((unsigned)mn[e] << 8) | ((unsigned)mx[e] << 16);
                     if(ymax > max_row) max_row = ymax;
                     if(slot_of[e] == 0) first_row = ymin;                                            // projekt.cpp:173
                 }
@@ -521,9 +526,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const unsigned seg_at = s_w_seg_at[slot], span_at = s_w_span_at[slot];
         const bool walking = (info & 0x8000u) != 0;
         const uint32_t *rec = s_edge + tri*kEdgeRec - R_EDGE0;
+        const float *nrm = PHONG ? (s_nrm + tri*9) : nullptr;
+        const int sw = out.span_words;
+        const uint32_t span_flags = (nonfinite ? kSpanNonFinite : 0u) | (PHONG ? kSpanPhong : 0u);
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
         ActiveEdge L, R;
         L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;
+        L.n0 = L.n1 = L.n2 = L.g0 = L.g1 = L.g2 = 0.0f;
         L.ymax = 0; L.id = -1; R = L;
         int nact = 0, next_ev = first_row;
         int y = first_row;
@@ -562,7 +571,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         while(__any_sync(0xffffffffu, walking && y < walk_end))
         {
             // (a) list events (projekt.cpp:202-296), together
-            if(walking && y < walk_end && y == next_ev) active_list_event(y, rec, nedges, L, R, nact, next_ev);
+            if(walking && y < walk_end && y == next_ev) active_list_event(y, rec, nedges, L, R, nact, next_ev, nrm);
             // (b) rows up to the next event
             const int nrow = (walking && y < walk_end) ? (min(next_ev, walk_end) - y) : 0;
             const int nrow_max = __reduce_max_sync(0xffffffffu, nrow);
@@ -586,11 +595,17 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         // ---- span set-up, projekt.cpp:306-412, once per row ----
                         const float xdiff = roundf(fsub(R.x, L.x));                   // :311-312
                         float zi = 0.0f, i0 = 0.0f, i1 = 0.0f, i2 = 0.0f, i3 = 0.0f;
+                        float ni0 = 0.0f, ni1 = 0.0f, ni2 = 0.0f;
                         if(xdiff != 0.0f)                                             // :333-363
                         {
                             i0 = fdiv(fsub(R.c0, L.c0), xdiff); i1 = fdiv(fsub(R.c1, L.c1), xdiff);
                             i2 = fdiv(fsub(R.c2, L.c2), xdiff); i3 = fdiv(fsub(R.c3, L.c3), xdiff);
                             zi = fdiv(fsub(R.z, L.z), xdiff);
+                            if(PHONG)                                                 // :344-349
+                            {
+                                ni0 = fdiv(fsub(R.n0, L.n0), xdiff); ni1 = fdiv(fsub(R.n1, L.n1), xdiff);
+                                ni2 = fdiv(fsub(R.n2, L.n2), xdiff);
+                            }
                         }
                         float xoff = 0.0f, leftx = L.x;                               // :381-390
                         if(leftx < 0.0f) { xoff = -leftx; leftx = 0.0f; }
@@ -603,6 +618,8 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         const float z = fadd(L.z, fmul(xoff, zi));                    // :375, :408
                         const float c0 = fadd(L.c0, fmul(xoff, i0)), c1 = fadd(L.c1, fmul(xoff, i1));   // :379, :412
                         const float c2 = fadd(L.c2, fmul(xoff, i2)), c3 = fadd(L.c3, fmul(xoff, i3));
+                        float sn0 = 0.0f, sn1 = 0.0f, sn2 = 0.0f;                     // :378, :411
+                        if(PHONG) { sn0 = fadd(L.n0, fmul(xoff, ni0)); sn1 = fadd(L.n1, fmul(xoff, ni1)); sn2 = fadd(L.n2, fmul(xoff, ni2)); }
                         if(maxx >= v.width && minx <= maxx)
                         {
                             // An end in [Width-0.5, Width) is not clamped (:387, :397) and rounds up to
@@ -614,8 +631,10 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                             if(v.alias_rows && ay < v.height && ay >= v.band_y0 && ay < v.band_y1)
                             {
                                 float az = z, a0 = c0, a1 = c1, a2 = c2, a3 = c3;
-                                for(int sx = minx; sx < v.width; ++sx)                // :534-535 up to that column
+                                float an0 = sn0, an1 = sn1, an2 = sn2;
+                                for(int sx = minx; sx < v.width; ++sx)                // :534-535 / :504-506 up to that column
                                 {
+                                    if(PHONG) { an0 = fadd(an0, ni0); an1 = fadd(an1, ni1); an2 = fadd(an2, ni2); normalize3f(an0, an1, an2); }
                                     a0 = fadd(a0, i0); a1 = fadd(a1, i1); a2 = fadd(a2, i2); a3 = fadd(a3, i3);
                                     az = fadd(az, zi);
                                 }
@@ -623,11 +642,15 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                                 if(ex < out.span_capacity && ex < out.seg_capacity)
                                 {
                                     const unsigned asp = out.span_capacity - 1u - ex, asg = out.seg_capacity - 1u - ex;
-                                    float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)asp*kSpanWords);
+                                    float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)asp*sw);
+                                    // the aliased pixel is shaded with its own X = Width, Row = y (:455-457);
+                                    // the span record says column 0 of row ay, so a Phong alias span carries the
+                                    // unprojection coordinates in its (unused) increment fields
                                     Q[0] = make_float4(__uint_as_float(prim), __int_as_float(ay), __int_as_float(0), __int_as_float(0));
                                     Q[1] = make_float4(az, a0, a1, a2);
                                     Q[2] = make_float4(a3, 0.0f, 0.0f, 0.0f);
-                                    Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(nonfinite ? kSpanNonFinite : 0u), az);
+                                    Q[3] = make_float4(0.0f, 0.0f, __uint_as_float(span_flags | (PHONG ? kSpanAlias : 0u)), az);
+                                    if(PHONG) { Q[4] = make_float4(an0, an1, an2, (float)v.width); Q[5] = make_float4((float)y, 0.0f, 0.0f, 0.0f); }
                                     SegInfo si;
                                     const unsigned trow = (unsigned)((ay - v.band_y0) >> v.tile_h_shift);
                                     si.tile_row = trow | (bucket << 24); si.tx = 0u; si.span_base = asp; si.nrows = 1u;
@@ -640,17 +663,17 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         }
                         if(in_band)
                         {
-                            float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+                            float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*sw);
                             Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
                             Q[1] = make_float4(z, c0, c1, c2);
                             Q[2] = make_float4(c3, zi, i0, i1);
-                            Q[3] = make_float4(i2, i3, __uint_as_float(nonfinite ? kSpanNonFinite : 0u),
-                                               span_depth_bound(z, zi, maxx - minx));
+                            Q[3] = make_float4(i2, i3, __uint_as_float(span_flags), span_depth_bound(z, zi, maxx - minx));
+                            if(PHONG) { Q[4] = make_float4(sn0, sn1, sn2, ni0); Q[5] = make_float4(ni1, ni2, 0.0f, 0.0f); }
                             ++span;
                             if(minx <= maxx) { seg_minx = min(seg_minx, minx); seg_maxx = max(seg_maxx, maxx); }
                         }
                     }
-                    step_edge(L); step_edge(R);                                   // :542-549
+                    step_edge<PHONG>(L); step_edge<PHONG>(R);                     // :542-552
                     if(L.x > R.x)                                                 // :562-572 (rare: keep it a branch)
                     {
                         asm volatile("" ::: "memory");
@@ -666,7 +689,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             // slots promised by the counts but not produced (cannot happen for finite input) are blanked
             for(; span < span_at + (unsigned)my_spans; ++span)
             {
-                float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*kSpanWords);
+                float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*sw);
                 Q[0] = make_float4(__uint_as_float(prim), 0.0f, __int_as_float(1), __int_as_float(0));
                 Q[1] = Q[2] = Q[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
@@ -703,7 +726,8 @@ void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &
 {
     if(m.ntri == 0) return;
     unsigned blocks = (m.ntri + kSetupThreads - 1)/kSetupThreads;
-    setup_kernel<<<blocks, kSetupThreads, 0, s>>>(v, m, out);
+    if(m.phong) setup_kernel<true><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
+    else setup_kernel<false><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
 }
 
 // ---------------------------------------------------------------- clear

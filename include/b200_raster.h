@@ -14,10 +14,11 @@
  * is included from inside the reference's own unity build, define B200R_NO_REFERENCE_TYPES
  * first so the renderer's own definitions are used.
  *
- * Semantics: Gouraud path (PhongShading == 0, Bitmap == 0); one triangle = one
- * object ("level 1"); coverage and depth bit-exact with the reference's
- * scalar arithmetic; equal depth resolved as in the reference (first submitted wins,
- * projekt.cpp:525).  There is no CPU fallback: every entry point fails with
+ * Semantics: untextured objects (Bitmap == 0), Gouraud (PhongShading == 0) or
+ * per-pixel Phong (PhongShading != 0, projekt.cpp:450-509); one triangle = one object ("level 1",
+ * SURVEY.md section 0); coverage and depth bit-exact with the reference's scalar arithmetic,
+ * Gouraud colour bit-exact, Phong colour within +-1 LSB per channel (pow(x,16) in double);
+ * equal depth resolved as in the reference (first submitted wins, projekt.cpp:525).  There is no CPU fallback: every entry point fails with
  * B200R_E_NO_DEVICE when no sm_100 device is usable.
  */
 #ifndef B200_RASTER_H
@@ -119,7 +120,7 @@ typedef struct edge_info                   /* projekt.h:17-37, 120 bytes */
 #define B200R_OK             0
 #define B200R_E_INVALID     (-1)   /* null / inconsistent arguments                           */
 #define B200R_E_CUDA        (-2)   /* a CUDA call failed; see b200r_last_error                 */
-#define B200R_E_UNSUPPORTED (-3)   /* Phong / textured object, LightCount == 0 or > 8          */
+#define B200R_E_UNSUPPORTED (-3)   /* textured object, > 8 lights, LightCount == 0 on the Gouraud path */
 #define B200R_E_NOMEM       (-4)
 #define B200R_E_NO_DEVICE   (-5)   /* no CUDA device of compute capability 10.x                */
 
@@ -158,8 +159,9 @@ int b200r_render_objects(b200r_context *Context, const render_entry_3d_object *O
 
 /* Replaces FillEdgeTable alone (projekt.cpp:3882): sorted edge_info records are written to
  * Object->EdgeMemory (host, room for VertexCount records) in the reference's MergeSort order
- * (projekt.cpp:2-72, ties included).  Only the fields the Gouraud path defines are written
- * (YMin YMax XMin Gradient ZMin ZGradient MinColor ColorGradient Left, plus Next = 0).
+ * (projekt.cpp:2-72, ties included).  Only the fields the selected path defines are written
+ * (YMin YMax XMin Gradient ZMin ZGradient MinColor ColorGradient Left, plus Next = 0; with
+ * PhongShading also MinNormal and NormalGradient).
  * Returns the edge count (>= 0) or a negative status. */
 int b200r_fill_edge_table(b200r_context *Context, const render_entry_3d_object *Object,
                           const game_render_commands *Commands, b32 PhongShading);
@@ -175,7 +177,9 @@ typedef struct b200r_device_mesh
     const r32 *Normals;        /* v3 per vertex (NormalData)  */
     u32 TriangleCount;         /* VertexCount / 3             */
     v3 P;                      /* render_entry_3d_object::P   */
+    u32 Flags;                 /* B200R_MESH_PHONG = render_entry_3d_object::PhongShading        */
 } b200r_device_mesh;
+#define B200R_MESH_PHONG 1u
 
 typedef struct b200r_device_target
 {

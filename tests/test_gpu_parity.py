@@ -220,11 +220,12 @@ def test_unsupported_and_invalid_inputs_return_codes(renderer):
     with pytest.raises(api.B200RasterError) as e:
         renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL)
     assert e.value.code == api.E_UNSUPPORTED
-    # Phong object -> unsupported, not silently Gouraud
+    # textured object -> unsupported, not silently untextured
     lib = renderer.lib
     o = api.render_entry_3d_object()
     o.VertexCount = 3
-    o.PhongShading = 1
+    dummy_bitmap = api.loaded_bitmap(1, 1, 4, color.ctypes.data)
+    o.Bitmap = C.cast(C.pointer(dummy_bitmap), C.c_void_p)
     o.VertexData, o.ColorData, o.NormalData = s.positions.ctypes.data, s.colors.ctypes.data, s.normals.ctypes.data
     cmd, keep = api.make_commands(s, z.ctypes.data, s.width)
     bmp = api.loaded_bitmap(s.width, s.height, s.width * 4, color.ctypes.data)
@@ -248,6 +249,84 @@ def test_growth_of_internal_lists_is_transparent(renderer):
         assert r.stats()["Reruns"] >= 1
     finally:
         r.close()
+
+
+# ---- per-pixel Phong path -----------------------------------------------------
+PHONG = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_phong.npz"))
+PHONG_TOLERANCE_LSB = 1      # stated bar for shaded colour: pow(x,16) is evaluated in double on both sides,
+                             # by libm's pow on the host and by four squarings on the device
+
+
+def check_phong(color, z, want_color, want_z):
+    assert np.array_equal(z.view(np.uint32), want_z.view(np.uint32))        # coverage + depth: bit-exact
+    ch = np.abs(want_color.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= PHONG_TOLERANCE_LSB, int(ch.max())
+    return int((want_color != color).sum())
+
+
+@pytest.mark.parametrize("name", sorted(kat_scenes.all_scenes()))
+def test_phong_kat_scene_against_verbatim_reference_image(renderer, name):
+    s = kat_scenes.all_scenes()[name]
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, phong=True)
+    ndiff = check_phong(color, z, PHONG[f"kat_{name}_color"], PHONG[f"kat_{name}_z"].view(np.float32))
+    assert ndiff <= 0.001 * color.size
+
+
+@pytest.mark.parametrize("tile", [(64, 32), (128, 16)])
+def test_phong_soups(renderer, tile):
+    for s in (sc.triangle_soup("ps", 0xB2000002, 30_000, 1280, 720, 1.5, 6.0),
+              sc.triangle_soup("pl", 0xB2000003, 1_500, 1280, 720, 32.0, 96.0)):
+        s.lights = [sc.Light(), sc.Light(P=(-4.0, 3.0, 6.0), intensity=(0.2, 0.5, 0.3, 0.1))]
+        want = ol.oracle_render(s, phong=True)
+        color, z, _ = ol.new_targets(s)
+        renderer.set_tile(*tile)
+        renderer.render_scene_host(s, color, z, phong=True)
+        ndiff = check_phong(color, z, want["color"], want["z"])
+        assert ndiff <= 1e-4 * color.size, ndiff
+
+
+def test_phong_sphere_and_edge_table(renderer):
+    s = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], 960, 540, 135.0)
+    e = renderer.fill_edge_table(s, phong=True)
+    words = np.concatenate([np.ascontiguousarray(e[f]).view(np.uint32).reshape(len(e), -1)
+                            for f in ol.PHONG_FIELDS], axis=1)
+    assert np.array_equal(words, PHONG["sphere_540p_edges"])
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, phong=True)
+    assert ol.fnv1a64_words(z) == str(PHONG["sphere_540p_z_hash"])
+    ch = np.abs(PHONG["sphere_540p_color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= PHONG_TOLERANCE_LSB
+
+
+def test_mixed_gouraud_and_phong_objects_in_one_call(renderer):
+    """Object 0 Gouraud, object 1 Phong, object 2 Gouraud, overlapping: submission order decides
+    equal depth across objects, whatever their shading."""
+    s = sc.triangle_soup("mix", 0x91, 9_000, 960, 540, 6.0, 40.0)
+    nv = s.positions.shape[0]
+    cuts = [0, nv // 9 * 3, nv // 9 * 6, nv]
+    want_c, want_z, _ = ol.new_targets(s)
+    for k, ph in enumerate([False, True, False]):
+        part = sc.Scene(s.name, s.width, s.height, s.transform, s.positions[cuts[k]:cuts[k + 1]],
+                        s.colors[cuts[k]:cuts[k + 1]], s.normals[cuts[k]:cuts[k + 1]], s.uvs[cuts[k]:cuts[k + 1]])
+        ol.oracle_render(part, targets=(want_c, want_z, None), phong=ph)
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, splits=[cuts[1] - cuts[0], cuts[2] - cuts[1], cuts[3] - cuts[2]],
+                               phong=[False, True, False])
+    check_phong(color, z, want_c, want_z)
+
+
+def test_phong_with_zero_lights_is_black(renderer):
+    s = sc.triangle_soup("nolight", 0x92, 500, 320, 200, 4.0, 20.0)
+    s.lights = []
+    want = ol.oracle_render(s, phong=True)
+    color, z, _ = ol.new_targets(s)
+    renderer.render_scene_host(s, color, z, phong=True)
+    check_phong(color, z, want["color"], want["z"])
+    assert (color[z != np.float32(s.clear_depth)] == 0).all()      # FinalColor stays {} (projekt.cpp:448)
 
 
 # ---- BASELINE.json sizes -------------------------------------------------------------------------
