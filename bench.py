@@ -154,7 +154,7 @@ def run_reference(args):
     scene = build_scene(args.config, 0, args.scale)
     s, sample, threads = cpu_sample(args.config, scene, sc, args.ref_sample, args.ref_threads)
     kind = "reference" if ol.ref_available() else "port"
-    res = time_cpu(ol, s, threads, args.steps, args.warmup, kind)
+    res = time_cpu(ol, s, threads, args.steps, args.warmup, kind, args.phong)
     ms = res["ms_per_step"]
     units = sample if unit == "Mtriangles/s" else scene.width * scene.height * (sample / scene.triangle_count)
     value = units / (ms * 1e-3) / 1e6
@@ -205,10 +205,10 @@ def cpu_model():
     return "unknown"
 
 
-def time_cpu(ol, s, threads, steps, warmup, kind):
+def time_cpu(ol, s, threads, steps, warmup, kind, phong=False):
     """Time the reference's scalar path (verbatim build if present, else the port) on scene s."""
     lib_o = ol.oracle()
-    pre = ol.oracle_render(s)                     # untimed: tells which triangles crash the reference
+    pre = ol.oracle_render(s, phong=phong)        # untimed: tells which triangles crash the reference
     skip = pre["would_crash"]
     n = s.triangle_count
     os_ = ol.OracleScene(s)
@@ -221,23 +221,24 @@ def time_cpu(ol, s, threads, steps, warmup, kind):
             ol.RefLoadedBitmap(s.width, s.height, c.strides[0], c.ctypes.data) for c in colors])
         zptrs = (ol.f32p * threads)(*[z.ctypes.data_as(ol.f32p) for z in zs])
         cmd = os_.ref_commands(zs[0])
-        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc), 0)
+        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc), 1 if phong else 0)
         fb = C.cast(lib_o.orc_ref_fallback, C.c_void_p)
         user = C.cast(C.pointer(ctx), C.c_void_p)
         for i in range(warmup + steps):
             colors[0].fill(s.clear_color); zs[0].fill(s.clear_depth)
             t0 = time.perf_counter()
             lib.ref_render_triangles_mt(os_.pos_p, os_.col_p, os_.nrm_p, os_.uvs_p, n, os_.P,
-                                        C.byref(cmd), bmps, zptrs, threads, skip.ctypes.data, fb, user, 0)
+                                        C.byref(cmd), bmps, zptrs, threads, skip.ctypes.data, fb, user, 1 if phong else 0)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
         same = bool(np.array_equal(zs[0].view(np.uint32), pre["z"].view(np.uint32)) and
                     np.array_equal(colors[0], pre["color"]))
-        note = (f"verbatim FillEdgeTable+DrawModel per single-triangle object (oracle/_ref), {threads} threads with "
+        note = (f"verbatim FillEdgeTable+DrawModel{' (PhongShading)' if phong else ''} per single-triangle object (oracle/_ref), {threads} threads with "
                 f"private targets folded in submission order; {int(skip.sum())} of {n} triangles that null-deref "
                 f"in the reference go through the oracle port; image identical to 1-thread oracle: {same}")
     else:
+        assert not phong, "the threaded port has no Phong variant; the verbatim build is required"
         for i in range(warmup + steps):
             color, z, _ = ol.new_targets(s)
             t = ol._orc_target(color, z, None)
@@ -291,6 +292,7 @@ def run_ours(args):
 
     # ---- the frames this rank renders in one step ------------------------------------------
     band_first, band_rows = 0, H
+    mesh_flags = api.MESH_PHONG if args.phong else 0
     frames = []                                   # (device_mesh, game_render_commands, keepalive)
     if cfgname == "c4":
         band_first, band_rows = shard.band_rows(H, world, rank, th)
@@ -301,12 +303,12 @@ def run_ours(args):
             sv.transform = copy.copy(scene.transform)
             sv.transform.distance_above_target = D
             cmd_v, keep_v = api.make_commands(sv)
-            frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*P)),
+            frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*P), mesh_flags),
                            cmd_v, keep_v))
     else:
         cmd0, keep0 = api.make_commands(scene)
         frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri,
-                                       api.v3(*scene.object_p)), cmd0, keep0))
+                                       api.v3(*scene.object_p), mesh_flags), cmd0, keep0))
     mesh, cmd, keep = frames[0]
     # c2/c3: one pre-cleared target pair per timed frame (clear outside the timed region).
     # c4/c5: one pair, cleared inside the step (a 16K^2 pair is 2 GiB; a real frame clears anyway).
@@ -418,11 +420,11 @@ def run_ours(args):
                 for _ in range(e2e_steps + 1)]
         hz = [torch.full((H, W), scene.clear_depth, dtype=torch.float32).pin_memory().numpy()
               for _ in range(e2e_steps + 1)]
-        r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps])       # warm-up (allocations)
+        r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps], phong=args.phong)       # warm-up (allocations)
         barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            r.render_scene_host(hs, hcol[i], hz[i])
+            r.render_scene_host(hs, hcol[i], hz[i], phong=args.phong)
         torch.cuda.synchronize()
         e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
         covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
@@ -492,7 +494,8 @@ def run_ours(args):
         "metric": unit, "value": to_value(ms, world), "unit": unit, "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING[cfgname],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "triangles": ntri, "width": W, "height": H,
+        "config": {"workload": workload + (" -- per-pixel Phong shading" if args.phong else ""),
+                   "shading": "phong" if args.phong else "gouraud", "triangles": ntri, "width": W, "height": H,
                    "parallelism": ({"c4": f"screen-space row bands x{world}", "c5": f"{C5_VIEWS} views over {world} ranks"}
                                    .get(cfgname, f"frame-parallel x{world}") if world > 1 else "1 GPU"),
                    "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": args.scale,
@@ -528,7 +531,7 @@ def run_ours(args):
             from cpu_renderer_b200 import scene as sc2
             s, sample, threads = cpu_sample(cfgname, scene, sc2)
             kind = "reference" if ol.ref_available() else "port"
-            res = time_cpu(ol, s, threads, 3, 1, kind)
+            res = time_cpu(ol, s, threads, 3, 1, kind, args.phong)
             units = sample if unit == "Mtriangles/s" else W * H * (sample / ntri)
             line["cpu_baseline"] = {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit,
                                     "cores": threads, "kind": kind, "sample": res["sample"],
@@ -548,6 +551,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c2", choices=sorted(METRICS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the triangle count (smoke runs only)")
+    ap.add_argument("--phong", action="store_true", help="per-pixel Phong shading (PhongShading = 1) instead of Gouraud")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", default=None, help="WxH: 64x32 (default), 32x32, 128x16, 64x16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
