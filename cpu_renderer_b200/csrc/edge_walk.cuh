@@ -38,9 +38,9 @@ __device__ __forceinline__ void load_edge(ActiveEdge &a, const uint32_t *rec, in
         const int mn = (int)((E[E_LEFT] >> 8) & 3u), mx = (int)((E[E_LEFT] >> 16) & 3u);
         const float ydiff = fsub(__int2float_rn((int)E[E_YMAX]), __int2float_rn((int)E[E_YMIN]));
         a.n0 = nrm[3*mn + 0]; a.n1 = nrm[3*mn + 1]; a.n2 = nrm[3*mn + 2];
-        a.g0 = fdiv(fsub(nrm[3*mx + 0], a.n0), ydiff);
-        a.g1 = fdiv(fsub(nrm[3*mx + 1], a.n1), ydiff);
-        a.g2 = fdiv(fsub(nrm[3*mx + 2], a.n2), ydiff);
+        a.g0 = fdiv_zq(fsub(nrm[3*mx + 0], a.n0), ydiff);
+        a.g1 = fdiv_zq(fsub(nrm[3*mx + 1], a.n1), ydiff);
+        a.g2 = fdiv_zq(fsub(nrm[3*mx + 2], a.n2), ydiff);
     }
 }
 

@@ -346,7 +346,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     }
                     int ymin = key[e];
                     float ydiff = fsub(__int2float_rn(ymax), __int2float_rn(ymin));                  // :4070
-                    float zg = fdiv(fsub(cam[mx[e]].z, cam[mn[e]].z), ydiff);                        // :4072
+                    float zg = fdiv_zq(fsub(cam[mx[e]].z, cam[mn[e]].z), ydiff);                        // :4072
                     float g = fdiv(fsub(maxv.x, minv.x), fsub(maxv.y, minv.y));                      // :4073
                     float x = fadd(minv.x, fmul(clipped, g));                                        // :4075
                     float z = fadd(cam[mn[e]].z, fmul(clipped, zg));                                 // :4076
@@ -359,7 +359,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     {
                         float c0 = fadd(fmul(omt, lit[mn[e]][i]), fmul(tt, lit[mx[e]][i]));          // :4091
                         E[E_C + i] = __float_as_uint(c0);
-                        E[E_DC + i] = __float_as_uint(fdiv(fsub(lit[mx[e]][i], c0), ydiff));         // :4096
+                        E[E_DC + i] = __float_as_uint(fdiv_zq(fsub(lit[mx[e]][i], c0), ydiff));         // :4096
                     }
                     E[E_LEFT] = ((ymin == round_s32(prj[e].y)) ? 1u : 0u) |                           // :4093
                                 ((unsigned)mn[e] << 8) | ((unsigned)mx[e] << 16);
@@ -598,13 +598,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         float ni0 = 0.0f, ni1 = 0.0f, ni2 = 0.0f;
                         if(xdiff != 0.0f)                                             // :333-363
                         {
-                            i0 = fdiv(fsub(R.c0, L.c0), xdiff); i1 = fdiv(fsub(R.c1, L.c1), xdiff);
-                            i2 = fdiv(fsub(R.c2, L.c2), xdiff); i3 = fdiv(fsub(R.c3, L.c3), xdiff);
-                            zi = fdiv(fsub(R.z, L.z), xdiff);
+                            i0 = fdiv_zn(fsub(R.c0, L.c0), xdiff); i1 = fdiv_zn(fsub(R.c1, L.c1), xdiff);
+                            i2 = fdiv_zn(fsub(R.c2, L.c2), xdiff); i3 = fdiv_zn(fsub(R.c3, L.c3), xdiff);
+                            zi = fdiv_zn(fsub(R.z, L.z), xdiff);
                             if(PHONG)                                                 // :344-349
                             {
-                                ni0 = fdiv(fsub(R.n0, L.n0), xdiff); ni1 = fdiv(fsub(R.n1, L.n1), xdiff);
-                                ni2 = fdiv(fsub(R.n2, L.n2), xdiff);
+                                ni0 = fdiv_zn(fsub(R.n0, L.n0), xdiff); ni1 = fdiv_zn(fsub(R.n1, L.n1), xdiff);
+                                ni2 = fdiv_zn(fsub(R.n2, L.n2), xdiff);
                             }
                         }
                         float xoff = 0.0f, leftx = L.x;                               // :381-390
