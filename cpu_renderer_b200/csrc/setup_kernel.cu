@@ -321,7 +321,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             if(k > 0)
             {
                 float lit[3][4];
-#pragma unroll
+#pragma unroll 1
                 for(int q = 0; q < 3; ++q)
                 {
                     float4 c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
@@ -331,7 +331,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     else light_vertex(cam[q], nr, col, v, lit[q]);
                 }
                 int max_row = (int)0x80000000;
-#pragma unroll
+#pragma unroll 1
                 for(int e = 0; e < 3; ++e)
                 {
                     if(slot_of[e] < 0) continue;
