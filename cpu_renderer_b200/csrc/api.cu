@@ -84,6 +84,14 @@ struct b200r_context
 
     // host-pointer path mirrors
     DeviceBuffer d_pos, d_col, d_nrm, d_color, d_depth;
+    // host-pointer path: uploads run on their own stream and the frame's kernels wait only for
+    // what they read -- the z-range pass for all positions, each chunk's set-up for that chunk's
+    // colours and normals, the raster kernel for the targets -- so set-up and binning overlap the
+    // rest of the upload instead of following it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pos_ready = nullptr, target_ready = nullptr;
+    std::vector<cudaEvent_t> chunk_ready;   // pool, grown on demand
+    bool host_path = false;                 // issue_frame: honour the events above
 };
 
 static int fail(b200r_context *c, int code, const char *what, cudaError_t e = cudaSuccess)
@@ -171,6 +179,7 @@ static int issue_frame(b200r_context *c)
     so.zrange = reinterpret_cast<const float *>(words->zkeys);
     so.counters = words->counters;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[0], c->stream));
+    if(c->host_path) CU(cudaStreamWaitEvent(c->stream, c->pos_ready, 0));
     for(const MeshParams &m : c->meshes)
     {
         launch_zrange(m, words->zkeys, c->stream);
@@ -178,8 +187,10 @@ static int issue_frame(b200r_context *c)
     }
     launch_zrange_finish(words->zkeys, c->stream);
     c->stats.KernelLaunches += 1;
-    for(const MeshParams &m : c->meshes)
+    for(size_t i = 0; i < c->meshes.size(); ++i)
     {
+        const MeshParams &m = c->meshes[i];
+        if(c->host_path && i < c->chunk_ready.size()) CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
         launch_setup(v, m, so, c->stream);
         if(m.ntri) c->stats.KernelLaunches += 1;
     }
@@ -231,6 +242,7 @@ static int issue_frame(b200r_context *c)
                   (c->target.Width & 3) == 0) ? 1 : 0;
     rp.refill_lanes = c->refill_lanes;
     rp.pend_lanes = c->pend_lanes;
+    if(c->host_path) CU(cudaStreamWaitEvent(c->stream, c->target_ready, 0));
     cudaError_t e = launch_raster(rp, c->sm_count, c->stream);
     if(e != cudaSuccess) return fail(c, B200R_E_CUDA, "raster_kernel launch", e);
     c->stats.KernelLaunches += 1;
@@ -324,6 +336,10 @@ void b200r_destroy(b200r_context *c)
     for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
     if(c->h_words) cudaFreeHost(c->h_words);
     if(c->total_ready) cudaEventDestroy(c->total_ready);
+    if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if(c->pos_ready) cudaEventDestroy(c->pos_ready);
+    if(c->target_ready) cudaEventDestroy(c->target_ready);
+    for(cudaEvent_t e : c->chunk_ready) if(e) cudaEventDestroy(e);
     if(c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -465,10 +481,15 @@ int b200r_get_stats(b200r_context *c, b200r_frame_stats *s)
 }
 
 // ---------------------------------------------------------------------------- host-pointer path
+// Objects become device meshes of at most kUploadChunk triangles each (same P and flags), so that
+// the set-up of one chunk can start while the next chunk's colours and normals are still on the bus.
+constexpr u32 kUploadChunk = 1u << 17;
+
 static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, u32 n,
                           std::vector<b200r_device_mesh> &meshes)
 {
     uint64_t verts = 0;
+    size_t chunks = 0;
     for(u32 i = 0; i < n; ++i)
     {
         const render_entry_3d_object &o = objs[i];
@@ -476,31 +497,60 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
         u32 tris = o.VertexCount/3;                          // projekt.cpp:3886
         if(tris && (!o.VertexData || !o.ColorData || !o.NormalData)) return fail(c, B200R_E_INVALID, "object with null vertex stream");
         verts += (uint64_t)tris*3;
+        chunks += std::max<size_t>(1, ((size_t)tris + kUploadChunk - 1)/kUploadChunk);
     }
     CU(c->d_pos.reserve((size_t)std::max<uint64_t>(verts, 1)*12));
     CU(c->d_col.reserve((size_t)std::max<uint64_t>(verts, 1)*16));
     CU(c->d_nrm.reserve((size_t)std::max<uint64_t>(verts, 1)*12));
+    if(!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if(!c->pos_ready) CU(cudaEventCreateWithFlags(&c->pos_ready, cudaEventDisableTiming));
+    if(!c->target_ready) CU(cudaEventCreateWithFlags(&c->target_ready, cudaEventDisableTiming));
+    while(c->chunk_ready.size() < chunks)
+    {
+        cudaEvent_t e = nullptr;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_ready.push_back(e);
+    }
+
+    // 1. every position (the z-range pass reads them all before any set-up can start)
     uint64_t at = 0;
     for(u32 i = 0; i < n; ++i)
     {
         const render_entry_3d_object &o = objs[i];
-        u32 tris = o.VertexCount/3;
-        size_t nv = (size_t)tris*3;
-        b200r_device_mesh m;
-        m.Positions = (const r32 *)c->d_pos.ptr + at*3;
-        m.Colors = (const r32 *)c->d_col.ptr + at*4;
-        m.Normals = (const r32 *)c->d_nrm.ptr + at*3;
-        m.TriangleCount = tris;
-        m.P = o.P;
-        m.Flags = o.PhongShading ? B200R_MESH_PHONG : 0u;
-        if(nv)
-        {
-            CU(cudaMemcpyAsync((void *)m.Positions, o.VertexData, nv*12, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync((void *)m.Colors, o.ColorData, nv*16, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaMemcpyAsync((void *)m.Normals, o.NormalData, nv*12, cudaMemcpyHostToDevice, c->stream));
-        }
+        const size_t nv = (size_t)(o.VertexCount/3)*3;
+        if(nv) CU(cudaMemcpyAsync((r32 *)c->d_pos.ptr + at*3, o.VertexData, nv*12, cudaMemcpyHostToDevice, c->copy_stream));
         at += nv;
-        meshes.push_back(m);
+    }
+    CU(cudaEventRecord(c->pos_ready, c->copy_stream));
+
+    // 2. colours and normals chunk by chunk, one event per chunk
+    at = 0;
+    for(u32 i = 0; i < n; ++i)
+    {
+        const render_entry_3d_object &o = objs[i];
+        const u32 tris = o.VertexCount/3;
+        u32 done = 0;
+        do
+        {
+            const u32 ct = std::min(tris - done, kUploadChunk);
+            const size_t nv = (size_t)ct*3, v0 = (size_t)done*3;
+            b200r_device_mesh m;
+            m.Positions = (const r32 *)c->d_pos.ptr + at*3;
+            m.Colors = (const r32 *)c->d_col.ptr + at*4;
+            m.Normals = (const r32 *)c->d_nrm.ptr + at*3;
+            m.TriangleCount = ct;
+            m.P = o.P;
+            m.Flags = o.PhongShading ? B200R_MESH_PHONG : 0u;
+            if(nv)
+            {
+                CU(cudaMemcpyAsync((void *)m.Colors, (const r32 *)o.ColorData + v0*4, nv*16, cudaMemcpyHostToDevice, c->copy_stream));
+                CU(cudaMemcpyAsync((void *)m.Normals, (const r32 *)o.NormalData + v0*3, nv*12, cudaMemcpyHostToDevice, c->copy_stream));
+            }
+            CU(cudaEventRecord(c->chunk_ready[meshes.size()], c->copy_stream));
+            at += nv;
+            done += ct;
+            meshes.push_back(m);
+        } while(done < tris);
     }
     return B200R_OK;
 }
@@ -519,7 +569,11 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
 
     std::vector<b200r_device_mesh> meshes;
     rc = upload_objects(c, objs, n, meshes);
-    if(rc != B200R_OK) return rc;
+    if(rc != B200R_OK)
+    {
+        if(c->copy_stream) cudaStreamSynchronize(c->copy_stream);   // copies already enqueued read the caller's memory
+        return rc;
+    }
 
     // device mirrors of the targets: rows padded to 64 pixels so every tile row is a 16-byte
     // aligned bulk copy
@@ -527,18 +581,26 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     const int wpad = (W + 63) & ~63;
     CU(c->d_color.reserve((size_t)wpad*H*4));
     CU(c->d_depth.reserve((size_t)wpad*H*4));
+    // 3. the targets, last: only the raster kernel reads them
     CU(cudaMemcpy2DAsync(c->d_color.ptr, (size_t)wpad*4, out->Memory, (size_t)out->Pitch, (size_t)W*4, H,
-                         cudaMemcpyHostToDevice, c->stream));
+                         cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpy2DAsync(c->d_depth.ptr, (size_t)wpad*4, cmd->ZBuffer, (size_t)cmd->Width*4, (size_t)W*4, H,
-                         cudaMemcpyHostToDevice, c->stream));
+                         cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->target_ready, c->copy_stream));
     b200r_device_target t;
     t.Color = (u32 *)c->d_color.ptr; t.Depth = (r32 *)c->d_depth.ptr;
     t.Width = W; t.Height = H; t.ColorPitch = wpad*4; t.DepthStride = wpad;
     t.BandFirstRow = 0; t.BandRows = H;
+    c->host_path = true;
     rc = b200r_render_device(c, meshes.data(), (u32)meshes.size(), cmd, &t, flags);
-    if(rc != B200R_OK) return rc;
-    rc = settle_pending(c);                     // re-issue before the read-back if the list grew
-    if(rc != B200R_OK) return rc;
+    if(rc == B200R_OK) rc = settle_pending(c);  // re-issue before the read-back if the list grew
+    c->host_path = false;
+    if(rc != B200R_OK)
+    {
+        cudaStreamSynchronize(c->copy_stream);  // the caller may free its buffers once we return
+        cudaStreamSynchronize(c->stream);
+        return rc;
+    }
     CU(cudaMemcpy2DAsync(out->Memory, (size_t)out->Pitch, c->d_color.ptr, (size_t)wpad*4, (size_t)W*4, H,
                          cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpy2DAsync(cmd->ZBuffer, (size_t)cmd->Width*4, c->d_depth.ptr, (size_t)wpad*4, (size_t)W*4, H,

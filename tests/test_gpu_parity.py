@@ -338,6 +338,17 @@ def test_c2_full_size(renderer):
     check(renderer, s, want=want)
 
 
+def test_host_path_upload_chunks_do_not_follow_object_boundaries(renderer):
+    """The host-pointer call uploads objects in chunks of 131 072 triangles and starts each chunk's
+    set-up as soon as that chunk has arrived: an object that spans two chunks next to one that fits
+    into one, against the oracle (submission order, and with it the tie-break, must survive)."""
+    s = sc.make_config("c2", 0.3)                       # 300 000 triangles
+    assert s.triangle_count == 300_000
+    want = ol.oracle_render(s, threads=8)
+    check(renderer, s, splits=[200_000 * 3, 100_000 * 3], want=want)
+    assert renderer.stats()["Triangles"] == 300_000
+
+
 def test_c3_full_size(renderer):
     """Config C3 at full size: 50 k large overlapping triangles, 3840x2160, ~35x overdraw."""
     s = sc.make_config("c3")
