@@ -11,7 +11,7 @@ uvs v2.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 
 import numpy as np
 
@@ -70,6 +70,7 @@ class Scene:
     lights: list = field(default_factory=lambda: [Light()])
     clear_color: int = 0
     clear_depth: float = -1e30
+    texture: np.ndarray | None = None   # [th, tw] uint32 ARGB8: the objects' loaded_bitmap (projekt.h:13), or None
 
     @property
     def triangle_count(self) -> int:
@@ -197,6 +198,29 @@ CONFIGS = {
     "c3": dict(seed=0xB2000003, count=50_000, width=3840, height=2160, rmin=32.0, rmax=96.0),
     "c4": dict(seed=0xB2000004, count=20_000_000, width=16384, height=16384, rmin=2.0, rmax=10.0),
 }
+
+
+def make_texture(width: int, height: int, seed: int = 0x7E57) -> np.ndarray:
+    """A deterministic ARGB8 texture in which neighbouring texels differ in every channel (an
+    off-by-one texel cannot go unnoticed) and no two texels of a 256x256 block are equal."""
+    y, x = np.mgrid[0:height, 0:width].astype(np.uint32)
+    h = (x * np.uint32(0x9E3779B1)) ^ (y * np.uint32(0x85EBCA77)) ^ np.uint32(seed)
+    h ^= h >> np.uint32(15); h *= np.uint32(0x2C1B3C6D); h ^= h >> np.uint32(12)
+    r = (x * 7 + (h & 3)) & 0xFF
+    g = (y * 11 + ((h >> 2) & 3)) & 0xFF
+    b = (h >> 8) & 0xFF
+    a = 0x80 | ((h >> 16) & 0x7F)
+    return ((a << 24) | (r << 16) | (g << 8) | b).astype(np.uint32)
+
+
+def textured(scene: Scene, tex_w: int = 64, tex_h: int = 48, seed: int = 0x7E57, lo: float = 0.1,
+             hi: float = 0.9) -> Scene:
+    """The same scene with a texture on every object: per-vertex UVs uniform in [lo, hi]^2 (SplitMix64)
+    and make_texture(tex_w, tex_h).  With the default range every texel coordinate the reference
+    computes stays inside the bitmap (the reference has no range check, projekt.cpp:433-438)."""
+    n = scene.positions.shape[0]
+    uv = (np.float32(lo) + np.float32(hi - lo) * u01(splitmix64(seed, 0, 2 * n))).astype(np.float32).reshape(n, 2)
+    return replace(scene, name=scene.name + "_tex", uvs=np.ascontiguousarray(uv), texture=make_texture(tex_w, tex_h, seed))
 
 
 def make_config(name: str, scale: float = 1.0) -> Scene:

@@ -102,11 +102,20 @@ int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm
     return orc_fill_edge_table_ex(Pos, Col, Nrm, VertexCount, P, Scene, 0, Edges, Temp);
 }
 
-/* projekt.cpp:3882-4121, Object->Bitmap == 0; Phong selects :4012-4019 instead of :4020-4064. */
 int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *Nrm,
                                uint32_t VertexCount, const float P[3], const orc_scene *Scene,
                                int32_t Phong, orc_edge *Edges, orc_edge *Temp)
 {
+    return orc_fill_edge_table_tex(Pos, Col, Nrm, 0, VertexCount, P, Scene, Phong, Edges, Temp);
+}
+
+/* projekt.cpp:3882-4121.  Phong selects :4012-4019 instead of :4020-4064; UV != 0 stands for
+ * Object->Bitmap != 0 (:4034, :4050, :4078). */
+int32_t orc_fill_edge_table_tex(const float *Pos, const float *Col, const float *Nrm, const float *UV,
+                                uint32_t VertexCount, const float P[3], const orc_scene *Scene,
+                                int32_t Phong, orc_edge *Edges, orc_edge *Temp)
+{
+    static const float White[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
     static const uint32_t Indices[3][2] = { {0, 1}, {1, 2}, {2, 0} };   /* :3936-3941 */
     if(Scene->LightCount == 0 && !Phong) return -1;
     uint32_t TriangleCount = VertexCount/3;                      /* :3886 */
@@ -139,7 +148,8 @@ int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *
             }
             else
             {
-                light_vertex(Cam[v], Nrm + 9*(size_t)Tri + 3*v, Col + 12*(size_t)Tri + 4*v, Scene, Lit[v]);
+                /* :4034-4060: a textured object is lit as if every vertex were white */
+                light_vertex(Cam[v], Nrm + 9*(size_t)Tri + 3*v, UV ? White : Col + 12*(size_t)Tri + 4*v, Scene, Lit[v]);
             }
         }
 
@@ -162,6 +172,20 @@ int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *
             E->YMin = (int32_t)((0.0f > RoundedMin) ? 0.0f : RoundedMin);   /* :3999 */
             E->XMin = MinV[0];                                   /* :4000 */
             E->ZMin = Cam[MinI][2];                              /* :4001 */
+            float FirstUV[2] = { 0, 0 }, SecondUV[2] = { 0, 0 };
+            E->UMin = E->VMin = E->OneOverZMin = 0.0f;
+            E->UGradient = E->VGradient = E->OneOverZGradient = 0.0f;
+            if(UV)
+            {
+                /* z of a PROJECTED vertex is DistanceAboveTarget - camera z (:81, :89) */
+                const float *U0 = UV + 6*(size_t)Tri + 2*MinI, *U1 = UV + 6*(size_t)Tri + 2*MaxI;   /* :3982-3983 */
+                E->UMin = U0[0]/MinV[2];                         /* :4002 a true division ... */
+                E->VMin = U0[1]/MinV[2];                         /* :4003 */
+                E->OneOverZMin = 1.0f/MinV[2];                   /* :4004 */
+                float InvMax = 1.0f/MaxV[2], InvMin = 1.0f/MinV[2];
+                SecondUV[0] = InvMax*U1[0]; SecondUV[1] = InvMax*U1[1];      /* :4006 ... the gradients */
+                FirstUV[0] = InvMin*U0[0];  FirstUV[1] = InvMin*U0[1];       /* :4008 use u*(1/z) */
+            }
             if(MinV[1] - MaxV[1] != 0)                           /* :4066 */
             {
                 float YDiff = (float)E->YMax - (float)E->YMin;   /* :4070 */
@@ -169,6 +193,15 @@ int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *
                 E->Gradient = (MaxV[0] - MinV[0])/(MaxV[1] - MinV[1]);       /* :4073 */
                 E->XMin += ClippedY*E->Gradient;                 /* :4075 */
                 E->ZMin += ClippedY*E->ZGradient;                /* :4076 */
+                if(UV)                                           /* :4078-4089 */
+                {
+                    E->UGradient = (SecondUV[0] - FirstUV[0])/YDiff;
+                    E->VGradient = (SecondUV[1] - FirstUV[1])/YDiff;
+                    E->UMin += ClippedY*E->UGradient;
+                    E->VMin += ClippedY*E->VGradient;
+                    E->OneOverZGradient = ((1.0f/MaxV[2]) - E->OneOverZMin)/YDiff;
+                    E->OneOverZMin += ClippedY*E->OneOverZGradient;
+                }
                 for(int i = 0; i < 4; ++i)                       /* :4091 */
                 {
                     E->MinColor[i] = (1.0f - T)*Lit[MinI][i] + T*Lit[MaxI][i];
@@ -197,6 +230,7 @@ int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *
 typedef struct active_edge {
     float X, Z, C[4];
     float N[3];                                                  /* Phong only */
+    float U, V, W;                                               /* textured only: u/z, v/z, 1/z */
     const orc_edge *E;
 } active_edge;
 
@@ -250,14 +284,34 @@ static void phong_shade(const float Color[4], const float Normal[3], float X, fl
     for(int i = 0; i < 4; ++i) Out[i] = clamp01(Final[i]);       /* :483 */
 }
 
+/* projekt.cpp:427-446: nearest texel at Round(uv*(dim-1)); r,g,b,a = channel/255. */
+static void sample_texture(const orc_texture *Tex, float U, float V, float W, float Out[4], orc_stats *Stats)
+{
+    float Inv = 1.0f/W;                                          /* :429 */
+    float Fu = Inv*U, Fv = Inv*V;
+    float Tx = Fu*(float)(Tex->Width - 1), Ty = Fv*(float)(Tex->Height - 1);   /* :430-432 */
+    int32_t X = round_s32(Tx), Y = round_s32(Ty);                /* :433-434 */
+    int Clamped = 0;
+    if(X < 0) { X = 0; Clamped = 1; } else if(X > Tex->Width - 1) { X = Tex->Width - 1; Clamped = 1; }
+    if(Y < 0) { Y = 0; Clamped = 1; } else if(Y > Tex->Height - 1) { Y = Tex->Height - 1; Clamped = 1; }
+    if(Clamped && Stats) Stats->TexelClamps += 1;
+    uint32_t Texel = *(const uint32_t *)((const uint8_t *)Tex->Memory + (size_t)X*4 + (size_t)Y*Tex->Pitch);   /* :436-438 */
+    Out[3] = (float)((Texel >> 24) & 0xFF)/255.0f;               /* :440-443 */
+    Out[0] = (float)((Texel >> 16) & 0xFF)/255.0f;
+    Out[1] = (float)((Texel >> 8) & 0xFF)/255.0f;
+    Out[2] = (float)((Texel >> 0) & 0xFF)/255.0f;
+}
+
 static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Row,
                           int32_t PrimIndex, orc_target *T, orc_stats *Stats,
-                          const orc_scene *Scene, int32_t Phong)
+                          const orc_scene *Scene, int32_t Phong, const orc_texture *Tex)
 {
     float XDiff = roundf(R->X - L->X);                           /* :311-312 */
-    float CInc[4], ZInc, NInc[3];
+    float CInc[4], ZInc, NInc[3], UInc, VInc, WInc;
     if(XDiff != 0.0f)                                            /* :333-363 */
     {
+        WInc = (R->W - L->W)/XDiff;                              /* :336 */
+        UInc = (R->U - L->U)/XDiff; VInc = (R->V - L->V)/XDiff;  /* :338-342 */
         for(int i = 0; i < 4; ++i) CInc[i] = (R->C[i] - L->C[i])/XDiff;
         for(int i = 0; i < 3; ++i) NInc[i] = (R->N[i] - L->N[i])/XDiff;      /* :344-349 */
         ZInc = (R->Z - L->Z)/XDiff;
@@ -266,8 +320,9 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
     {
         for(int i = 0; i < 4; ++i) CInc[i] = 0.0f;
         for(int i = 0; i < 3; ++i) NInc[i] = 0.0f;
-        ZInc = 0.0f;
+        ZInc = 0.0f; UInc = VInc = WInc = 0.0f;
     }
+    float U = L->U, V = L->V, W = L->W;                          /* :376-377 */
     float N[3] = { L->N[0], L->N[1], L->N[2] };                  /* :378 */
     float Z = L->Z;                                              /* :375 */
     float C[4] = { L->C[0], L->C[1], L->C[2], L->C[3] };         /* :379 */
@@ -281,6 +336,8 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
     int32_t MinX = (int32_t)(float)round_s32(LeftX);             /* :402-406 */
     int32_t MaxX = (int32_t)(float)round_s32(RightX);
     Z += XOffset*ZInc;                                           /* :408 */
+    W += XOffset*WInc;                                           /* :409 */
+    U += XOffset*UInc; V += XOffset*VInc;                        /* :410 */
     for(int i = 0; i < 3; ++i) N[i] += XOffset*NInc[i];          /* :411 */
     for(int i = 0; i < 4; ++i) C[i] += XOffset*CInc[i];          /* :412 */
 
@@ -302,9 +359,10 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
             ++ZPixel; ++Pixel; if(Prim) ++Prim;
             if(Phong) { float Tn[3] = { N[0] + NInc[0], N[1] + NInc[1], N[2] + NInc[2] }; normalize3(Tn, N); }
             for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];
-            Z += ZInc;
+            Z += ZInc; U += UInc; V += VInc; W += WInc;
             continue;
         }
+        if(Tex) sample_texture(Tex, U, V, W, C, Stats);          /* :427-446: replaces the running colour */
         float F[4] = { C[0], C[1], C[2], C[3] };                 /* :513 */
         if(Phong) phong_shade(C, N, (float)X, (float)Row, Z, Scene, F);     /* :450-483 */
         /* colour is r,g,b,a = C[0..3]; packed A R G B (:520-523) */
@@ -322,6 +380,7 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
         if(Phong) { float Tn[3] = { N[0] + NInc[0], N[1] + NInc[1], N[2] + NInc[2] }; normalize3(Tn, N); }   /* :504 */
         for(int i = 0; i < 4; ++i) C[i] = C[i] + CInc[i];        /* :534 / :505 */
         Z += ZInc;                                               /* :535 / :506 */
+        U += UInc; V += VInc; W += WInc;                         /* :507-508 / :536-537 */
     }
 }
 
@@ -341,6 +400,13 @@ int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t Pri
 
 int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
                              orc_target *T, orc_stats *Stats, const orc_scene *Scene, int32_t Phong)
+{
+    return orc_draw_triangle_tex(Edges, EdgeCount, PrimIndex, T, Stats, Scene, Phong, 0);
+}
+
+int32_t orc_draw_triangle_tex(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
+                              orc_target *T, orc_stats *Stats, const orc_scene *Scene, int32_t Phong,
+                              const orc_texture *Tex)
 {
     if(EdgeCount == 0) return 0;
     if(EdgeCount > 3) EdgeCount = 3;
@@ -362,6 +428,7 @@ int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t 
             New.X = Edges[e].XMin; New.Z = Edges[e].ZMin; New.E = Edges + e;
             for(int i = 0; i < 4; ++i) New.C[i] = Edges[e].MinColor[i];
             for(int i = 0; i < 3; ++i) New.N[i] = Edges[e].MinNormal[i];
+            New.U = Edges[e].UMin; New.V = Edges[e].VMin; New.W = Edges[e].OneOverZMin;
             uint32_t At = Count;
             for(uint32_t k = 0; k < Count; ++k)
             {
@@ -381,7 +448,7 @@ int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t 
         if(Count < 2) continue;                                  /* defined: nothing happens */
 
         active_edge *L = &List[0], *R = &List[1];                /* :300-303, first pair only */
-        orc_fill_span(L, R, Row, PrimIndex, T, Stats, Scene, Phong);   /* Row >= 0 always (:308) */
+        orc_fill_span(L, R, Row, PrimIndex, T, Stats, Scene, Phong, Tex);   /* Row >= 0 always (:308) */
         Result |= 1;
         L->X += L->E->Gradient;      R->X += R->E->Gradient;     /* :542-543 */
         L->Z += L->E->ZGradient;     R->Z += R->E->ZGradient;    /* :545-546 */
@@ -397,6 +464,8 @@ int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t 
             normalize3(Tl, L->N);
             normalize3(Tr, R->N);
         }
+        L->U += L->E->UGradient; L->V += L->E->VGradient; L->W += L->E->OneOverZGradient;   /* :554-556 */
+        R->U += R->E->UGradient; R->V += R->E->VGradient; R->W += R->E->OneOverZGradient;   /* :558-560 */
         if(L->X > R->X)                                          /* :562-572 */
         {
             active_edge Tmp = *L; *L = *R; *R = Tmp;
@@ -407,18 +476,26 @@ int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t 
 }
 
 /* One triangle = one object: FillEdgeTable on the 3-vertex object, then the level-1 walk. */
+static int32_t render_one_tex(const float *Pos, const float *Col, const float *Nrm, const float *UV, uint32_t Tri,
+                              const float P[3], const orc_scene *Scene, int32_t Phong, const orc_texture *Tex,
+                              orc_target *T, int32_t PrimIndex, orc_stats *Stats)
+{
+    orc_edge Edges[3], Temp[3];
+    const int Textured = UV && Tex;
+    int32_t Count = orc_fill_edge_table_tex(Pos + 9*(size_t)Tri, Col + 12*(size_t)Tri, Nrm + 9*(size_t)Tri,
+                                            Textured ? UV + 6*(size_t)Tri : 0, 3, P, Scene, Phong, Edges, Temp);
+    if(Count < 0) return Count;
+    if(Stats) { Stats->Triangles += 1; if(Count > 0) Stats->Visible += 1; }
+    int32_t R = orc_draw_triangle_tex(Edges, (uint32_t)Count, PrimIndex, T, Stats, Scene, Phong, Textured ? Tex : 0);
+    if(Stats && (R & 2)) Stats->RefWouldCrash += 1;
+    return R;
+}
+
 static int32_t render_one_ex(const float *Pos, const float *Col, const float *Nrm, uint32_t Tri,
                              const float P[3], const orc_scene *Scene, int32_t Phong, orc_target *T,
                              int32_t PrimIndex, orc_stats *Stats)
 {
-    orc_edge Edges[3], Temp[3];
-    int32_t Count = orc_fill_edge_table_ex(Pos + 9*(size_t)Tri, Col + 12*(size_t)Tri, Nrm + 9*(size_t)Tri,
-                                           3, P, Scene, Phong, Edges, Temp);
-    if(Count < 0) return Count;
-    if(Stats) { Stats->Triangles += 1; if(Count > 0) Stats->Visible += 1; }
-    int32_t R = orc_draw_triangle_ex(Edges, (uint32_t)Count, PrimIndex, T, Stats, Scene, Phong);
-    if(Stats && (R & 2)) Stats->RefWouldCrash += 1;
-    return R;
+    return render_one_tex(Pos, Col, Nrm, 0, Tri, P, Scene, Phong, 0, T, PrimIndex, Stats);
 }
 
 static int32_t render_one(const float *Pos, const float *Col, const float *Nrm, uint32_t Tri,
@@ -445,6 +522,21 @@ int32_t orc_render_triangles_ex(const float *Pos, const float *Col, const float 
     for(uint32_t Tri = 0; Tri < TriangleCount; ++Tri)
     {
         int32_t R = render_one_ex(Pos, Col, Nrm, Tri, P, Scene, Phong, Target, PrimBase + (int32_t)Tri, Stats);
+        if(WouldCrash) WouldCrash[Tri] = (uint8_t)((R & 2) ? 1 : 0);
+    }
+    return 0;
+}
+
+int32_t orc_render_triangles_tex(const float *Pos, const float *Col, const float *Nrm, const float *UV,
+                                 uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
+                                 int32_t Phong, const orc_texture *Texture, orc_target *Target,
+                                 int32_t PrimBase, uint8_t *WouldCrash, orc_stats *Stats)
+{
+    if(Scene->LightCount == 0 && !Phong) return -1;
+    for(uint32_t Tri = 0; Tri < TriangleCount; ++Tri)
+    {
+        int32_t R = render_one_tex(Pos, Col, Nrm, UV, Tri, P, Scene, Phong, Texture, Target,
+                                   PrimBase + (int32_t)Tri, Stats);
         if(WouldCrash) WouldCrash[Tri] = (uint8_t)((R & 2) ? 1 : 0);
     }
     return 0;
@@ -546,6 +638,6 @@ void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
     orc_target T;
     T.Width = B->Width; T.Height = B->Height; T.Pitch = B->Pitch;
     T.Color = (uint32_t *)B->Memory; T.Z = C->ZBuffer; T.ZStride = C->Width; T.Prim = 0;
-    render_one_ex(Ctx->Pos, Ctx->Col, Ctx->Nrm, TriangleIndex, Ctx->P, Ctx->Scene, Ctx->Phong, &T,
-                  (int32_t)TriangleIndex, 0);
+    render_one_tex(Ctx->Pos, Ctx->Col, Ctx->Nrm, Ctx->UV, TriangleIndex, Ctx->P, Ctx->Scene, Ctx->Phong,
+                   Ctx->Texture, &T, (int32_t)TriangleIndex, 0);
 }

@@ -57,7 +57,15 @@ typedef struct orc_edge {
     int32_t Triangle;                   /* provenance only (not in the reference) */
     float MinNormal[3];                 /* Phong only (projekt.cpp:4017, 4104-4109) */
     float NormalGradient[3];
+    float UMin, VMin, OneOverZMin;      /* textured only (projekt.cpp:4002-4004, 4078-4089): u/z, v/z, 1/z */
+    float UGradient, VGradient, OneOverZGradient;
 } orc_edge;
+
+/* loaded_bitmap as a texture (projekt.cpp:427-446): ARGB8 texels, Pitch in bytes. */
+typedef struct orc_texture {
+    int32_t Width, Height, Pitch;
+    const uint32_t *Memory;
+} orc_texture;
 
 typedef struct orc_target {
     int32_t Width, Height;              /* loaded_bitmap.Width/Height, projekt.cpp:193, 387 */
@@ -77,6 +85,7 @@ typedef struct orc_stats {
     uint64_t DepthPasses;               /* fragments that won the test when drawn */
     uint64_t RefWouldCrash;             /* triangles on which the verbatim reference
                                            null-dereferences (edges cross before the last row) */
+    uint64_t TexelClamps;               /* textured pixels whose texel coordinates left the bitmap */
 } orc_stats;
 
 void orc_project_vertex(const float Cam[3], const orc_transform *T, float Out[3]);
@@ -90,6 +99,11 @@ int32_t orc_fill_edge_table(const float *Pos, const float *Col, const float *Nrm
 int32_t orc_fill_edge_table_ex(const float *Pos, const float *Col, const float *Nrm,
                                uint32_t VertexCount, const float P[3], const orc_scene *Scene,
                                int32_t Phong, orc_edge *Edges, orc_edge *Temp);
+/* Same for an object with a Bitmap (UV != 0; projekt.cpp:3919-3923, 4002-4008, 4034-4060,
+ * 4078-4089): perspective-correct u/z, v/z, 1/z per edge; Gouraud colours are lit WHITE. */
+int32_t orc_fill_edge_table_tex(const float *Pos, const float *Col, const float *Nrm, const float *UV,
+                                uint32_t VertexCount, const float P[3], const orc_scene *Scene,
+                                int32_t Phong, orc_edge *Edges, orc_edge *Temp);
 
 void orc_merge_sort(uint32_t Count, orc_edge *First, orc_edge *Temp);
 
@@ -100,6 +114,14 @@ int32_t orc_draw_triangle(const orc_edge *Edges, uint32_t EdgeCount, int32_t Pri
 /* Same with per-pixel Phong shading (projekt.cpp:450-509, 551-552); Scene gives lights + transform. */
 int32_t orc_draw_triangle_ex(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
                              orc_target *Target, orc_stats *Stats, const orc_scene *Scene, int32_t Phong);
+/* Same with a texture (projekt.cpp:427-446): every pixel's colour is the texel at
+ * Round(uv * (dim - 1)), nearest.  The reference does not range-check the texel coordinates and
+ * reads outside the bitmap when they leave it; DEFINED here: they are clamped to the bitmap
+ * (cvtss2si's INT_MIN for NaN / overflow clamps to 0).  Stats->TexelClamps counts such pixels, so a
+ * caller can tell whether a comparison with the verbatim reference is meaningful. */
+int32_t orc_draw_triangle_tex(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimIndex,
+                              orc_target *Target, orc_stats *Stats, const orc_scene *Scene, int32_t Phong,
+                              const orc_texture *Texture);
 
 /* Per-triangle semantics over a soup, in submission order.  PrimBase is added to the
  * triangle index stored in Target->Prim.  WouldCrash (optional, one byte per triangle). */
@@ -111,6 +133,11 @@ int32_t orc_render_triangles_ex(const float *Pos, const float *Col, const float 
                                 uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
                                 int32_t Phong, orc_target *Target, int32_t PrimBase, uint8_t *WouldCrash,
                                 orc_stats *Stats);
+/* UV and Texture both non-null: the soup is textured. */
+int32_t orc_render_triangles_tex(const float *Pos, const float *Col, const float *Nrm, const float *UV,
+                                 uint32_t TriangleCount, const float P[3], const orc_scene *Scene,
+                                 int32_t Phong, const orc_texture *Texture, orc_target *Target,
+                                 int32_t PrimBase, uint8_t *WouldCrash, orc_stats *Stats);
 
 /* Same result, Threads workers with private targets folded in submission order. */
 int32_t orc_render_triangles_mt(const float *Pos, const float *Col, const float *Nrm,
@@ -124,6 +151,8 @@ typedef struct orc_fallback_ctx {
     float P[3];
     const orc_scene *Scene;
     int32_t Phong;
+    const float *UV;                    /* textured soups: both non-null */
+    const orc_texture *Texture;
 } orc_fallback_ctx;
 void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
                       void *RefGameRenderCommands);

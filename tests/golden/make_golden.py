@@ -15,6 +15,7 @@ import os
 import sys
 
 import numpy as np
+from dataclasses import replace
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
@@ -141,6 +142,42 @@ def main():
     phong["sphere_540p_color"] = r["color"]
     phong["sphere_540p_z_hash"] = np.array(ol.fnv1a64_words(r["z"]))
     np.savez_compressed(os.path.join(HERE, "reference_vectors_phong.npz"), **phong)
+
+    # ---- textured path (projekt.cpp:427-446, 4002-4008, 4078-4089), Gouraud and Phong ---------------
+    # Depth is always the verbatim build's.  Colour is the verbatim build's wherever every texel
+    # coordinate stays inside the bitmap (clamps == 0); where the reference reads outside its texture
+    # (undefined) the golden colour is the oracle's defined clamp, and the number of such pixels is stored.
+    tex = {}
+    for phong in (False, True):
+        tag = "phong" if phong else "gouraud"
+        for name, s0 in kat_scenes.all_scenes().items():
+            s = sc.textured(s0)
+            o = ol.oracle_render(s, phong=phong)
+            r = ol.ref_render_triangles(s, skip=o["would_crash"], use_fallback=True, phong=phong)
+            clamps = o["stats"]["TexelClamps"]
+            assert (o["z"].view(np.uint32) == r["z"].view(np.uint32)).all(), name
+            if clamps == 0:
+                assert (o["color"] == r["color"]).all(), name
+            tex[f"{tag}_kat_{name}_z"] = r["z"].view(np.uint32)
+            tex[f"{tag}_kat_{name}_color"] = r["color"] if clamps == 0 else o["color"]
+            tex[f"{tag}_kat_{name}_clamps"] = np.int64(clamps)
+        for name, kw in {"soup_small": dict(seed=0xB2000002, count=30_000, width=1280, height=720, rmin=1.5, rmax=6.0),
+                         "soup_large": dict(seed=0xB2000003, count=1_500, width=1280, height=720, rmin=32.0, rmax=96.0)}.items():
+            # UVs in [0.4, 0.6]: spans overshoot tiny triangles by a pixel, and with a wider range the
+            # steep UV gradients there extrapolate out of the bitmap (481 pixels at [0.1, 0.9])
+            s = sc.textured(sc.triangle_soup(name, **kw), 256, 128, lo=0.4, hi=0.6)
+            o = ol.oracle_render(s, phong=phong)
+            r = ol.ref_render_triangles(s, skip=o["would_crash"], use_fallback=True, phong=phong)
+            assert o["stats"]["TexelClamps"] == 0, (name, o["stats"]["TexelClamps"])
+            tex[f"{tag}_{name}_color_hash"] = np.array(ol.fnv1a64_words(r["color"]))
+            tex[f"{tag}_{name}_z_hash"] = np.array(ol.fnv1a64_words(r["z"]))
+        # the demo sphere with the UVs ConstructSphere gives it (projekt.cpp:4174-4277), one object
+        s = replace(sc.sphere_scene(pos, col, nrm, uvs, 960, 540, 135.0), texture=sc.make_texture(64, 48))
+        e, n = ol.ref_edge_table(s, phong=phong)
+        fields = (ol.PHONG_FIELDS if phong else ol.GOURAUD_FIELDS) + ol.TEX_FIELDS
+        tex[f"{tag}_sphere_540p_edges"] = np.concatenate(
+            [np.ascontiguousarray(e[f]).view(np.uint32).reshape(len(e), -1) for f in fields], axis=1)
+    np.savez_compressed(os.path.join(HERE, "reference_vectors_tex.npz"), **tex)
 
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     for k in sorted(out):

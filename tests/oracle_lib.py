@@ -45,13 +45,22 @@ class OrcEdge(C.Structure):
                 ("Gradient", C.c_float), ("ZMin", C.c_float), ("ZGradient", C.c_float),
                 ("MinColor", C.c_float * 4), ("ColorGradient", C.c_float * 4),
                 ("Left", C.c_int32), ("Triangle", C.c_int32),
-                ("MinNormal", C.c_float * 3), ("NormalGradient", C.c_float * 3)]
+                ("MinNormal", C.c_float * 3), ("NormalGradient", C.c_float * 3),
+                ("UMin", C.c_float), ("VMin", C.c_float), ("OneOverZMin", C.c_float),
+                ("UGradient", C.c_float), ("VGradient", C.c_float), ("OneOverZGradient", C.c_float)]
+
+
+class OrcTexture(C.Structure):
+    _fields_ = [("Width", C.c_int32), ("Height", C.c_int32), ("Pitch", C.c_int32),
+                ("Memory", C.POINTER(C.c_uint32))]
 
 
 ORC_EDGE_DTYPE = np.dtype([("YMin", "<i4"), ("YMax", "<i4"), ("XMin", "<f4"), ("Gradient", "<f4"),
                            ("ZMin", "<f4"), ("ZGradient", "<f4"), ("MinColor", "<f4", 4),
                            ("ColorGradient", "<f4", 4), ("Left", "<i4"), ("Triangle", "<i4"),
-                           ("MinNormal", "<f4", 3), ("NormalGradient", "<f4", 3)])
+                           ("MinNormal", "<f4", 3), ("NormalGradient", "<f4", 3),
+                           ("UMin", "<f4"), ("VMin", "<f4"), ("OneOverZMin", "<f4"),
+                           ("UGradient", "<f4"), ("VGradient", "<f4"), ("OneOverZGradient", "<f4")])
 
 
 class OrcTarget(C.Structure):
@@ -63,7 +72,7 @@ class OrcTarget(C.Structure):
 class OrcStats(C.Structure):
     _fields_ = [("Triangles", C.c_uint64), ("Visible", C.c_uint64), ("SpanRows", C.c_uint64),
                 ("Fragments", C.c_uint64), ("DepthPasses", C.c_uint64),
-                ("RefWouldCrash", C.c_uint64)]
+                ("RefWouldCrash", C.c_uint64), ("TexelClamps", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -71,7 +80,8 @@ class OrcStats(C.Structure):
 
 class OrcFallbackCtx(C.Structure):
     _fields_ = [("Pos", f32p), ("Col", f32p), ("Nrm", f32p), ("P", C.c_float * 3),
-                ("Scene", C.POINTER(OrcScene)), ("Phong", C.c_int32)]
+                ("Scene", C.POINTER(OrcScene)), ("Phong", C.c_int32),
+                ("UV", f32p), ("Texture", C.POINTER(OrcTexture))]
 
 
 # ------------------------------------------------------------------ reference structs
@@ -125,6 +135,8 @@ GOURAUD_FIELDS = ["YMin", "YMax", "XMin", "Gradient", "ZMin", "ZGradient", "MinC
                   "ColorGradient", "Left"]
 # Phong mode additionally defines the normals (projekt.cpp:4017, 4104-4109)
 PHONG_FIELDS = GOURAUD_FIELDS + ["MinNormal", "NormalGradient"]
+# an object with a Bitmap additionally defines u/z, v/z, 1/z (projekt.cpp:4002-4004, 4078-4089)
+TEX_FIELDS = ["UMin", "VMin", "OneOverZMin", "UGradient", "VGradient", "OneOverZGradient"]
 
 REF_FALLBACK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
 
@@ -168,6 +180,13 @@ def oracle():
         lib.orc_fill_edge_table_ex.argtypes = [f32p, f32p, f32p, C.c_uint32, f32p, C.POINTER(OrcScene),
                                                C.c_int32, C.c_void_p, C.c_void_p]
         lib.orc_fill_edge_table_ex.restype = C.c_int32
+        lib.orc_fill_edge_table_tex.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p, C.POINTER(OrcScene),
+                                                C.c_int32, C.c_void_p, C.c_void_p]
+        lib.orc_fill_edge_table_tex.restype = C.c_int32
+        lib.orc_render_triangles_tex.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p, C.POINTER(OrcScene),
+                                                 C.c_int32, C.POINTER(OrcTexture), C.POINTER(OrcTarget),
+                                                 C.c_int32, C.c_void_p, C.POINTER(OrcStats)]
+        lib.orc_render_triangles_tex.restype = C.c_int32
         lib.orc_render_triangles_mt.argtypes = [f32p, f32p, f32p, C.c_uint32, f32p,
                                                 C.POINTER(OrcScene), C.POINTER(OrcTarget),
                                                 C.c_uint32, C.POINTER(OrcStats)]
@@ -206,6 +225,8 @@ def ref():
         lib.ref_render_triangles.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p,
                                              C.POINTER(RefCommands), C.POINTER(RefLoadedBitmap),
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        lib.ref_set_texture.argtypes = [C.c_void_p]
+        lib.ref_set_texture.restype = None
         lib.ref_render_triangles_mt.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p,
                                                 C.POINTER(RefCommands), C.POINTER(RefLoadedBitmap),
                                                 C.POINTER(f32p), C.c_uint32, C.c_void_p,
@@ -225,6 +246,12 @@ class OracleScene:
         self.nrm, self.nrm_p = _np_f32(scene.normals)
         self.uvs, self.uvs_p = _np_f32(scene.uvs)
         self.P = (C.c_float * 3)(*scene.object_p)
+        self.tex = self.orc_tex = self.ref_tex = None
+        if getattr(scene, "texture", None) is not None:
+            self.tex = np.ascontiguousarray(scene.texture, dtype=np.uint32)
+            th, tw = self.tex.shape
+            self.orc_tex = OrcTexture(tw, th, self.tex.strides[0], self.tex.ctypes.data_as(C.POINTER(C.c_uint32)))
+            self.ref_tex = RefLoadedBitmap(tw, th, self.tex.strides[0], self.tex.ctypes.data)
         n = len(scene.lights)
         self.orc_lights = (OrcLight * max(n, 1))()
         self.ref_lights = (RefLightInfo * max(n, 1))()
@@ -285,7 +312,11 @@ def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0, 
     stats = OrcStats()
     n = scene.triangle_count
     crash = np.zeros(n, dtype=np.uint8)
-    if phong:
+    if s.orc_tex is not None:
+        rc = lib.orc_render_triangles_tex(s.pos_p, s.col_p, s.nrm_p, s.uvs_p, n, s.P, C.byref(s.orc),
+                                          1 if phong else 0, C.byref(s.orc_tex), C.byref(t), prim_base,
+                                          crash.ctypes.data, C.byref(stats))
+    elif phong:
         rc = lib.orc_render_triangles_ex(s.pos_p, s.col_p, s.nrm_p, n, s.P, C.byref(s.orc), 1, C.byref(t),
                                          prim_base, crash.ctypes.data, C.byref(stats))
     elif threads > 1:
@@ -307,9 +338,10 @@ def oracle_edge_table(scene, first_vertex=0, vertex_count=None, phong=False):
     edges = np.zeros(max(vertex_count, 1), dtype=ORC_EDGE_DTYPE)
     tmp = np.zeros(max(vertex_count, 1), dtype=ORC_EDGE_DTYPE)
     off = first_vertex
-    n = lib.orc_fill_edge_table_ex(s.pos[off:].ctypes.data_as(f32p), s.col[off:].ctypes.data_as(f32p),
-                                   s.nrm[off:].ctypes.data_as(f32p), vertex_count, s.P,
-                                   C.byref(s.orc), 1 if phong else 0, edges.ctypes.data, tmp.ctypes.data)
+    uv_p = s.uvs[off:].ctypes.data_as(f32p) if s.orc_tex is not None else None
+    n = lib.orc_fill_edge_table_tex(s.pos[off:].ctypes.data_as(f32p), s.col[off:].ctypes.data_as(f32p),
+                                    s.nrm[off:].ctypes.data_as(f32p), uv_p, vertex_count, s.P,
+                                    C.byref(s.orc), 1 if phong else 0, edges.ctypes.data, tmp.ctypes.data)
     return edges[:max(n, 0)].copy(), n
 
 
@@ -333,6 +365,8 @@ def ref_edge_table(scene, first_vertex=0, vertex_count=None, phong=False):
     obj.UVData = s.uvs.ctypes.data + first_vertex * 8
     obj.EdgeMemory = edges.ctypes.data
     obj.PhongShading = 1 if phong else 0
+    if s.ref_tex is not None:
+        obj.Bitmap = C.addressof(s.ref_tex)
     n = lib.ref_fill_edge_table(C.byref(obj), C.byref(cmd), 1 if phong else 0)
     return edges[:max(n, 0)].copy(), n
 
@@ -354,6 +388,8 @@ def ref_render_object(scene, targets=None, phong=False):
     obj.NormalData, obj.UVData = s.nrm.ctypes.data, s.uvs.ctypes.data
     obj.EdgeMemory = edges.ctypes.data
     obj.PhongShading = 1 if phong else 0
+    if s.ref_tex is not None:
+        obj.Bitmap = C.addressof(s.ref_tex)
     rc = lib.ref_render_object(C.byref(obj), C.byref(cmd), C.byref(bmp))
     return dict(color=color, z=z, status=rc)
 
@@ -372,9 +408,12 @@ def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, target
     fb, user = None, None
     ctx = None
     if use_fallback:
-        ctx = OrcFallbackCtx(s.pos_p, s.col_p, s.nrm_p, s.P, C.pointer(s.orc), 1 if phong else 0)
+        ctx = OrcFallbackCtx(s.pos_p, s.col_p, s.nrm_p, s.P, C.pointer(s.orc), 1 if phong else 0,
+                             s.uvs_p if s.orc_tex is not None else None,
+                             C.pointer(s.orc_tex) if s.orc_tex is not None else None)
         fb = C.cast(oracle().orc_ref_fallback, C.c_void_p)
         user = C.cast(C.pointer(ctx), C.c_void_p)
+    lib.ref_set_texture(C.addressof(s.ref_tex) if s.ref_tex is not None else None)
     if threads <= 1:
         lib.ref_render_triangles(s.pos_p, s.col_p, s.nrm_p, s.uvs_p, n, s.P, C.byref(cmd),
                                  C.byref(bmp), skip_p, status.ctypes.data, fb, user, 1 if phong else 0)
@@ -386,6 +425,7 @@ def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, target
         zptrs = (f32p * threads)(*[zz.ctypes.data_as(f32p) for zz in zs])
         lib.ref_render_triangles_mt(s.pos_p, s.col_p, s.nrm_p, s.uvs_p, n, s.P, C.byref(cmd), bmps,
                                     zptrs, threads, skip_p, fb, user, 1 if phong else 0)
+    lib.ref_set_texture(None)
     return dict(color=color, z=z, status=status)
 
 
