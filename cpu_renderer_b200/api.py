@@ -71,9 +71,14 @@ class render_entry_3d_object(C.Structure):
                 ("Bitmap", C.c_void_p)]
 
 
+class device_texture(C.Structure):
+    _fields_ = [("Memory", C.c_void_p), ("Width", C.c_int32), ("Height", C.c_int32), ("Pitch", C.c_int32)]
+
+
 class device_mesh(C.Structure):
     _fields_ = [("Positions", C.c_void_p), ("Colors", C.c_void_p), ("Normals", C.c_void_p),
-                ("TriangleCount", C.c_uint32), ("P", v3), ("Flags", C.c_uint32)]
+                ("TriangleCount", C.c_uint32), ("P", v3), ("Flags", C.c_uint32),
+                ("UVs", C.c_void_p), ("Texture", C.POINTER(device_texture))]
 
 
 class device_target(C.Structure):
@@ -215,15 +220,25 @@ class Renderer:
         return s.as_dict()
 
     # ---- host-pointer drop-in (FillEdgeTable + DrawModel pair, projekt.cpp:3882 + 162) ----
-    def render_scene_host(self, scene, color: np.ndarray, depth: np.ndarray, splits=None, flags=0, phong=False):
+    def render_scene_host(self, scene, color: np.ndarray, depth: np.ndarray, splits=None, flags=0, phong=False,
+                          textured=None):
         """Render ``scene`` into host arrays color[H,W] u32 / depth[H,W] f32 in place.
         ``splits``: optional list of vertex counts to submit the scene as several objects.
-        ``phong``: bool, or one bool per split (render_entry_3d_object::PhongShading)."""
+        ``phong``: bool, or one bool per split (render_entry_3d_object::PhongShading).
+        ``textured``: bool, or one bool per split: the object carries scene.texture as its Bitmap
+        (default: every object, when the scene has a texture)."""
         assert color.dtype == np.uint32 and depth.dtype == np.float32
         nv = scene.positions.shape[0]
         splits = splits or [nv]
         assert sum(splits) == nv
         objs = (render_entry_3d_object * len(splits))()
+        tex = getattr(scene, "texture", None)
+        if textured is None:
+            textured = tex is not None
+        tex_bmp = None
+        if tex is not None:
+            tex = np.ascontiguousarray(tex, dtype=np.uint32)
+            tex_bmp = loaded_bitmap(tex.shape[1], tex.shape[0], tex.strides[0], tex.ctypes.data)
         at = 0
         for i, cnt in enumerate(splits):
             o = objs[i]
@@ -234,6 +249,8 @@ class Renderer:
             o.ColorData = scene.colors.ctypes.data + at * 16
             o.NormalData = scene.normals.ctypes.data + at * 12
             o.UVData = scene.uvs.ctypes.data + at * 8
+            if tex_bmp is not None and (textured[i] if isinstance(textured, (list, tuple)) else textured):
+                o.Bitmap = C.addressof(tex_bmp)
             at += cnt
         cmd, keep = make_commands(scene, depth.ctypes.data, depth.strides[0] // 4)
         bmp = loaded_bitmap(color.shape[1], color.shape[0], color.strides[0], color.ctypes.data)
@@ -254,6 +271,11 @@ class Renderer:
         o.NormalData = scene.normals.ctypes.data + first_vertex * 12
         o.UVData = scene.uvs.ctypes.data + first_vertex * 8
         o.EdgeMemory = edges.ctypes.data
+        tex = getattr(scene, "texture", None)
+        if tex is not None:
+            tex = np.ascontiguousarray(tex, dtype=np.uint32)
+            tex_bmp = loaded_bitmap(tex.shape[1], tex.shape[0], tex.strides[0], tex.ctypes.data)
+            o.Bitmap = C.addressof(tex_bmp)
         cmd, keep = make_commands(scene)
         o.PhongShading = 1 if phong else 0
         n = self._check(self.lib.b200r_fill_edge_table(self.ctx, C.byref(o), C.byref(cmd), 1 if phong else 0))

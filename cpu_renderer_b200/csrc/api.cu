@@ -69,6 +69,9 @@ struct b200r_context
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
+    // textures of the last issued frame: distinct b200r_device_texture descriptors, uploaded as a table
+    std::vector<TexDesc> tex_host;
+    DeviceBuffer tex_dev;
 
     // the last issued frame, kept so it can be issued again after the pair list grew
     bool pending = false;
@@ -83,7 +86,9 @@ struct b200r_context
     cudaEvent_t stage_ev[B200R_STAGES + 1] = {};
 
     // host-pointer path mirrors
-    DeviceBuffer d_pos, d_col, d_nrm, d_color, d_depth;
+    DeviceBuffer d_pos, d_col, d_nrm, d_uv, d_color, d_depth;
+    struct HostTexture { const loaded_bitmap *host; DeviceBuffer pixels; b200r_device_texture desc; };
+    std::vector<HostTexture> host_textures;     // device copies of the objects' Bitmaps, one per distinct pointer
     // host-pointer path: uploads run on their own stream and the frame's kernels wait only for
     // what they read -- the z-range pass for all positions, each chunk's set-up for that chunk's
     // colours and normals, the raster kernel for the targets -- so set-up and binning overlap the
@@ -240,6 +245,14 @@ static int issue_frame(b200r_context *c)
     rp.bulk_ok = ((((uintptr_t)c->target.Color) & 15) == 0 && (((uintptr_t)c->target.Depth) & 15) == 0 &&
                   (c->target.ColorPitch & 15) == 0 && ((c->target.DepthStride*4) & 15) == 0 &&
                   (c->target.Width & 3) == 0) ? 1 : 0;
+    rp.textures = nullptr;
+    if(!c->tex_host.empty())
+    {
+        CU(c->tex_dev.reserve(c->tex_host.size()*sizeof(TexDesc)));
+        CU(cudaMemcpyAsync(c->tex_dev.ptr, c->tex_host.data(), c->tex_host.size()*sizeof(TexDesc),
+                           cudaMemcpyHostToDevice, c->stream));
+        rp.textures = (const TexDesc *)c->tex_dev.ptr;
+    }
     rp.refill_lanes = c->refill_lanes;
     rp.pend_lanes = c->pend_lanes;
     if(c->host_path) CU(cudaStreamWaitEvent(c->stream, c->target_ready, 0));
@@ -332,7 +345,9 @@ void b200r_destroy(b200r_context *c)
     cudaSetDevice(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
     c->recs.release(); c->segs.release(); c->spans.release(); c->tiles.release(); c->pairs.release(); c->words.release();
-    c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_color.release(); c->d_depth.release();
+    c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_uv.release(); c->d_color.release(); c->d_depth.release();
+    c->tex_dev.release();
+    for(b200r_context::HostTexture &ht : c->host_textures) ht.pixels.release();
     for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
     if(c->h_words) cudaFreeHost(c->h_words);
     if(c->total_ready) cudaEventDestroy(c->total_ready);
@@ -389,11 +404,12 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     int rc = settle_pending(c);                 // the previous frame must be complete in the stream
     if(rc != B200R_OK) return rc;
 
-    bool any_phong = false, all_phong = mesh_count > 0;
+    bool any_phong = false, all_phong = mesh_count > 0, any_tex = false;
     for(u32 i = 0; i < mesh_count; ++i)
     {
         const bool ph = (meshes[i].Flags & B200R_MESH_PHONG) != 0;
         any_phong |= ph; all_phong &= ph;
+        any_tex |= meshes[i].Texture != nullptr;
     }
     ViewParams v;
     rc = fill_view(c, cmd, target, v, all_phong);
@@ -401,6 +417,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
 
     uint64_t total = 0;
     std::vector<MeshParams> ms;
+    std::vector<TexDesc> texs;
     ms.reserve(mesh_count);
     for(u32 i = 0; i < mesh_count; ++i)
     {
@@ -413,6 +430,24 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
         mp.px = m.P.x; mp.py = m.P.y; mp.pz = m.P.z;
         mp.prim_base = (unsigned)total;
         mp.phong = (m.Flags & B200R_MESH_PHONG) ? 1 : 0;
+        mp.uv = nullptr; mp.tex = -1; mp.white = 0;
+        if(m.Texture)
+        {
+            const b200r_device_texture &t = *m.Texture;
+            if(m.TriangleCount && !m.UVs) return fail(c, B200R_E_INVALID, "textured mesh without UVs");
+            if(!t.Memory || t.Width <= 0 || t.Height <= 0 || t.Pitch < t.Width*4 || (t.Pitch & 3))
+                return fail(c, B200R_E_INVALID, "bad texture geometry");
+            size_t k = 0;
+            for(; k < texs.size(); ++k)
+                if(texs[k].mem == t.Memory && texs[k].w == t.Width && texs[k].h == t.Height && texs[k].pitch == t.Pitch) break;
+            if(k == texs.size())
+            {
+                if(k >= 65536) return fail(c, B200R_E_UNSUPPORTED, "more than 65536 distinct textures per call");
+                TexDesc d; d.mem = t.Memory; d.w = t.Width; d.h = t.Height; d.pitch = t.Pitch;
+                texs.push_back(d);
+            }
+            mp.uv = m.UVs; mp.tex = (int)k;
+        }
         total += m.TriangleCount;
         ms.push_back(mp);
     }
@@ -421,8 +456,9 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
     // first guesses (2.5 segments, 6 spans, 8 queue entries per triangle); all lists grow on demand
     if(c->segs.bytes == 0) CU(c->segs.reserve((size_t)std::max<uint64_t>(total*5/2, 1u << 16)*sizeof(SegInfo)));
-    // a frame with a Phong mesh uses the wider span record for all its spans
-    c->span_words = any_phong ? kSpanWordsPhong : kSpanWords;
+    // a frame with a Phong or a textured mesh uses the wider span record (and the raster kernel's
+    // general variant, which shades per span flag) for all its spans
+    c->span_words = (any_phong || any_tex) ? kSpanWordsPhong : kSpanWords;
     if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*c->span_words*sizeof(uint32_t)));
     // counts, cursors, offsets (+1 end entry), and the scan's chunk scratch
     CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1 + 2*((size_t)ntiles*kDepthBuckets/8192 + 2))*sizeof(unsigned)));
@@ -431,6 +467,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
 
     c->view = v;
     c->meshes.swap(ms);
+    c->tex_host.swap(texs);
     c->target = *target;
     c->total_tris = (unsigned)total;
     c->ntiles = ntiles;
@@ -490,18 +527,27 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
 {
     uint64_t verts = 0;
     size_t chunks = 0;
+    bool any_uv = false;
     for(u32 i = 0; i < n; ++i)
     {
         const render_entry_3d_object &o = objs[i];
-        if(o.Bitmap) return fail(c, B200R_E_UNSUPPORTED, "textured objects are not implemented (SURVEY.md 8f row 2)");
         u32 tris = o.VertexCount/3;                          // projekt.cpp:3886
         if(tris && (!o.VertexData || !o.ColorData || !o.NormalData)) return fail(c, B200R_E_INVALID, "object with null vertex stream");
+        if(o.Bitmap)
+        {
+            const loaded_bitmap &b = *o.Bitmap;
+            if(tris && !o.UVData) return fail(c, B200R_E_INVALID, "textured object without UVData");
+            if(!b.Memory || b.Width <= 0 || b.Height <= 0 || b.Pitch < b.Width*4 || (b.Pitch & 3))
+                return fail(c, B200R_E_INVALID, "bad Bitmap geometry");
+            any_uv = true;
+        }
         verts += (uint64_t)tris*3;
         chunks += std::max<size_t>(1, ((size_t)tris + kUploadChunk - 1)/kUploadChunk);
     }
     CU(c->d_pos.reserve((size_t)std::max<uint64_t>(verts, 1)*12));
     CU(c->d_col.reserve((size_t)std::max<uint64_t>(verts, 1)*16));
     CU(c->d_nrm.reserve((size_t)std::max<uint64_t>(verts, 1)*12));
+    if(any_uv) CU(c->d_uv.reserve((size_t)std::max<uint64_t>(verts, 1)*8));
     if(!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     if(!c->pos_ready) CU(cudaEventCreateWithFlags(&c->pos_ready, cudaEventDisableTiming));
     if(!c->target_ready) CU(cudaEventCreateWithFlags(&c->target_ready, cudaEventDisableTiming));
@@ -510,6 +556,31 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
         cudaEvent_t e = nullptr;
         CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         c->chunk_ready.push_back(e);
+    }
+
+    // 0. the objects' Bitmaps, one device copy per distinct pointer (tightly packed rows); the raster
+    //    kernel is the only reader and waits for the targets, which are enqueued after these
+    size_t ntex = 0;
+    std::vector<int> tex_of(n, -1);
+    for(u32 i = 0; i < n; ++i)
+    {
+        const loaded_bitmap *b = objs[i].Bitmap;
+        if(!b) continue;
+        size_t k = 0;
+        for(; k < ntex; ++k) if(c->host_textures[k].host == b) break;
+        if(k == ntex)
+        {
+            if(c->host_textures.size() <= ntex) c->host_textures.emplace_back();
+            b200r_context::HostTexture &ht = c->host_textures[ntex];
+            CU(ht.pixels.reserve((size_t)b->Width*b->Height*4));
+            ht.host = b;
+            ht.desc.Memory = (const u32 *)ht.pixels.ptr; ht.desc.Width = b->Width; ht.desc.Height = b->Height;
+            ht.desc.Pitch = b->Width*4;
+            CU(cudaMemcpy2DAsync(ht.pixels.ptr, (size_t)b->Width*4, b->Memory, (size_t)b->Pitch, (size_t)b->Width*4,
+                                 b->Height, cudaMemcpyHostToDevice, c->copy_stream));
+            ++ntex;
+        }
+        tex_of[i] = (int)k;
     }
 
     // 1. every position (the z-range pass reads them all before any set-up can start)
@@ -541,9 +612,19 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
             m.TriangleCount = ct;
             m.P = o.P;
             m.Flags = o.PhongShading ? B200R_MESH_PHONG : 0u;
+            m.UVs = nullptr; m.Texture = nullptr;
+            if(tex_of[i] >= 0)
+            {
+                m.UVs = (const r32 *)c->d_uv.ptr + at*2;
+                m.Texture = &c->host_textures[tex_of[i]].desc;
+            }
             if(nv)
             {
-                CU(cudaMemcpyAsync((void *)m.Colors, (const r32 *)o.ColorData + v0*4, nv*16, cudaMemcpyHostToDevice, c->copy_stream));
+                // a textured object's vertex colours never reach the image (MeshParams::uv): not uploaded
+                if(tex_of[i] < 0)
+                    CU(cudaMemcpyAsync((void *)m.Colors, (const r32 *)o.ColorData + v0*4, nv*16, cudaMemcpyHostToDevice, c->copy_stream));
+                else
+                    CU(cudaMemcpyAsync((void *)m.UVs, (const r32 *)o.UVData + v0*2, nv*8, cudaMemcpyHostToDevice, c->copy_stream));
                 CU(cudaMemcpyAsync((void *)m.Normals, (const r32 *)o.NormalData + v0*3, nv*12, cudaMemcpyHostToDevice, c->copy_stream));
             }
             CU(cudaEventRecord(c->chunk_ready[meshes.size()], c->copy_stream));
@@ -634,14 +715,22 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
 {
     if(!c) return B200R_E_INVALID;
     if(!obj || !cmd) return fail(c, B200R_E_INVALID, "null argument");
-    if(obj->Bitmap) return fail(c, B200R_E_UNSUPPORTED, "textured edge tables are not implemented");
     if(!obj->EdgeMemory) return fail(c, B200R_E_INVALID, "null EdgeMemory");
+    const bool textured = obj->Bitmap != nullptr;
+    if(textured && obj->VertexCount >= 3 && !obj->UVData) return fail(c, B200R_E_INVALID, "textured object without UVData");
     CU(cudaSetDevice(c->device));
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
+    // A textured object takes two passes of the set-up kernel: colours (lit white on the Gouraud
+    // path, projekt.cpp:4034-4060; the vertex colours on the Phong path, :4014) and then u/z, v/z,
+    // 1/z, which travel in the colour words (MeshParams::uv).  The first pass is an untextured upload.
+    render_entry_3d_object plain = *obj;
+    plain.Bitmap = nullptr;
     std::vector<b200r_device_mesh> meshes;
-    rc = upload_objects(c, obj, 1, meshes);
+    rc = upload_objects(c, &plain, 1, meshes);
     if(rc != B200R_OK) return rc;
+    CU(cudaStreamWaitEvent(c->stream, c->pos_ready, 0));
+    CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[meshes.size() - 1], 0));
     const u32 tris = meshes[0].TriangleCount;
     if(tris == 0) return 0;
 
@@ -672,11 +761,23 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     mp.pos = meshes[0].Positions; mp.col = meshes[0].Colors; mp.nrm = meshes[0].Normals;
     mp.ntri = tris; mp.px = obj->P.x; mp.py = obj->P.y; mp.pz = obj->P.z; mp.prim_base = 0;
     mp.phong = phong ? 1 : 0;
+    mp.uv = nullptr; mp.tex = -1; mp.white = (textured && !phong) ? 1 : 0;
     launch_setup(v, mp, so, c->stream);
     c->stats.KernelLaunches += 1;
     CU(cudaGetLastError());
-    std::vector<uint32_t> recs((size_t)tris*kRecWords);
+    std::vector<uint32_t> recs((size_t)tris*kRecWords), uvrecs;
     CU(cudaMemcpyAsync(recs.data(), c->recs.ptr, recs.size()*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if(textured)
+    {
+        CU(c->d_uv.reserve((size_t)tris*3*8));
+        CU(cudaMemcpyAsync(c->d_uv.ptr, obj->UVData, (size_t)tris*3*8, cudaMemcpyHostToDevice, c->stream));
+        mp.uv = (const float *)c->d_uv.ptr; mp.tex = 0; mp.white = 0;
+        launch_setup(v, mp, so, c->stream);
+        c->stats.KernelLaunches += 1;
+        CU(cudaGetLastError());
+        uvrecs.resize(recs.size());
+        CU(cudaMemcpyAsync(uvrecs.data(), c->recs.ptr, uvrecs.size()*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
 
     // Host side of FillEdgeTable's tail: append each triangle's edges in the reference's
@@ -720,6 +821,15 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
         o.ColorGradient.z = f(E_DC + 2); o.ColorGradient.w = f(E_DC + 3);
         o.Left = (b32)(E[E_LEFT] & 1u);
         o.Next = nullptr;
+        if(textured)
+        {
+            // same triangle, same slot of the second pass: u/z, v/z, 1/z in the colour words
+            const uint32_t *U = uvrecs.data() + (E - recs.data());
+            auto g = [&](int w) { uint32_t u = U[w]; if((u & 0x7fffffffu) > 0x7f800000u) u = 0xffc00000u;
+                                  float x; memcpy(&x, &u, 4); return x; };
+            o.UMin = g(E_C + 0); o.VMin = g(E_C + 1); o.OneOverZMin = g(E_C + 2);
+            o.UGradient = g(E_DC + 0); o.VGradient = g(E_DC + 1); o.OneOverZGradient = g(E_DC + 2);
+        }
         if(phong)
         {
             // projekt.cpp:4017-4018, 4104-4109: MinNormal = the upper vertex's normal (not advanced by

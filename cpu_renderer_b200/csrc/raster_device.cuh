@@ -52,7 +52,17 @@ struct MeshParams
     float px, py, pz;           // render_entry_3d_object::P
     unsigned prim_base;         // submission index of this mesh's first triangle
     int phong;                  // render_entry_3d_object::PhongShading
+    // Textured mesh (render_entry_3d_object::Bitmap != 0).  Every pixel of such a mesh takes its
+    // colour from the texel (projekt.cpp:427-446), so the interpolated vertex colours never reach the
+    // image, and u/z, v/z, 1/z are interpolated by exactly the operations the colour channels use
+    // (edge step += gradient :554-560, span increment (R-L)/XDifference :336-342, start += XOffset*inc
+    // :409-410): in tex mode the four colour interpolants CARRY (u/z, v/z, 1/z, 0).
+    const float *uv;            // v2 x 3 per triangle, or null
+    int tex;                    // index into the frame's texture table, -1: untextured
+    int white;                  // b200r_fill_edge_table of a textured Gouraud object: light white vertices (:4034-4060)
 };
+
+struct TexDesc { const uint32_t *mem; int w, h, pitch; };   // loaded_bitmap of a texture; pitch in bytes
 
 // Compact per-triangle record written by the setup kernel and read by the raster kernel:
 // the fields of edge_info (projekt.h:17-37) that the Gouraud path defines, for the <= 3 edges
@@ -75,6 +85,7 @@ enum { P_PRIM = 0, P_Y = 1, P_MINX = 2, P_MAXX = 3, P_Z = 4, P_C = 5, P_ZI = 9, 
 // P_ZUB: an upper bound of every depth value the span can produce (see span_depth_bound)
 constexpr unsigned kSpanNonFinite = 1u;   // colours may be NaN/Inf/huge -> guarded pack
 constexpr unsigned kSpanAlias = 4u;       // Phong alias pixel: shade at X = word 19, Row = word 20 (not at its own column/row)
+constexpr unsigned kSpanTex = 8u;         // textured: colour words hold u/z, v/z, 1/z; texture index in bits 8..23 of P_FLAGS
 constexpr unsigned kSpanPhong = 2u;       // per-pixel Phong shading (projekt.cpp:450-509): words 16..21 hold the normals
 
 // Segment: the consecutive spans of one triangle that share one pair of active edges and lie in
@@ -105,6 +116,7 @@ struct RasterParams
     int color_pitch_words;      // u32 per row
     int depth_stride;           // floats per row
     int bulk_ok;                // rows may be moved with cp.async.bulk (16-byte aligned)
+    const TexDesc *textures;    // device: the frame's texture table (null without textured meshes)
     int refill_lanes;           // idle lanes of a warp that trigger a refill from the span queue
     int pend_lanes;             // parked lanes of a warp that trigger the depth-pass path
 };

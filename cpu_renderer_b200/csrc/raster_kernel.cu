@@ -119,6 +119,33 @@ __device__ __noinline__ uint32_t phong_pixel(const ViewParams &v, float c0, floa
     return pack_argb(clamp01(f[0]), clamp01(f[1]), clamp01(f[2]), clamp01(f[3]), guarded);   // :483-493
 }
 
+// ---- textured pixel, projekt.cpp:427-446 ----------------------------------------------------
+// (uz, vz, oz): the span's interpolated u/z, v/z, 1/z at this pixel.  Nearest texel at
+// Round(uv*(dim-1)); coordinates that leave the bitmap are clamped (the reference reads outside it;
+// cvtss2si's INT_MIN for NaN / overflow clamps to 0).  Unlit (Gouraud) pixels are the texel word
+// itself: Round((b/255)*255) == b for every byte (tests/test_oracle_tex.py), and the channel order
+// of the pack (:520-523) is the texel's.  Phong pixels take the texel as base colour (:444, :466).
+__device__ __noinline__ uint32_t tex_pixel(const ViewParams &v, const TexDesc *textures, int tex_id,
+                                           float uz, float vz, float oz, bool phong,
+                                           float n0, float n1, float n2, float X, float Row, float Z)
+{
+    const TexDesc td = textures[tex_id];
+    const float inv = fdiv(1.0f, oz);                                       // :429
+    const float fu = fmul(inv, uz), fv = fmul(inv, vz);
+    const float tx = fmul(fu, (float)(td.w - 1)), ty = fmul(fv, (float)(td.h - 1));   // :430-432
+    int ix = round_s32(tx), iy = round_s32(ty);                             // :433-434
+    ix = min(max(ix, 0), td.w - 1);
+    iy = min(max(iy, 0), td.h - 1);
+    const uint32_t texel = __ldg(reinterpret_cast<const uint32_t *>(
+        reinterpret_cast<const unsigned char *>(td.mem) + (size_t)iy*(size_t)td.pitch) + ix);   // :436-438
+    if(!phong) return texel;
+    const float sa = fdiv((float)((texel >> 24) & 0xFFu), 255.0f);          // :440-443
+    const float sr = fdiv((float)((texel >> 16) & 0xFFu), 255.0f);
+    const float sg = fdiv((float)((texel >> 8) & 0xFFu), 255.0f);
+    const float sb = fdiv((float)(texel & 0xFFu), 255.0f);
+    return phong_pixel(v, sr, sg, sb, sa, n0, n1, n2, X, Row, Z, true);
+}
+
 template<int TW, int TH>
 struct TileLayout
 {
@@ -247,6 +274,7 @@ raster_kernel(const RasterParams p)
             float n0 = 0, n1 = 0, n2 = 0, ni0 = 0, ni1 = 0, ni2 = 0;       // Phong: normal and its per-pixel increment
             float shade_dx = 0, shade_row = 0;                             // Phong: X = x + shade_dx, Row for UnprojectVertex
             bool phong_span = false;
+            int tex_id = -1;                                               // textured span: c0..c2 carry u/z, v/z, 1/z
             int prim = 0, n_left = 0, x = 0;
             uint32_t rowaddr = tile_addr;                  // shared address of column 0 of the span's row
             bool guarded = false, exhausted = false, pending = false;
@@ -264,9 +292,13 @@ raster_kernel(const RasterParams p)
                     const uint32_t pa = rowaddr + (uint32_t)x*16u;
                     Pixel mine;
                     mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
-                    mine.color = (PHONG && phong_span)
-                                 ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
-                                 : pack_argb(c0, c1, c2, c3, guarded);
+                    if(PHONG && tex_id >= 0)
+                        mine.color = tex_pixel(p.v, p.textures, tex_id, c0, c1, c2, phong_span, n0, n1, n2,
+                                               fadd((float)x, shade_dx), shade_row, z);
+                    else
+                        mine.color = (PHONG && phong_span)
+                                     ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
+                                     : pack_argb(c0, c1, c2, c3, guarded);
                     mine.pad = 0;
                     Pixel old = lds_pixel(pa);
                     while(true)
@@ -319,6 +351,7 @@ raster_kernel(const RasterParams p)
                             {
                                 const unsigned fl = __float_as_uint(q3.z);
                                 phong_span = (fl & kSpanPhong) != 0;
+                                tex_id = (fl & kSpanTex) ? (int)((fl >> 8) & 0xffffu) : -1;
                                 shade_dx = 0.0f; shade_row = (float)y;
                                 if(phong_span)
                                 {

@@ -181,7 +181,15 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const float *gc = m.col + (size_t)base*12;
         const float *gn = m.nrm + (size_t)base*9;
         const bool aligned = ((((uintptr_t)gp) | ((uintptr_t)gc) | ((uintptr_t)gn)) & 15) == 0;
-        if(n == (unsigned)kSetupThreads && aligned)
+        if(m.uv != nullptr)
+        {
+            // textured mesh: the vertex colours never reach the image (MeshParams::uv); the colour
+            // slots of the staging area take the UVs, two floats per vertex
+            const float *gu = m.uv + (size_t)base*6;
+            for(unsigned i = t; i < n*9; i += kSetupThreads) { s_pos[i] = __ldg(gp + i); s_nrm[i] = __ldg(gn + i); }
+            for(unsigned i = t; i < n*6; i += kSetupThreads) s_col[(i/6)*12 + (i%6)] = __ldg(gu + i);
+        }
+        else if(n == (unsigned)kSetupThreads && aligned)
         {
             constexpr int kPos4 = kSetupThreads*9/4, kCol4 = kSetupThreads*12/4;     // 288, 384 float4
             const float4 *gp4 = reinterpret_cast<const float4 *>(gp);
@@ -327,8 +335,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     float4 c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
                     float col[4] = { c4.x, c4.y, c4.z, c4.w };
                     V3 nr = { s_nrm[tri*9 + 3*q + 0], s_nrm[tri*9 + 3*q + 1], s_nrm[tri*9 + 3*q + 2] };
-                    if(PHONG) { lit[q][0] = col[0]; lit[q][1] = col[1]; lit[q][2] = col[2]; lit[q][3] = col[3]; }   // :4014-4015
-                    else light_vertex(cam[q], nr, col, v, lit[q]);
+                    if(m.uv != nullptr) { lit[q][0] = s_col[tri*12 + 2*q]; lit[q][1] = s_col[tri*12 + 2*q + 1]; lit[q][2] = 0.0f; lit[q][3] = 0.0f; }
+                    else if(PHONG) { lit[q][0] = col[0]; lit[q][1] = col[1]; lit[q][2] = col[2]; lit[q][3] = col[3]; }   // :4014-4015
+                    else
+                    {
+                        if(m.white) { col[0] = col[1] = col[2] = col[3] = 1.0f; }   // :4034-4060: Hadamard(V4(1,1,1,1), ...)
+                        light_vertex(cam[q], nr, col, v, lit[q]);
+                    }
                 }
                 int max_row = (int)0x80000000;
 #pragma unroll 1
@@ -353,13 +366,36 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     E[E_YMIN] = (uint32_t)ymin; E[E_YMAX] = (uint32_t)ymax;
                     E[E_X] = __float_as_uint(x); E[E_DX] = __float_as_uint(g);
                     E[E_Z] = __float_as_uint(z); E[E_DZ] = __float_as_uint(zg);
-                    float omt = fsub(1.0f, tt);
-#pragma unroll
-                    for(int i = 0; i < 4; ++i)
+                    if(m.uv != nullptr)
                     {
-                        float c0 = fadd(fmul(omt, lit[mn[e]][i]), fmul(tt, lit[mx[e]][i]));          // :4091
-                        E[E_C + i] = __float_as_uint(c0);
-                        E[E_DC + i] = __float_as_uint(fdiv_zq(fsub(lit[mx[e]][i], c0), ydiff));         // :4096
+                        // projekt.cpp:4002-4008, 4078-4089.  z of a projected vertex is
+                        // DistanceAboveTarget - camera z (:81, :89).  UMin is u/z, a true division; the
+                        // gradient is built from u*(1/z) -- both forms are kept.
+                        const float zmin_p = minv.z, zmax_p = maxv.z;
+                        const float u0 = lit[mn[e]][0], v0 = lit[mn[e]][1], u1 = lit[mx[e]][0], v1 = lit[mx[e]][1];
+                        float umin = fdiv(u0, zmin_p), vmin = fdiv(v0, zmin_p), wmin = fdiv(1.0f, zmin_p);   // :4002-4004
+                        const float inv_max = fdiv(1.0f, zmax_p), inv_min = fdiv(1.0f, zmin_p);
+                        const float su = fmul(inv_max, u1), sv = fmul(inv_max, v1);                    // :4006
+                        const float fu = fmul(inv_min, u0), fv = fmul(inv_min, v0);                    // :4008
+                        const float ug = fdiv_zq(fsub(su, fu), ydiff), vg = fdiv_zq(fsub(sv, fv), ydiff);   // :4080-4081
+                        umin = fadd(umin, fmul(clipped, ug)); vmin = fadd(vmin, fmul(clipped, vg));    // :4083-4084
+                        const float wg = fdiv_zq(fsub(fdiv(1.0f, zmax_p), wmin), ydiff);               // :4086
+                        wmin = fadd(wmin, fmul(clipped, wg));                                          // :4088
+                        E[E_C + 0] = __float_as_uint(umin); E[E_C + 1] = __float_as_uint(vmin);
+                        E[E_C + 2] = __float_as_uint(wmin); E[E_C + 3] = 0u;
+                        E[E_DC + 0] = __float_as_uint(ug); E[E_DC + 1] = __float_as_uint(vg);
+                        E[E_DC + 2] = __float_as_uint(wg); E[E_DC + 3] = 0u;
+                    }
+                    else
+                    {
+                        float omt = fsub(1.0f, tt);
+#pragma unroll
+                        for(int i = 0; i < 4; ++i)
+                        {
+                            float c0 = fadd(fmul(omt, lit[mn[e]][i]), fmul(tt, lit[mx[e]][i]));          // :4091
+                            E[E_C + i] = __float_as_uint(c0);
+                            E[E_DC + i] = __float_as_uint(fdiv_zq(fsub(lit[mx[e]][i], c0), ydiff));         // :4096
+                        }
                     }
                     E[E_LEFT] = ((ymin == round_s32(prj[e].y)) ? 1u : 0u) |                           // :4093
                                 ((unsigned)mn[e] << 8) | ((unsigned)mx[e] << 16);
@@ -379,7 +415,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 
         have_walk = (nedges >= 2) && out.spans != nullptr;
         nonfinite = 0;
-        if(have_walk)
+        if(have_walk && m.uv == nullptr)
         {
             // RoundR32ToU32 (cvtss2si) and cvt.rni.s32.f32 agree only for |c*255| < 2^31.  Colours of
             // finite scenes stay near [0,1]; a triangle whose edge colours could leave that range
@@ -528,7 +564,8 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const uint32_t *rec = s_edge + tri*kEdgeRec - R_EDGE0;
         const float *nrm = PHONG ? (s_nrm + tri*9) : nullptr;
         const int sw = out.span_words;
-        const uint32_t span_flags = (nonfinite ? kSpanNonFinite : 0u) | (PHONG ? kSpanPhong : 0u);
+        const uint32_t span_flags = (nonfinite ? kSpanNonFinite : 0u) | (PHONG ? kSpanPhong : 0u) |
+                                    (m.tex >= 0 ? (kSpanTex | ((uint32_t)m.tex << 8)) : 0u);
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
         ActiveEdge L, R;
         L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;

@@ -161,7 +161,8 @@ int b200r_render_objects(b200r_context *Context, const render_entry_3d_object *O
  * Object->EdgeMemory (host, room for VertexCount records) in the reference's MergeSort order
  * (projekt.cpp:2-72, ties included).  Only the fields the selected path defines are written
  * (YMin YMax XMin Gradient ZMin ZGradient MinColor ColorGradient Left, plus Next = 0; with
- * PhongShading also MinNormal and NormalGradient).
+ * PhongShading also MinNormal and NormalGradient; with Object->Bitmap also UMin VMin OneOverZMin
+ * and their gradients, and Gouraud colours are lit white as in projekt.cpp:4034-4060).
  * Returns the edge count (>= 0) or a negative status. */
 int b200r_fill_edge_table(b200r_context *Context, const render_entry_3d_object *Object,
                           const game_render_commands *Commands, b32 PhongShading);
@@ -170,6 +171,17 @@ int b200r_fill_edge_table(b200r_context *Context, const render_entry_3d_object *
  * Device-resident path (what the host-pointer call is built from).  All pointers below are
  * device pointers; calls are asynchronous on the context's stream.
  * ------------------------------------------------------------------------------------------ */
+/* render_entry_3d_object::Bitmap (projekt.h:13) resident on the device: nearest-texel, perspective
+ * correct sampling at Round(uv * (dim - 1)) (projekt.cpp:427-446).  The reference does not
+ * range-check texel coordinates and reads outside the bitmap when they leave it; here they are
+ * clamped to the bitmap (NaN samples texel 0,0). */
+typedef struct b200r_device_texture
+{
+    const u32 *Memory;         /* device pointer, ARGB8 (loaded_bitmap::Memory) */
+    s32 Width, Height;
+    s32 Pitch;                 /* bytes per row, a multiple of 4                */
+} b200r_device_texture;
+
 typedef struct b200r_device_mesh
 {
     const r32 *Positions;      /* v3 per vertex (VertexData)  */
@@ -178,6 +190,8 @@ typedef struct b200r_device_mesh
     u32 TriangleCount;         /* VertexCount / 3             */
     v3 P;                      /* render_entry_3d_object::P   */
     u32 Flags;                 /* B200R_MESH_PHONG = render_entry_3d_object::PhongShading        */
+    const r32 *UVs;            /* v2 per vertex (UVData); read only when Texture != 0            */
+    const b200r_device_texture *Texture;   /* host struct describing device memory; 0: untextured */
 } b200r_device_mesh;
 #define B200R_MESH_PHONG 1u
 

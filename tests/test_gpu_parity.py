@@ -8,6 +8,8 @@ tests assert the stronger result -- colour identical too -- and report the LSB d
 import ctypes as C
 import os
 
+from dataclasses import replace
+
 import numpy as np
 import pytest
 
@@ -220,20 +222,27 @@ def test_unsupported_and_invalid_inputs_return_codes(renderer):
     with pytest.raises(api.B200RasterError) as e:
         renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL)
     assert e.value.code == api.E_UNSUPPORTED
-    # textured object -> unsupported, not silently untextured
+    # textured object without UVData, or with a malformed Bitmap -> invalid, not silently untextured
     lib = renderer.lib
     o = api.render_entry_3d_object()
     o.VertexCount = 3
-    dummy_bitmap = api.loaded_bitmap(1, 1, 4, color.ctypes.data)
+    texel = np.zeros((1, 1), np.uint32)
+    dummy_bitmap = api.loaded_bitmap(1, 1, 4, texel.ctypes.data)
     o.Bitmap = C.cast(C.pointer(dummy_bitmap), C.c_void_p)
     o.VertexData, o.ColorData, o.NormalData = s.positions.ctypes.data, s.colors.ctypes.data, s.normals.ctypes.data
     cmd, keep = api.make_commands(s, z.ctypes.data, s.width)
     bmp = api.loaded_bitmap(s.width, s.height, s.width * 4, color.ctypes.data)
-    assert lib.b200r_render_objects(renderer.ctx, C.byref(o), 1, C.byref(cmd), C.byref(bmp), 0) == api.E_UNSUPPORTED
+    assert lib.b200r_render_objects(renderer.ctx, C.byref(o), 1, C.byref(cmd), C.byref(bmp), 0) == api.E_INVALID
+    o.UVData = s.uvs.ctypes.data
+    dummy_bitmap.Pitch = 2
+    assert lib.b200r_render_objects(renderer.ctx, C.byref(o), 1, C.byref(cmd), C.byref(bmp), 0) == api.E_INVALID
+    dummy_bitmap.Pitch = 4
+    assert lib.b200r_render_objects(renderer.ctx, C.byref(o), 1, C.byref(cmd), C.byref(bmp), 0) == api.OK
     assert lib.b200r_render_objects(renderer.ctx, None, 1, C.byref(cmd), C.byref(bmp), 0) == api.E_INVALID
-    # an empty submission is fine and leaves the targets alone
+    # an empty submission is fine and leaves the targets alone (the textured call above drew one triangle)
+    z_before, color_before = z.copy(), color.copy()
     assert lib.b200r_render_objects(renderer.ctx, None, 0, C.byref(cmd), C.byref(bmp), 0) == api.OK
-    assert (z == np.float32(s.clear_depth)).all()
+    assert np.array_equal(z.view(np.uint32), z_before.view(np.uint32)) and np.array_equal(color, color_before)
 
 
 def test_growth_of_internal_lists_is_transparent(renderer):
@@ -327,6 +336,93 @@ def test_phong_with_zero_lights_is_black(renderer):
     renderer.render_scene_host(s, color, z, phong=True)
     check_phong(color, z, want["color"], want["z"])
     assert (color[z != np.float32(s.clear_depth)] == 0).all()      # FinalColor stays {} (projekt.cpp:448)
+
+
+# ---- textured, perspective-correct path (projekt.cpp:427-446, 4002-4008, 4078-4089) ----
+TEX = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_tex.npz"))
+
+
+def check_tex(renderer, s, want_color, want_z, phong, tile=(64, 32), **kw):
+    """Coverage and depth bit-exact; colour exact on the unlit path (the texel word itself), within
+    PHONG_TOLERANCE_LSB when the texel is the base colour of a Phong pixel."""
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(*tile)
+    renderer.render_scene_host(s, color, z, phong=phong, **kw)
+    assert np.array_equal(z.view(np.uint32), np.asarray(want_z).view(np.uint32))
+    if not phong:
+        assert np.array_equal(color, want_color), int((color != want_color).sum())
+        return 0
+    ch = np.abs(want_color.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= PHONG_TOLERANCE_LSB, int(ch.max())
+    return int((want_color != color).sum())
+
+
+@pytest.mark.parametrize("phong", [False, True])
+@pytest.mark.parametrize("name", sorted(kat_scenes.all_scenes()))
+def test_textured_kat_scene_against_golden(renderer, name, phong):
+    """Depth from the verbatim build; colour from the verbatim build where every texel coordinate
+    stays inside the bitmap, the defined clamp elsewhere (tests/golden/make_golden.py)."""
+    tag = "phong" if phong else "gouraud"
+    s = sc.textured(kat_scenes.all_scenes()[name])
+    ndiff = check_tex(renderer, s, TEX[f"{tag}_kat_{name}_color"], TEX[f"{tag}_kat_{name}_z"], phong)
+    assert ndiff <= 0.001 * s.width * s.height
+
+
+@pytest.mark.parametrize("phong", [False, True])
+@pytest.mark.parametrize("tile", [(64, 32), (128, 16)])
+def test_textured_soups(renderer, tile, phong):
+    for s in (sc.textured(sc.triangle_soup("ts", 0xB2000002, 30_000, 1280, 720, 1.5, 6.0), 256, 128, lo=0.4, hi=0.6),
+              sc.textured(sc.triangle_soup("tl", 0xB2000003, 1_500, 1280, 720, 32.0, 96.0), 256, 128),
+              sc.textured(sc.triangle_soup("tw", 0x5151, 8_000, 800, 600, 1.0, 40.0, jitter=2.5), 33, 17)):
+        s.lights = [sc.Light(), sc.Light(P=(-4.0, 3.0, 6.0), intensity=(0.2, 0.5, 0.3, 0.1))]
+        want = ol.oracle_render(s, phong=phong)
+        ndiff = check_tex(renderer, s, want["color"], want["z"], phong, tile=tile)
+        assert ndiff <= 1e-4 * s.width * s.height, ndiff
+
+
+@pytest.mark.parametrize("phong", [False, True])
+def test_textured_sphere_edge_table(renderer, phong):
+    """b200r_fill_edge_table of a textured object: u/z, v/z, 1/z and their gradients, and the
+    white-lit Gouraud colours, against verbatim FillEdgeTable records."""
+    tag = "phong" if phong else "gouraud"
+    s = replace(sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], 960, 540, 135.0),
+                texture=sc.make_texture(64, 48))
+    e = renderer.fill_edge_table(s, phong=phong)
+    fields = (ol.PHONG_FIELDS if phong else ol.GOURAUD_FIELDS) + ol.TEX_FIELDS
+    words = np.concatenate([np.ascontiguousarray(e[f]).view(np.uint32).reshape(len(e), -1) for f in fields], axis=1)
+    assert np.array_equal(words, TEX[f"{tag}_sphere_540p_edges"])
+
+
+def test_textured_and_untextured_objects_in_one_call(renderer):
+    """Three objects in one submission: Gouraud, textured Gouraud, textured Phong; the oracle
+    renders them in the same order into the same targets."""
+    s = sc.textured(sc.triangle_soup("mix", 0x7171, 9_000, 960, 540, 4.0, 40.0), 128, 64)
+    nv = s.positions.shape[0]
+    cuts = [0, nv // 9 * 3, nv // 9 * 6, nv]
+    color_w, z_w, _ = ol.new_targets(s)
+    for k, (ph, tx) in enumerate([(False, False), (False, True), (True, True)]):
+        part = replace(s, positions=s.positions[cuts[k]:cuts[k + 1]], colors=s.colors[cuts[k]:cuts[k + 1]],
+                       normals=s.normals[cuts[k]:cuts[k + 1]], uvs=s.uvs[cuts[k]:cuts[k + 1]],
+                       texture=s.texture if tx else None)
+        ol.oracle_render(part, phong=ph, targets=(color_w, z_w, None), prim_base=cuts[k] // 3)
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, splits=[cuts[1] - cuts[0], cuts[2] - cuts[1], cuts[3] - cuts[2]],
+                               phong=[False, False, True], textured=[False, True, True])
+    assert np.array_equal(z.view(np.uint32), z_w.view(np.uint32))
+    ch = np.abs(color_w.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= PHONG_TOLERANCE_LSB
+
+
+def test_out_of_range_uvs_are_clamped_like_the_oracle(renderer):
+    s = sc.textured(kat_scenes.all_scenes()["ties"], 16, 8)
+    uv = s.uvs.copy()
+    uv[0::3] = (7.5, -3.0); uv[1::3] = (9.0, -2.0); uv[2::3] = (8.0, -4.0)
+    for bad in (uv, np.full_like(uv, np.nan)):
+        sb = replace(s, uvs=bad)
+        want = ol.oracle_render(sb)
+        assert want["stats"]["TexelClamps"] > 0
+        check_tex(renderer, sb, want["color"], want["z"], False)
 
 
 # ---- BASELINE.json sizes -------------------------------------------------------------------------
