@@ -43,6 +43,7 @@ METRICS = {
 # set of 256 views split over the ranks (strong: the total work does not grow with N).
 SCALING = {"c2": "weak", "c3": "weak", "c4": "strong", "c5": "strong"}
 C5_VIEWS = 256
+TEX_SIZE = 1024                # --textured: the objects' Bitmap is TEX_SIZE x TEX_SIZE ARGB8
 
 
 def log(*a):
@@ -152,6 +153,8 @@ def run_reference(args):
     from cpu_renderer_b200 import scene as sc
     unit, workload = METRICS[args.config]
     scene = build_scene(args.config, 0, args.scale)
+    if args.textured:
+        scene = sc.textured(scene, TEX_SIZE, TEX_SIZE, lo=0.05, hi=0.95)
     s, sample, threads = cpu_sample(args.config, scene, sc, args.ref_sample, args.ref_threads)
     kind = "reference" if ol.ref_available() else "port"
     res = time_cpu(ol, s, threads, args.steps, args.warmup, kind, args.phong)
@@ -186,7 +189,7 @@ def cpu_sample(config, scene, sc, sample=0, threads=0):
     else:
         arrays = [a[:sample * 3] for a in (scene.positions, scene.colors, scene.normals, scene.uvs)]
     s = sc.Scene(scene.name, scene.width, scene.height, copy.copy(scene.transform), *arrays,
-                 scene.object_p, scene.ambient, scene.lights)
+                 scene.object_p, scene.ambient, scene.lights, texture=scene.texture)
     if config == "c5":
         s.object_p, s.transform.distance_above_target = c5_view(0)
     # every worker owns a private colour/depth pair: 2 GiB each at 16384^2, so c4 uses few workers
@@ -221,9 +224,12 @@ def time_cpu(ol, s, threads, steps, warmup, kind, phong=False):
             ol.RefLoadedBitmap(s.width, s.height, c.strides[0], c.ctypes.data) for c in colors])
         zptrs = (ol.f32p * threads)(*[z.ctypes.data_as(ol.f32p) for z in zs])
         cmd = os_.ref_commands(zs[0])
-        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc), 1 if phong else 0)
+        ctx = ol.OrcFallbackCtx(os_.pos_p, os_.col_p, os_.nrm_p, os_.P, C.pointer(os_.orc), 1 if phong else 0,
+                                os_.uvs_p if os_.orc_tex is not None else None,
+                                C.pointer(os_.orc_tex) if os_.orc_tex is not None else None)
         fb = C.cast(lib_o.orc_ref_fallback, C.c_void_p)
         user = C.cast(C.pointer(ctx), C.c_void_p)
+        lib.ref_set_texture(C.addressof(os_.ref_tex) if os_.ref_tex is not None else None)   # Object->Bitmap
         for i in range(warmup + steps):
             colors[0].fill(s.clear_color); zs[0].fill(s.clear_depth)
             t0 = time.perf_counter()
@@ -232,13 +238,14 @@ def time_cpu(ol, s, threads, steps, warmup, kind, phong=False):
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
+        lib.ref_set_texture(None)
         same = bool(np.array_equal(zs[0].view(np.uint32), pre["z"].view(np.uint32)) and
-                    np.array_equal(colors[0], pre["color"]))
-        note = (f"verbatim FillEdgeTable+DrawModel{' (PhongShading)' if phong else ''} per single-triangle object (oracle/_ref), {threads} threads with "
+                    (np.array_equal(colors[0], pre["color"]) or pre["stats"]["TexelClamps"] > 0))
+        note = (f"verbatim FillEdgeTable+DrawModel{' (PhongShading)' if phong else ''}{' (Bitmap)' if os_.ref_tex is not None else ''} per single-triangle object (oracle/_ref), {threads} threads with "
                 f"private targets folded in submission order; {int(skip.sum())} of {n} triangles that null-deref "
                 f"in the reference go through the oracle port; image identical to 1-thread oracle: {same}")
     else:
-        assert not phong, "the threaded port has no Phong variant; the verbatim build is required"
+        assert not phong and os_.orc_tex is None, "the threaded port has no Phong / textured variant; the verbatim build is required"
         for i in range(warmup + steps):
             color, z, _ = ol.new_targets(s)
             t = ol._orc_target(color, z, None)
@@ -275,6 +282,9 @@ def run_ours(args):
     unit, workload = METRICS[args.config]
     cfgname = args.config
     scene = build_scene(cfgname, rank, args.scale)
+    if args.textured:
+        from cpu_renderer_b200 import scene as sc_
+        scene = sc_.textured(scene, TEX_SIZE, TEX_SIZE, lo=0.05, hi=0.95)
     ntri, W, H = scene.triangle_count, scene.width, scene.height
     K, Wm = args.steps, args.warmup
     wpad = (W + 63) // 64 * 64
@@ -289,6 +299,12 @@ def run_ours(args):
     d_pos = torch.from_numpy(scene.positions).to(dev)
     d_col = torch.from_numpy(scene.colors).to(dev)
     d_nrm = torch.from_numpy(scene.normals).to(dev)
+    mesh_uv, mesh_tex = None, None
+    if args.textured:
+        d_uv = torch.from_numpy(scene.uvs).to(dev)
+        d_tex = torch.from_numpy(scene.texture.view(np.int32)).to(dev)
+        dtex = api.device_texture(d_tex.data_ptr(), scene.texture.shape[1], scene.texture.shape[0], scene.texture.shape[1] * 4)
+        mesh_uv, mesh_tex = d_uv.data_ptr(), C.pointer(dtex)
 
     # ---- the frames this rank renders in one step ------------------------------------------
     band_first, band_rows = 0, H
@@ -303,12 +319,12 @@ def run_ours(args):
             sv.transform = copy.copy(scene.transform)
             sv.transform.distance_above_target = D
             cmd_v, keep_v = api.make_commands(sv)
-            frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*P), mesh_flags),
-                           cmd_v, keep_v))
+            frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*P), mesh_flags,
+                                           mesh_uv, mesh_tex), cmd_v, keep_v))
     else:
         cmd0, keep0 = api.make_commands(scene)
         frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri,
-                                       api.v3(*scene.object_p), mesh_flags), cmd0, keep0))
+                                       api.v3(*scene.object_p), mesh_flags, mesh_uv, mesh_tex), cmd0, keep0))
     mesh, cmd, keep = frames[0]
     # c2/c3: one pre-cleared target pair per timed frame (clear outside the timed region).
     # c4/c5: one pair, cleared inside the step (a 16K^2 pair is 2 GiB; a real frame clears anyway).
@@ -415,7 +431,9 @@ def run_ours(args):
         r.set_stream(0)
         e2e_steps = min(K, 10)
         hs = sc.Scene(scene.name, W, H, scene.transform, pin(scene.positions).numpy(), pin(scene.colors).numpy(),
-                      pin(scene.normals).numpy(), scene.uvs, scene.object_p, scene.ambient, scene.lights)
+                      pin(scene.normals).numpy(), pin(scene.uvs).numpy() if args.textured else scene.uvs,
+                      scene.object_p, scene.ambient, scene.lights,
+                      texture=pin(scene.texture.view(np.int32)).numpy().view(np.uint32) if args.textured else None)
         hcol = [torch.full((H, W), scene.clear_color, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
                 for _ in range(e2e_steps + 1)]
         hz = [torch.full((H, W), scene.clear_depth, dtype=torch.float32).pin_memory().numpy()
@@ -429,7 +447,9 @@ def run_ours(args):
         e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
         covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
         e2e_api = "b200r_render_objects (host pointers, pinned)"
-        h2d_bytes, d2h_bytes = int(ntri * 120 + 2 * W * H * 4), int(2 * W * H * 4)
+        # a textured object's vertex colours are not uploaded (they never reach the image); its UVs and Bitmap are
+        h2d_bytes = int(ntri * (96 if args.textured else 120) + 2 * W * H * 4 + (scene.texture.nbytes if args.textured else 0))
+        d2h_bytes = int(2 * W * H * 4)
     else:
         # c4/c5: vertices from pinned host memory every step, b200r_clear_device + b200r_render_device
         # per frame (band / view), colour and depth of every frame read back to pinned host memory
@@ -484,7 +504,9 @@ def run_ours(args):
     nframes = len(frames)
     # algorithmic bytes of what THIS rank does in one step: read every vertex
     # attribute once per frame, load + store colour and depth once per pixel of its target
-    a_frame = nframes * (120.0 * ntri + 16.0 * W * band_rows)
+    # (textured: positions + normals + UVs = 96 B per triangle -- the vertex colours never reach the image)
+    tri_bytes = 96.0 if args.textured else 120.0
+    a_frame = nframes * (tri_bytes * ntri + 16.0 * W * band_rows)
     own_bytes = {"setup_kernel": 120.0 * ntri, "raster_kernel": 16.0 * W * band_rows,
                  "tile_scan_kernel": 0.0, "scatter_kernel": 0.0}[dominant]
     achieved = own_bytes / (stage_ms[dominant] * 1e-3) / 1e9
@@ -494,8 +516,9 @@ def run_ours(args):
         "metric": unit, "value": to_value(ms, world), "unit": unit, "n_gpus": world, "steps": K,
         "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING[cfgname],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload + (" -- per-pixel Phong shading" if args.phong else ""),
-                   "shading": "phong" if args.phong else "gouraud", "triangles": ntri, "width": W, "height": H,
+        "config": {"workload": workload + (" -- per-pixel Phong shading" if args.phong else "") +
+                               (f" -- textured, {TEX_SIZE}x{TEX_SIZE} ARGB8, perspective correct" if args.textured else ""),
+                   "shading": ("phong" if args.phong else "gouraud") + ("+texture" if args.textured else ""), "triangles": ntri, "width": W, "height": H,
                    "parallelism": ({"c4": f"screen-space row bands x{world}", "c5": f"{C5_VIEWS} views over {world} ranks"}
                                    .get(cfgname, f"frame-parallel x{world}") if world > 1 else "1 GPU"),
                    "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": args.scale,
@@ -551,6 +574,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="c2", choices=sorted(METRICS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the triangle count (smoke runs only)")
+    ap.add_argument("--textured", action="store_true", help="every object carries a 1024x1024 Bitmap and per-vertex UVs")
     ap.add_argument("--phong", action="store_true", help="per-pixel Phong shading (PhongShading = 1) instead of Gouraud")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", default=None, help="WxH: 64x32 (default), 32x32, 128x16, 64x16")
