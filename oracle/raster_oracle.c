@@ -475,6 +475,178 @@ int32_t orc_draw_triangle_tex(const orc_edge *Edges, uint32_t EdgeCount, int32_t
     return Result;
 }
 
+/* ---- level 0: the whole-object list, link by link (see raster_oracle.h) ---------------------- */
+typedef struct object_walk {
+    active_edge *A;            /* running values; the reference keeps them in the edge records */
+    int32_t *Next;             /* edge_info::Next as an index, -1 = null */
+    uint32_t Count;
+} object_walk;
+
+/* projekt.cpp:212-216 / 229-233 on list members */
+static int walk_before(const object_walk *W, int32_t New, int32_t Old)
+{
+    return edge_before(&W->A[New], &W->A[Old]);
+}
+
+int32_t orc_draw_object(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimBase,
+                        orc_target *T, orc_stats *Stats, const orc_scene *Scene, int32_t Phong,
+                        const orc_texture *Tex, int32_t *SpansDrawn)
+{
+    if(SpansDrawn) *SpansDrawn = 0;
+    if(EdgeCount == 0) return 0;
+    int32_t FirstRow = Edges[0].YMin;                            /* :173 */
+    int32_t MaxRow = Edges[0].YMax;                              /* :176-185 */
+    for(uint32_t e = 1; e < EdgeCount; ++e) if(MaxRow < Edges[e].YMax) MaxRow = Edges[e].YMax;
+    int32_t MaxY = MaxRow;                                       /* :187-196 */
+    if(MaxY > T->Height) MaxY = T->Height;
+
+    object_walk W;
+    W.Count = EdgeCount;
+    W.A = (active_edge *)malloc(sizeof(active_edge)*EdgeCount);
+    W.Next = (int32_t *)malloc(sizeof(int32_t)*EdgeCount);
+    for(uint32_t e = 0; e < EdgeCount; ++e)
+    {
+        active_edge *N = &W.A[e];
+        N->X = Edges[e].XMin; N->Z = Edges[e].ZMin; N->E = Edges + e;
+        for(int i = 0; i < 4; ++i) N->C[i] = Edges[e].MinColor[i];
+        for(int i = 0; i < 3; ++i) N->N[i] = Edges[e].MinNormal[i];
+        N->U = Edges[e].UMin; N->V = Edges[e].VMin; N->W = Edges[e].OneOverZMin;
+        W.Next[e] = -1;                                          /* FillEdgeTable: Next = 0 (:4094) */
+    }
+    int32_t *Next = W.Next;
+    active_edge *A = W.A;
+    int32_t Head = -1, Tail = -1;                                /* :189-190 */
+    int32_t Result = 0, Spans = 0;
+    /* any loop of the reference that follows Next more often than this has entered a cycle */
+    const uint64_t Fuse = 4ull*EdgeCount + 64;
+#define NULL_DEREF() do { Result |= 2; goto done; } while(0)
+
+    for(int32_t Row = FirstRow; Row < MaxY; ++Row)               /* :198 */
+    {
+        for(uint32_t e = 0; e < EdgeCount; ++e)                  /* :202-260 insertion */
+        {
+            if(Edges[e].YMin != Row) continue;
+            const int32_t Cur = (int32_t)e;
+            if(Head >= 0)
+            {
+                if(walk_before(&W, Cur, Head)) { Next[Cur] = Head; Head = Cur; }        /* :212-220 */
+                else
+                {
+                    int32_t Compared = Head, Previous = Head;                            /* :223-224 */
+                    uint64_t Steps = 0;
+                    while(Compared != Tail)                                               /* :225 */
+                    {
+                        Compared = Next[Compared];                                        /* :227 */
+                        if(Compared < 0 || ++Steps > Fuse) NULL_DEREF();                  /* stale ListTail */
+                        if(walk_before(&W, Cur, Compared))                                /* :229-233 */
+                        {
+                            Next[Cur] = Compared; Next[Previous] = Cur; Compared = Tail;  /* :235-237 */
+                        }
+                        else Previous = Compared;                                         /* :241 */
+                    }
+                    if(Previous == Compared) { Next[Tail] = Cur; Tail = Cur; }            /* :246-250 */
+                }
+            }
+            else { Head = Cur; Tail = Head; }                                             /* :254-258 */
+        }
+
+        for(uint64_t Steps = 0;; ++Steps)                        /* :262-267 expiry at the head */
+        {
+            if(Head < 0 || Steps > Fuse) NULL_DEREF();           /* the list ran empty */
+            if(!(A[Head].E->YMax <= Row)) break;
+            int32_t Removed = Head; Head = Next[Head]; Next[Removed] = -1;
+        }
+        {
+            int32_t Previous = Head, Checked = Head;             /* :269-296 expiry behind the head */
+            uint64_t Steps = 0;
+            while(Checked != Tail)
+            {
+                Checked = Next[Checked];
+                if(Checked < 0 || ++Steps > Fuse) NULL_DEREF();
+                if(A[Checked].E->YMax <= Row)
+                {
+                    if(Checked == Tail) { Tail = Previous; Next[Tail] = -1; Checked = Tail; }
+                    else { Next[Previous] = Next[Checked]; Checked = Previous; }
+                }
+                Previous = Checked;
+            }
+        }
+
+        int32_t PrevCur = -1, PrevNext = -1;                     /* :298-303 */
+        int32_t Cur = Head, Nxt = Next[Cur];                     /* Head >= 0 here */
+        uint64_t Pairs = 0;
+        while(Nxt >= 0)
+        {
+            if(++Pairs > Fuse) NULL_DEREF();
+            orc_fill_span(&A[Cur], &A[Nxt], Row, PrimBase + Spans, T, Stats, Scene, Phong, Tex);   /* :306-540 */
+            ++Spans; Result |= 1;
+            active_edge *L = &A[Cur], *R = &A[Nxt];
+            L->X += L->E->Gradient;      R->X += R->E->Gradient;     /* :542-543 */
+            L->Z += L->E->ZGradient;     R->Z += R->E->ZGradient;    /* :545-546 */
+            for(int i = 0; i < 4; ++i) { L->C[i] += L->E->ColorGradient[i]; R->C[i] += R->E->ColorGradient[i]; }   /* :548-549 */
+            if(Phong)                                                /* :551-552 */
+            {
+                float Tl[3], Tr[3];
+                for(int i = 0; i < 3; ++i) { Tl[i] = L->N[i] + L->E->NormalGradient[i]; Tr[i] = R->N[i] + R->E->NormalGradient[i]; }
+                normalize3(Tl, L->N);
+                normalize3(Tr, R->N);
+            }
+            L->U += L->E->UGradient; L->V += L->E->VGradient; L->W += L->E->OneOverZGradient;   /* :554-556 */
+            R->U += R->E->UGradient; R->V += R->E->VGradient; R->W += R->E->OneOverZGradient;   /* :558-560 */
+
+            if(A[Cur].X > A[Nxt].X)                                  /* :562-572: exchange inside the pair */
+            {
+                Next[Cur] = Next[Nxt];
+                Next[Nxt] = Cur;
+                if(PrevNext >= 0) Next[PrevNext] = Nxt;
+                Cur = Nxt;
+                Nxt = Next[Cur];
+            }
+            if(PrevNext >= 0)                                        /* :574-584: exchange across pairs */
+            {
+                if(A[PrevNext].X > A[Cur].X)
+                {
+                    Next[PrevNext] = Next[Cur];
+                    Next[Cur] = PrevNext;
+                    Next[PrevCur] = Cur;
+                    PrevNext = Cur;
+                    Cur = Next[PrevNext];
+                    if(Cur < 0) NULL_DEREF();
+                }
+            }
+            PrevCur = Cur; PrevNext = Nxt;                           /* :586-587 */
+            if(Nxt < 0) NULL_DEREF();
+            if(Next[Nxt] >= 0) { Cur = Next[Nxt]; Nxt = Next[Cur]; } /* :589-597 */
+            else Nxt = -1;
+        }
+    }
+done:
+#undef NULL_DEREF
+    free(W.A); free(W.Next);
+    if(SpansDrawn) *SpansDrawn = Spans;
+    return Result;
+}
+
+int32_t orc_render_object(const float *Pos, const float *Col, const float *Nrm, const float *UV,
+                          uint32_t VertexCount, const float P[3], const orc_scene *Scene, int32_t Phong,
+                          const orc_texture *Tex, orc_target *T, int32_t PrimBase, orc_stats *Stats)
+{
+    if(VertexCount < 3) return 0;
+    orc_edge *Edges = (orc_edge *)malloc(sizeof(orc_edge)*VertexCount);
+    orc_edge *Temp = (orc_edge *)malloc(sizeof(orc_edge)*VertexCount);
+    const int Textured = UV && Tex;
+    int32_t Count = orc_fill_edge_table_tex(Pos, Col, Nrm, Textured ? UV : 0, VertexCount, P, Scene, Phong, Edges, Temp);
+    int32_t R = Count;
+    if(Count > 0)
+    {
+        if(Stats) { Stats->Triangles += VertexCount/3; }
+        R = orc_draw_object(Edges, (uint32_t)Count, PrimBase, T, Stats, Scene, Phong, Textured ? Tex : 0, 0);
+        if(Stats && (R & 2)) Stats->RefWouldCrash += 1;
+    }
+    free(Edges); free(Temp);
+    return R;
+}
+
 /* One triangle = one object: FillEdgeTable on the 3-vertex object, then the level-1 walk. */
 static int32_t render_one_tex(const float *Pos, const float *Col, const float *Nrm, const float *UV, uint32_t Tri,
                               const float P[3], const orc_scene *Scene, int32_t Phong, const orc_texture *Tex,

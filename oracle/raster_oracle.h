@@ -123,6 +123,22 @@ int32_t orc_draw_triangle_tex(const orc_edge *Edges, uint32_t EdgeCount, int32_t
                               orc_target *Target, orc_stats *Stats, const orc_scene *Scene, int32_t Phong,
                               const orc_texture *Texture);
 
+/* LEVEL 0, whole-object semantics: DrawModel's intrusive active-edge list over
+ * ALL edges of an object (projekt.cpp:198-303, 542-597), replayed link by link with indices instead
+ * of pointers -- including what makes its images differ from level 1: consecutive list entries are
+ * paired whatever triangle they belong to (:300-303, :584-592), and the exchanges (:562-583) relink
+ * nodes without updating ListHead / ListTail.  Where the reference dereferences a null pointer
+ * (empty list :262, :300; stale tail :222, :275) or would follow a cycle, the object STOPS drawing:
+ * bit 2 of the result (the verbatim build crashes there).  Spans get PrimBase + their draw order as
+ * owner.  Returns 1 if anything was drawn, | 2 if the reference would crash. */
+int32_t orc_draw_object(const orc_edge *Edges, uint32_t EdgeCount, int32_t PrimBase,
+                        orc_target *Target, orc_stats *Stats, const orc_scene *Scene, int32_t Phong,
+                        const orc_texture *Texture, int32_t *SpansDrawn);
+/* FillEdgeTable over the whole vertex array as ONE object, then orc_draw_object. */
+int32_t orc_render_object(const float *Pos, const float *Col, const float *Nrm, const float *UV,
+                          uint32_t VertexCount, const float P[3], const orc_scene *Scene, int32_t Phong,
+                          const orc_texture *Texture, orc_target *Target, int32_t PrimBase, orc_stats *Stats);
+
 /* Per-triangle semantics over a soup, in submission order.  PrimBase is added to the
  * triangle index stored in Target->Prim.  WouldCrash (optional, one byte per triangle). */
 int32_t orc_render_triangles(const float *Pos, const float *Col, const float *Nrm,

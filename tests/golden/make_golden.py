@@ -179,6 +179,28 @@ def main():
             [np.ascontiguousarray(e[f]).view(np.uint32).reshape(len(e), -1) for f in fields], axis=1)
     np.savez_compressed(os.path.join(HERE, "reference_vectors_tex.npz"), **tex)
 
+    # ---- level 0: whole objects through the verbatim call pair --------------------
+    # status >= 0: the edge count; -2: the reference dereferenced a null list pointer (the image holds
+    # what it had drawn until then -- the oracle stops at the same place)
+    lvl0 = {}
+    cases = {}
+    s540 = sc.sphere_scene(pos, col, nrm, uvs, 960, 540, 135.0)
+    cases["sphere"] = (s540, False)
+    cases["sphere_phong"] = (s540, True)
+    cases["sphere_tex"] = (replace(s540, texture=sc.make_texture(64, 48)), False)
+    cases["sphere_tex_phong"] = (replace(s540, texture=sc.make_texture(64, 48)), True)
+    for k, (P, m2p) in enumerate([((0.9, 0.0, 0.0), 300.0), ((-0.8, -0.6, 0.0), 400.0), ((0.0, 0.75, 0.0), 350.0),
+                                  ((0.3, -0.2, 0.5), 150.0), ((0.0, 0.0, 0.0), 60.0)]):
+        cases[f"sphere_moved{k}"] = (sc.sphere_scene(pos, col, nrm, uvs, 960, 540, m2p, object_p=P), False)
+    for seed, cnt in ((1, 40), (2, 200), (3, 1000)):
+        cases[f"soup_as_object{seed}"] = (sc.triangle_soup("one", seed, cnt, 640, 360, 4.0, 30.0), False)
+    for name, (s, phong) in cases.items():
+        r = ol.ref_render_object(s, phong=phong)
+        lvl0[f"{name}_status"] = np.int64(r["status"])
+        lvl0[f"{name}_color_hash"] = np.array(ol.fnv1a64_words(r["color"]))
+        lvl0[f"{name}_z_hash"] = np.array(ol.fnv1a64_words(r["z"]))
+    np.savez_compressed(os.path.join(HERE, "reference_vectors_level0.npz"), **lvl0)
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     for k in sorted(out):
         v = out[k]

@@ -187,6 +187,9 @@ def oracle():
                                                  C.c_int32, C.POINTER(OrcTexture), C.POINTER(OrcTarget),
                                                  C.c_int32, C.c_void_p, C.POINTER(OrcStats)]
         lib.orc_render_triangles_tex.restype = C.c_int32
+        lib.orc_render_object.argtypes = [f32p, f32p, f32p, f32p, C.c_uint32, f32p, C.POINTER(OrcScene), C.c_int32,
+                                          C.POINTER(OrcTexture), C.POINTER(OrcTarget), C.c_int32, C.POINTER(OrcStats)]
+        lib.orc_render_object.restype = C.c_int32
         lib.orc_render_triangles_mt.argtypes = [f32p, f32p, f32p, C.c_uint32, f32p,
                                                 C.POINTER(OrcScene), C.POINTER(OrcTarget),
                                                 C.c_uint32, C.POINTER(OrcStats)]
@@ -327,6 +330,21 @@ def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0, 
                                       prim_base, crash.ctypes.data, C.byref(stats))
     assert rc == 0, rc
     return dict(color=color, z=z, prim=prim, stats=stats.as_dict(), would_crash=crash)
+
+
+def oracle_render_object(scene, with_prim=False, targets=None, prim_base=0, phong=False):
+    """Level 0: the whole scene as ONE object (orc_render_object).  status: bit 0 drew, bit 1 the
+    verbatim reference would crash (the object stops drawing there); negative: no lights."""
+    lib = oracle()
+    s = OracleScene(scene)
+    color, z, prim = targets if targets is not None else new_targets(scene, with_prim)
+    t = _orc_target(color, z, prim)
+    stats = OrcStats()
+    rc = lib.orc_render_object(s.pos_p, s.col_p, s.nrm_p, s.uvs_p if s.orc_tex is not None else None,
+                               scene.positions.shape[0], s.P, C.byref(s.orc), 1 if phong else 0,
+                               C.byref(s.orc_tex) if s.orc_tex is not None else None, C.byref(t), prim_base,
+                               C.byref(stats))
+    return dict(color=color, z=z, prim=prim, stats=stats.as_dict(), status=rc)
 
 
 def oracle_edge_table(scene, first_vertex=0, vertex_count=None, phong=False):
