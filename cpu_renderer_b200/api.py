@@ -90,7 +90,7 @@ class device_target(C.Structure):
 class frame_stats(C.Structure):
     _fields_ = [("Triangles", C.c_uint64), ("Binned", C.c_uint64), ("Segments", C.c_uint64),
                 ("Spans", C.c_uint64), ("AliasPixels", C.c_uint64), ("TilePairs", C.c_uint64),
-                ("Tiles", C.c_uint64), ("KernelLaunches", C.c_uint64), ("Reruns", C.c_uint64)]
+                ("Tiles", C.c_uint64), ("KernelLaunches", C.c_uint64), ("Reruns", C.c_uint64), ("StoppedObjects", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -47,6 +47,7 @@ struct FrameWords
     unsigned extra_total;
     unsigned overflow;                  // finalize_kernel: some list did not fit
     unsigned seg_max, span_max;         // finalize_kernel: largest region fill (incl. alias entries)
+    unsigned stopped;                   // whole-object mode: objects that stopped where the reference dereferences null
     unsigned zkeys[2];                  // z range of the frame: ordered keys, then {zmax, 1/range} as floats
     unsigned long long counters[4];     // binned triangles, queue entries, segments, spans
     unsigned seg_fill[kSubAllocators];
@@ -69,6 +70,12 @@ struct b200r_context
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
+    // whole-object mode (B200R_WHOLE_OBJECT_AEL): the last issued frame's objects
+    bool object_mode = false;
+    std::vector<ObjectDesc> obj_host;
+    DeviceBuffer obj_dev, edges_pristine, edges_work;
+    size_t edges_bytes = 0;
+    unsigned obj_total_slots = 0;       // sum of the objects' span bounds
     // textures of the last issued frame: distinct b200r_device_texture descriptors, uploaded as a table
     std::vector<TexDesc> tex_host;
     DeviceBuffer tex_dev;
@@ -168,8 +175,13 @@ static int issue_frame(b200r_context *c)
     CU(cudaMemsetAsync(tile_count, 0, (size_t)nbins*2*sizeof(unsigned), c->stream));
     CU(cudaMemsetAsync(words, 0, sizeof(FrameWords), c->stream));
 
-    const unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
-    const unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(c->span_words*sizeof(uint32_t)), 0xffffffffu);
+    unsigned seg_cap = (unsigned)std::min<size_t>(c->segs.bytes/sizeof(SegInfo), 0xffffffffu);
+    unsigned span_cap = (unsigned)std::min<size_t>(c->spans.bytes/(c->span_words*sizeof(uint32_t)), 0xffffffffu);
+    if(c->object_mode)
+    {
+        // one slot index addresses a span AND its one-row segment: both arrays get the same geometry
+        seg_cap = span_cap = std::min(seg_cap, span_cap)/kSubAllocators*kSubAllocators;
+    }
     SetupOutputs so;
     so.recs = nullptr;
     so.spans = (uint32_t *)c->spans.ptr;
@@ -184,6 +196,29 @@ static int issue_frame(b200r_context *c)
     so.zrange = reinterpret_cast<const float *>(words->zkeys);
     so.counters = words->counters;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[0], c->stream));
+    if(c->object_mode)
+    {
+        // slots are striped over the regions (object_walk_kernel.cu), so the fills are known up front
+        unsigned fills[kSubAllocators];
+        for(int r = 0; r < kSubAllocators; ++r)
+            fills[r] = c->obj_total_slots/kSubAllocators + ((unsigned)r < c->obj_total_slots%kSubAllocators ? 1u : 0u);
+        CU(cudaMemcpyAsync(words->seg_fill, fills, sizeof(fills), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(words->span_fill, fills, sizeof(fills), cudaMemcpyHostToDevice, c->stream));
+        // the walk mutates its edge records like DrawModel does: every (re-)issue starts from the pristine copy
+        if(c->edges_bytes)
+            CU(cudaMemcpyAsync(c->edges_work.ptr, c->edges_pristine.ptr, c->edges_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        ObjectWalkParams op;
+        op.edges = c->edges_work.ptr;
+        op.objects = (const ObjectDesc *)c->obj_dev.ptr; op.nobjects = (unsigned)c->obj_host.size();
+        op.spans = so.spans; op.span_words = c->span_words; op.segs = so.segs;
+        op.extra_total = &words->extra_total;
+        op.seg_capacity = seg_cap; op.span_capacity = span_cap; op.region_size = seg_cap/kSubAllocators;
+        op.tile_count = tile_count; op.counters = words->counters; op.stopped = &words->stopped;
+        launch_object_walk(v, op, c->stream);
+        c->stats.KernelLaunches += 1;
+    }
+    else
+    {
     if(c->host_path) CU(cudaStreamWaitEvent(c->stream, c->pos_ready, 0));
     for(const MeshParams &m : c->meshes)
     {
@@ -198,6 +233,7 @@ static int issue_frame(b200r_context *c)
         if(c->host_path && i < c->chunk_ready.size()) CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
         launch_setup(v, m, so, c->stream);
         if(m.ntri) c->stats.KernelLaunches += 1;
+    }
     }
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[1], c->stream));
     launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, tile_offset + nbins + 1, c->stream);
@@ -222,7 +258,7 @@ static int issue_frame(b200r_context *c)
     sp.tiles_x = v.tiles_x;
     sp.tile_offset = tile_offset; sp.tile_fill = tile_fill; sp.pair_list = (unsigned *)c->pairs.ptr;
     launch_scatter(sp, c->stream);
-    if(c->total_tris) c->stats.KernelLaunches += 1;
+    if(c->total_tris || c->object_mode) c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[3], c->stream));
 
     RasterParams rp;
@@ -281,6 +317,7 @@ static int settle_pending(b200r_context *c)
         c->stats.Segments = nseg;
         c->stats.Spans = nspan;
         c->stats.AliasPixels = hw.extra_total;
+        c->stats.StoppedObjects = hw.stopped;
         c->pending = false;
         if(hw.overflow)
         {
@@ -398,7 +435,8 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
                         const game_render_commands *cmd, const b200r_device_target *target, u32 flags)
 {
     if(!c) return B200R_E_INVALID;
-    if(flags & B200R_WHOLE_OBJECT_AEL) return fail(c, B200R_E_UNSUPPORTED, "whole-object AEL pairing is not implemented");
+    if(flags & B200R_WHOLE_OBJECT_AEL)
+        return fail(c, B200R_E_UNSUPPORTED, "whole-object mode needs the host-pointer call (b200r_render_objects)");
     if(mesh_count && !meshes) return fail(c, B200R_E_INVALID, "null Meshes");
     CU(cudaSetDevice(c->device));
     int rc = settle_pending(c);                 // the previous frame must be complete in the stream
@@ -636,6 +674,9 @@ static int upload_objects(b200r_context *c, const render_entry_3d_object *objs, 
     return B200R_OK;
 }
 
+static int render_objects_whole(b200r_context *c, const render_entry_3d_object *objs, u32 n,
+                                const game_render_commands *cmd, const loaded_bitmap *out);
+
 int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u32 n,
                          const game_render_commands *cmd, const loaded_bitmap *out, u32 flags)
 {
@@ -643,10 +684,10 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     if(!cmd || !out || !out->Memory || !cmd->ZBuffer || (n && !objs)) return fail(c, B200R_E_INVALID, "null argument");
     if(out->Width <= 0 || out->Height <= 0 || out->Pitch < out->Width*4 || cmd->Width < (u32)out->Width)
         return fail(c, B200R_E_INVALID, "bad OutputTarget / Commands->Width");
-    if(flags & B200R_WHOLE_OBJECT_AEL) return fail(c, B200R_E_UNSUPPORTED, "whole-object AEL pairing is not implemented");
     CU(cudaSetDevice(c->device));
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
+    if(flags & B200R_WHOLE_OBJECT_AEL) return render_objects_whole(c, objs, n, cmd, out);
 
     std::vector<b200r_device_mesh> meshes;
     rc = upload_objects(c, objs, n, meshes);
@@ -710,12 +751,11 @@ static uint32_t merge_tie_key(uint32_t i, uint32_t n)
     return key << (32 - depth);
 }
 
-int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
-                          const game_render_commands *cmd, b32 phong)
+// FillEdgeTable of one object (projekt.cpp:3882) into outp (room for VertexCount records), in the
+// reference's MergeSort order.  Returns the edge count or a negative status.
+static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
+                            const game_render_commands *cmd, b32 phong, edge_info *outp)
 {
-    if(!c) return B200R_E_INVALID;
-    if(!obj || !cmd) return fail(c, B200R_E_INVALID, "null argument");
-    if(!obj->EdgeMemory) return fail(c, B200R_E_INVALID, "null EdgeMemory");
     const bool textured = obj->Bitmap != nullptr;
     if(textured && obj->VertexCount >= 3 && !obj->UVData) return fail(c, B200R_E_INVALID, "textured object without UVData");
     CU(cudaSetDevice(c->device));
@@ -803,7 +843,6 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
         order[i].key = ((uint64_t)(ymin ^ 0x80000000u) << 32) | merge_tie_key(i, n);
     }
     std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.key < b.key; });
-    edge_info *outp = (edge_info *)obj->EdgeMemory;
     for(uint32_t i = 0; i < n; ++i)
     {
         const uint32_t *E = order[i].edge;
@@ -845,6 +884,135 @@ int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
         }
     }
     return (int)n;
+}
+
+int b200r_fill_edge_table(b200r_context *c, const render_entry_3d_object *obj,
+                          const game_render_commands *cmd, b32 phong)
+{
+    if(!c) return B200R_E_INVALID;
+    if(!obj || !cmd) return fail(c, B200R_E_INVALID, "null argument");
+    if(!obj->EdgeMemory) return fail(c, B200R_E_INVALID, "null EdgeMemory");
+    return build_edge_table(c, obj, cmd, phong, (edge_info *)obj->EdgeMemory);
+}
+
+// ---------------------------------------------------------------------------- whole-object mode
+// b200r_render_objects with B200R_WHOLE_OBJECT_AEL: per object, the sorted edge_info array (the
+// same records b200r_fill_edge_table returns) goes to the device and ONE thread replays DrawModel's
+// active-edge list on it (object_walk_kernel.cu); binning and raster are the usual kernels.
+static int render_objects_whole(b200r_context *c, const render_entry_3d_object *objs, u32 n,
+                                const game_render_commands *cmd, const loaded_bitmap *out)
+{
+    const int W = out->Width, H = out->Height;
+    std::vector<edge_info> all;
+    std::vector<ObjectDesc> descs;
+    std::vector<TexDesc> texs;
+    std::vector<edge_info> scratch;
+    uint64_t slots = 0;
+    bool general = false;
+    size_t ntex = 0;
+    for(u32 i = 0; i < n; ++i)
+    {
+        const render_entry_3d_object &o = objs[i];
+        if(o.VertexCount < 3) continue;
+        scratch.assign(o.VertexCount, edge_info());
+        const int ne = build_edge_table(c, &o, cmd, o.PhongShading, scratch.data());
+        if(ne < 0) return ne;
+        ObjectDesc d;
+        d.first_edge = (unsigned)all.size(); d.edge_count = (unsigned)ne;
+        d.phong = o.PhongShading ? 1 : 0; d.tex = -1;
+        // every pair consumes one row of two active edges: half the edge rows bound the spans
+        uint64_t edge_rows = 0;
+        for(int e = 0; e < ne; ++e)
+        {
+            scratch[e].Next = (edge_info *)(intptr_t)-1;           // an index on the device, -1 = null
+            const int64_t y0 = std::max<int64_t>(scratch[e].YMin, 0), y1 = std::min<int64_t>(scratch[e].YMax, H);
+            if(y1 > y0) edge_rows += (uint64_t)(y1 - y0);
+        }
+        const uint64_t bound = edge_rows/2 + 1;
+        if(slots + bound > 0x7fffffffull) return fail(c, B200R_E_UNSUPPORTED, "more than 2^31-1 spans per call");
+        d.span_base = d.prim_base = (unsigned)slots; d.span_bound = (unsigned)bound;
+        slots += bound;
+        if(o.Bitmap)
+        {
+            const loaded_bitmap *b = o.Bitmap;
+            size_t k = 0;
+            for(; k < ntex; ++k) if(c->host_textures[k].host == b) break;
+            if(k == ntex)
+            {
+                if(c->host_textures.size() <= ntex) c->host_textures.emplace_back();
+                b200r_context::HostTexture &ht = c->host_textures[ntex];
+                CU(ht.pixels.reserve((size_t)b->Width*b->Height*4));
+                ht.host = b;
+                CU(cudaMemcpy2DAsync(ht.pixels.ptr, (size_t)b->Width*4, b->Memory, (size_t)b->Pitch, (size_t)b->Width*4,
+                                     b->Height, cudaMemcpyHostToDevice, c->stream));
+                TexDesc td; td.mem = (const uint32_t *)ht.pixels.ptr; td.w = b->Width; td.h = b->Height; td.pitch = b->Width*4;
+                texs.push_back(td);
+                ++ntex;
+            }
+            d.tex = (int)k;
+        }
+        general |= d.phong != 0 || d.tex >= 0;
+        all.insert(all.end(), scratch.begin(), scratch.begin() + ne);
+        descs.push_back(d);
+    }
+
+    // targets (as in the per-triangle call): device mirrors with rows padded to 64 pixels
+    const int wpad = (W + 63) & ~63;
+    CU(c->d_color.reserve((size_t)wpad*H*4));
+    CU(c->d_depth.reserve((size_t)wpad*H*4));
+    CU(cudaMemcpy2DAsync(c->d_color.ptr, (size_t)wpad*4, out->Memory, (size_t)out->Pitch, (size_t)W*4, H,
+                         cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->d_depth.ptr, (size_t)wpad*4, cmd->ZBuffer, (size_t)cmd->Width*4, (size_t)W*4, H,
+                         cudaMemcpyHostToDevice, c->stream));
+    b200r_device_target t;
+    t.Color = (u32 *)c->d_color.ptr; t.Depth = (r32 *)c->d_depth.ptr;
+    t.Width = W; t.Height = H; t.ColorPitch = wpad*4; t.DepthStride = wpad;
+    t.BandFirstRow = 0; t.BandRows = H;
+    ViewParams v;
+    int rc = fill_view(c, cmd, &t, v, true);            // light-count rules were applied per object above
+    if(rc != B200R_OK) return rc;
+
+    if(!descs.empty())
+    {
+        c->edges_bytes = all.size()*sizeof(edge_info);
+        CU(c->edges_pristine.reserve(std::max<size_t>(c->edges_bytes, 16)));
+        CU(c->edges_work.reserve(std::max<size_t>(c->edges_bytes, 16)));
+        CU(c->obj_dev.reserve(descs.size()*sizeof(ObjectDesc)));
+        if(c->edges_bytes) CU(cudaMemcpyAsync(c->edges_pristine.ptr, all.data(), c->edges_bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->obj_dev.ptr, descs.data(), descs.size()*sizeof(ObjectDesc), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));           // `all` and `descs` are stack vectors
+    }
+    const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
+    c->span_words = general ? kSpanWordsPhong : kSpanWords;
+    // exact needs are known: the promised slots, striped over the regions, plus room for alias pixels
+    const size_t region = (size_t)(slots/kSubAllocators) + 2 + 1024;
+    CU(c->segs.reserve(region*kSubAllocators*sizeof(SegInfo)));
+    CU(c->spans.reserve(region*kSubAllocators*c->span_words*sizeof(uint32_t)));
+    CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1 + 2*((size_t)ntiles*kDepthBuckets/8192 + 2))*sizeof(unsigned)));
+    if(c->pairs.bytes == 0) CU(c->pairs.reserve((size_t)std::max<uint64_t>(slots*2, 1u << 16)*sizeof(unsigned)));
+
+    c->view = v;
+    c->meshes.clear();
+    c->tex_host.swap(texs);
+    c->target = t;
+    c->total_tris = 0;
+    c->ntiles = ntiles;
+    c->obj_host.swap(descs);
+    c->obj_total_slots = (unsigned)slots;
+    c->stats.Triangles = 0;
+    for(u32 i = 0; i < n; ++i) c->stats.Triangles += objs[i].VertexCount/3;
+    c->stats.Tiles = ntiles;
+    c->object_mode = true;
+    rc = issue_frame(c);
+    if(rc == B200R_OK) rc = settle_pending(c);
+    c->object_mode = false;
+    if(rc != B200R_OK) { cudaStreamSynchronize(c->stream); return rc; }
+    CU(cudaMemcpy2DAsync(out->Memory, (size_t)out->Pitch, c->d_color.ptr, (size_t)wpad*4, (size_t)W*4, H,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(cmd->ZBuffer, (size_t)cmd->Width*4, c->d_depth.ptr, (size_t)wpad*4, (size_t)W*4, H,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200R_OK;
 }
 
 } // extern "C"

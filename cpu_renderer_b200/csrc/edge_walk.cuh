@@ -145,4 +145,18 @@ __device__ __forceinline__ void active_list_event(int y, const uint32_t *rec, in
     next_ev = ev;
 }
 
+// Upper bound of every depth value of a span: z_k = fl(z_{k-1} + zi), k <= n.  Each add rounds by
+// at most half an ulp of a value no larger than |z0| + n|zi| (plus the bound itself), so
+//   z_k <= max(z0, z0 + n*zi) + n * 2^-23 * (|z0| + n*|zi|)        (2x the worst case),
+// evaluated with every operation rounded towards +inf.  NaN / Inf input gives +inf or NaN: the
+// raster kernel culls only on a strict, ordered "bound < row minimum", so such spans are kept.
+__device__ __forceinline__ float span_depth_bound(float z0, float zi, int n)
+{
+    const float fn = (float)max(n, 0);
+    const float end = __fadd_ru(z0, __fmul_ru(fn, zi));
+    const float mag = __fadd_ru(fabsf(z0), __fmul_ru(fn, fabsf(zi)));
+    const float slack = __fmul_ru(__fmul_ru(fn, 1.1920929e-7f), mag);
+    return __fadd_ru(__fadd_ru(fmaxf(z0, end), slack), 1.0e-30f);    // absolute term: subnormal rounding
+}
+
 } // namespace b200r

@@ -232,6 +232,31 @@ struct SetupOutputs
 };
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
+
+// ---- whole-object mode (object_walk_kernel.cu) ----
+struct ObjectDesc
+{
+    unsigned first_edge, edge_count;    // the object's sorted edge_info records
+    unsigned span_base, span_bound;     // its promised span / segment slots (frame-wide draw-order index of the first one)
+    unsigned prim_base;                 // owner of its first span
+    int phong;                          // render_entry_3d_object::PhongShading
+    int tex;                            // texture table index, -1: untextured
+};
+struct ObjectWalkParams
+{
+    void *edges;                        // device copy of the edge_info arrays, mutated by the walk
+    const ObjectDesc *objects;
+    unsigned nobjects;
+    uint32_t *spans; int span_words;
+    SegInfo *segs;
+    unsigned *extra_total;
+    unsigned seg_capacity, span_capacity;   // equal in this mode: one slot index addresses both arrays
+    unsigned region_size;               // capacity / kSubAllocators
+    unsigned *tile_count;
+    unsigned long long *counters;
+    unsigned *stopped;                  // objects that stopped where the reference dereferences null
+};
+void launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s);
 // zrange[0..1] start as {-inf as ordered key, +inf as ordered key}; zrange_finish turns them into
 // {zmax, 1/(zmax - zmin)}
 void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s);

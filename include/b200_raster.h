@@ -127,8 +127,13 @@ typedef struct edge_info                   /* projekt.h:17-37, 120 bytes */
 #define B200R_MAX_LIGHTS 8
 
 /* flags of the render calls */
-#define B200R_WHOLE_OBJECT_AEL 1u  /* reserved: reproduce the whole-object active-edge pairing of
-                                      projekt.cpp:198-303; -> UNSUPPORTED   */
+#define B200R_WHOLE_OBJECT_AEL 1u  /* b200r_render_objects: reproduce DrawModel's whole-object active-edge list
+                                      (projekt.cpp:198-303, 542-597) link by link: consecutive entries are
+                                      paired whatever triangle they belong to, as in the reference's own
+                                      images of multi-triangle objects.  A compatibility mode: objects run in
+                                      parallel, the rows of one object do not.  Where the reference dereferences
+                                      a null list pointer the object stops drawing (b200r_frame_stats::
+                                      StoppedObjects).  b200r_render_device: B200R_E_UNSUPPORTED.          */
 
 typedef struct b200r_context b200r_context;
 
@@ -228,6 +233,8 @@ typedef struct b200r_frame_stats
     uint64_t Tiles;            /* screen tiles of the band                                      */
     uint64_t KernelLaunches;   /* kernels launched by this context since creation               */
     uint64_t Reruns;           /* frames re-issued because the pair list had to grow            */
+    uint64_t StoppedObjects;   /* B200R_WHOLE_OBJECT_AEL: objects that stopped drawing where the
+                                  reference dereferences a null list pointer (it crashes there)  */
 } b200r_frame_stats;
 
 /* Valid after b200r_sync (or any blocking call). */

@@ -219,8 +219,11 @@ def test_unsupported_and_invalid_inputs_return_codes(renderer):
         renderer.render_scene_host(s, color, z)
     assert e.value.code == api.E_UNSUPPORTED
     s.lights = [sc.Light()]
+    # whole-object mode exists on the host-pointer call only; the device-resident call refuses the flag
     with pytest.raises(api.B200RasterError) as e:
-        renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL)
+        cmd, keep = api.make_commands(s)
+        renderer.render_device([api.device_mesh()], cmd, api.device_target(1, 1, 64, 64, 256, 64, 0, 64),
+                               flags=api.WHOLE_OBJECT_AEL)
     assert e.value.code == api.E_UNSUPPORTED
     # textured object without UVData, or with a malformed Bitmap -> invalid, not silently untextured
     lib = renderer.lib
@@ -423,6 +426,73 @@ def test_out_of_range_uvs_are_clamped_like_the_oracle(renderer):
         want = ol.oracle_render(sb)
         assert want["stats"]["TexelClamps"] > 0
         check_tex(renderer, sb, want["color"], want["z"], False)
+
+
+# ---- whole-object mode: DrawModel's list over all edges of an object ----------
+import level0_cases  # noqa: E402
+
+LEVEL0 = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_level0.npz"))
+LEVEL0_CASES = level0_cases.cases()
+
+
+@pytest.mark.parametrize("name", sorted(LEVEL0_CASES))
+def test_whole_object_mode_against_verbatim_golden(renderer, name):
+    """The object as ONE render_entry_3d_object with B200R_WHOLE_OBJECT_AEL against the verbatim
+    FillEdgeTable + DrawModel image -- including the inputs on which the verbatim build crashes (the
+    image then holds what it had drawn until the null dereference; the GPU stops at the same pair)."""
+    s, phong = LEVEL0_CASES[name]
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL, phong=phong)
+    assert ol.fnv1a64_words(z) == str(LEVEL0[f"{name}_z_hash"])
+    ref_crashed = int(LEVEL0[f"{name}_status"]) < 0
+    assert renderer.stats()["StoppedObjects"] == (1 if ref_crashed else 0)
+    if not phong:
+        assert ol.fnv1a64_words(color) == str(LEVEL0[f"{name}_color_hash"])
+    else:
+        want = ol.oracle_render_object(s, phong=True)
+        ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+        assert int(ch.max()) <= PHONG_TOLERANCE_LSB
+
+
+def test_whole_object_mode_differs_from_per_triangle_mode_like_the_reference(renderer):
+    """C1 at 1080p: level 0 vs level 1 differ on exactly the pixels SURVEY.md probe P4 counted."""
+    s = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], 1920, 1080, 500.0)
+    c0, z0, _ = ol.new_targets(s)
+    c1, z1, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, c0, z0, flags=api.WHOLE_OBJECT_AEL)
+    renderer.render_scene_host(s, c1, z1)
+    assert ol.fnv1a64_words(z0) == str(GOLD["c1_1080p_level0_z_hash"])
+    assert ol.fnv1a64_words(c0) == str(GOLD["c1_1080p_level0_color_hash"])
+    assert int((z0.view(np.uint32) != z1.view(np.uint32)).sum()) == int(GOLD["c1_1080p_level01_z_diff"])
+    assert int((c0 != c1).sum()) == int(GOLD["c1_1080p_level01_color_diff"])
+
+
+def test_whole_object_mode_several_objects_one_call(renderer):
+    """Three spheres (one textured, one Phong) as three objects of one call: the oracle draws them in
+    the same order into the same targets; owners keep the submission order across objects."""
+    base = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], 960, 540, 200.0)
+    nv = base.positions.shape[0]
+    offs = [(-0.9, -0.2, 0.0), (0.2, 0.1, 0.4), (0.9, 0.3, -0.3)]
+    pos = np.concatenate([base.positions + np.float32(o) for o in offs]).astype(np.float32)
+    s = replace(base, positions=pos, colors=np.tile(base.colors, (3, 1)), normals=np.tile(base.normals, (3, 1)),
+                uvs=np.tile(base.uvs, (3, 1)), texture=sc.make_texture(64, 48))
+    shading = [(False, False), (False, True), (True, False)]        # (phong, textured)
+    color_w, z_w, _ = ol.new_targets(s)
+    for k, (ph, tx) in enumerate(shading):
+        part = replace(s, positions=s.positions[k * nv:(k + 1) * nv], colors=s.colors[k * nv:(k + 1) * nv],
+                       normals=s.normals[k * nv:(k + 1) * nv], uvs=s.uvs[k * nv:(k + 1) * nv],
+                       texture=s.texture if tx else None)
+        ol.oracle_render_object(part, phong=ph, targets=(color_w, z_w, None))
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, splits=[nv, nv, nv], flags=api.WHOLE_OBJECT_AEL,
+                               phong=[p for p, _ in shading], textured=[t for _, t in shading])
+    assert np.array_equal(z.view(np.uint32), z_w.view(np.uint32))
+    ch = np.abs(color_w.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= PHONG_TOLERANCE_LSB
+    assert renderer.stats()["StoppedObjects"] == 0
 
 
 # ---- BASELINE.json sizes -------------------------------------------------------------------------
