@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRICS = {
+    "c1": ("Mpixels/s", "C1: the reference's demo, ConstructSphere (2 208 triangles) as one object, 1920x1080"),
     "c2": ("Mtriangles/s", "C2: 1M ~10px triangles, 1920x1080, depth-tested Gouraud (setup/binning bound)"),
     "c3": ("Mpixels/s", "C3: 50k large overlapping triangles, 3840x2160, ~35x overdraw (fill bound)"),
     "c4": ("Mpixels/s", "C4: 20M triangles, 16384x16384, screen-space tile bands across the GPUs, NCCL gather"),
@@ -41,7 +42,7 @@ METRICS = {
 }
 # c2/c3: every rank renders its own frame (weak).  c4: one frame split in row bands, c5: a fixed
 # set of 256 views split over the ranks (strong: the total work does not grow with N).
-SCALING = {"c2": "weak", "c3": "weak", "c4": "strong", "c5": "strong"}
+SCALING = {"c1": "weak", "c2": "weak", "c3": "weak", "c4": "strong", "c5": "strong"}
 C5_VIEWS = 256
 TEX_SIZE = 1024                # --textured: the objects' Bitmap is TEX_SIZE x TEX_SIZE ARGB8
 
@@ -126,6 +127,10 @@ def build_scene(config, rank, scale=1.0):
         step = max(4, int(round(708 * scale ** 0.5)))
         pos, col, nrm, uvs = sc.construct_sphere(step)
         return sc.sphere_scene(pos, col, nrm, uvs, 1920, 1080, 500.0, name="c5")
+    if config == "c1":
+        # the verbatim ConstructSphere mesh (projekt.cpp:4123), committed with the golden vectors
+        m = np.load(os.path.join(ROOT, "tests", "golden", "sphere_mesh.npz"))
+        return sc.sphere_scene(m["pos"], m["col"], m["nrm"], m["uvs"], 1920, 1080, 500.0, name="c1")
     cfg = dict(sc.CONFIGS[config])
     cfg["count"] = max(1, int(round(cfg["count"] * scale)))
     if config in ("c2", "c3"):
@@ -178,7 +183,7 @@ def run_reference(args):
 def cpu_sample(config, scene, sc, sample=0, threads=0):
     """Bounded CPU sample of a config: a prefix of the frame's triangle list (for c5: of view 0)."""
     import copy
-    default = {"c2": 250_000, "c3": 4000, "c4": 250_000, "c5": 250_000}[config]
+    default = {"c1": 1 << 20, "c2": 250_000, "c3": 4000, "c4": 250_000, "c5": 250_000}[config]
     sample = min(scene.triangle_count, sample or default)
     if config == "c5":
         # a mesh is ordered: take every k-th triangle so the sample covers the whole sphere
@@ -423,6 +428,7 @@ def run_ours(args):
         with_gather = {"ms_per_step": float(g.item()), "what": "NCCL gather of the finished colour image(s) to rank 0 after every step",
                        "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1))}
 
+    whole_object = None
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region ---------
     pin = lambda a: torch.from_numpy(a).pin_memory()              # noqa: E731
     from cpu_renderer_b200 import scene as sc
@@ -447,6 +453,33 @@ def run_ours(args):
         e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
         covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
         e2e_api = "b200r_render_objects (host pointers, pinned)"
+        if cfgname == "c1" and rank == 0:
+            # the same frame as ONE object through the whole-object mode, beside the
+            # verbatim reference's own call pair on one host core (it is a single-threaded path)
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol
+            wo_c = [c.copy() for c in hcol[:3]]
+            wo_z = [z_.copy() for z_ in hz[:3]]
+            for c_, z_ in zip(wo_c, wo_z):
+                c_.fill(scene.clear_color); z_.fill(scene.clear_depth)
+            r.render_scene_host(hs, wo_c[2], wo_z[2], flags=api.WHOLE_OBJECT_AEL, phong=args.phong)   # warm-up
+            t0 = time.perf_counter()
+            for i in range(2):
+                r.render_scene_host(hs, wo_c[i], wo_z[i], flags=api.WHOLE_OBJECT_AEL, phong=args.phong)
+            wo_ms = (time.perf_counter() - t0) / 2 * 1e3
+            whole_object = {"e2e_ms": wo_ms, "api": "b200r_render_objects + B200R_WHOLE_OBJECT_AEL",
+                            "stopped_objects": r.stats()["StoppedObjects"]}
+            if ol.ref_available():
+                ref_t = []
+                for i in range(3):
+                    t0 = time.perf_counter()
+                    ref = ol.ref_render_object(scene, phong=args.phong)
+                    ref_t.append((time.perf_counter() - t0) * 1e3)
+                whole_object["cpu_reference_ms"] = min(ref_t)
+                whole_object["cpu_reference"] = "verbatim FillEdgeTable + DrawModel on the whole object, 1 thread, incl. clearing the targets"
+                whole_object["depth_identical_to_reference"] = bool(np.array_equal(ref["z"].view(np.uint32), wo_z[0].view(np.uint32)))
+                whole_object["colour_max_lsb_vs_reference"] = int(np.abs(ref["color"].view(np.uint8).astype(np.int16) -
+                                                                         wo_c[0].view(np.uint8).astype(np.int16)).max())
         # a textured object's vertex colours are not uploaded (they never reach the image); its UVs and Bitmap are
         h2d_bytes = int(ntri * (96 if args.textured else 120) + 2 * W * H * 4 + (scene.texture.nbytes if args.textured else 0))
         d2h_bytes = int(2 * W * H * 4)
@@ -529,6 +562,7 @@ def run_ours(args):
                                "one pre-cleared colour/depth pair per timed frame (clear outside the timed region)")},
         "frame_ms": ms / nframes,
         "gpu_launches": int(launches),
+        **({"whole_object": whole_object} if whole_object else {}),
         "stage_ms": stage_ms,
         "binner": {"binned_triangles": stats["Binned"], "segments": stats["Segments"], "spans": stats["Spans"],
                    "queue_entries": stats["TilePairs"], "tiles": stats["Tiles"], "reruns": stats["Reruns"]},

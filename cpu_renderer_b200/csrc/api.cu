@@ -76,6 +76,7 @@ struct b200r_context
     DeviceBuffer obj_dev, edges_pristine, edges_work;
     size_t edges_bytes = 0;
     unsigned obj_total_slots = 0;       // sum of the objects' span bounds
+    unsigned obj_smem_bytes = 0;        // walk state of the largest object that fits into shared memory
     // textures of the last issued frame: distinct b200r_device_texture descriptors, uploaded as a table
     std::vector<TexDesc> tex_host;
     DeviceBuffer tex_dev;
@@ -204,11 +205,12 @@ static int issue_frame(b200r_context *c)
             fills[r] = c->obj_total_slots/kSubAllocators + ((unsigned)r < c->obj_total_slots%kSubAllocators ? 1u : 0u);
         CU(cudaMemcpyAsync(words->seg_fill, fills, sizeof(fills), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(words->span_fill, fills, sizeof(fills), cudaMemcpyHostToDevice, c->stream));
-        // the walk mutates its edge records like DrawModel does: every (re-)issue starts from the pristine copy
-        if(c->edges_bytes)
-            CU(cudaMemcpyAsync(c->edges_work.ptr, c->edges_pristine.ptr, c->edges_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        // the walk keeps what DrawModel mutates (running values, Next) beside the edge records, in shared
+        // memory when the object fits and in edges_work otherwise: a re-issue starts from the same records
         ObjectWalkParams op;
-        op.edges = c->edges_work.ptr;
+        op.edges = c->edges_pristine.ptr;
+        op.state_scratch = (float *)c->edges_work.ptr;
+        op.state_smem_bytes = c->obj_smem_bytes;
         op.objects = (const ObjectDesc *)c->obj_dev.ptr; op.nobjects = (unsigned)c->obj_host.size();
         op.spans = so.spans; op.span_words = c->span_words; op.segs = so.segs;
         op.extra_total = &words->extra_total;
@@ -976,7 +978,7 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
     {
         c->edges_bytes = all.size()*sizeof(edge_info);
         CU(c->edges_pristine.reserve(std::max<size_t>(c->edges_bytes, 16)));
-        CU(c->edges_work.reserve(std::max<size_t>(c->edges_bytes, 16)));
+        CU(c->edges_work.reserve(std::max<size_t>(all.size()*10*sizeof(float), 16)));     // WalkState scratch
         CU(c->obj_dev.reserve(descs.size()*sizeof(ObjectDesc)));
         if(c->edges_bytes) CU(cudaMemcpyAsync(c->edges_pristine.ptr, all.data(), c->edges_bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->obj_dev.ptr, descs.data(), descs.size()*sizeof(ObjectDesc), cudaMemcpyHostToDevice, c->stream));
@@ -999,6 +1001,12 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
     c->ntiles = ntiles;
     c->obj_host.swap(descs);
     c->obj_total_slots = (unsigned)slots;
+    c->obj_smem_bytes = 0;
+    for(const ObjectDesc &d : c->obj_host)
+    {
+        const size_t need = (size_t)d.edge_count*(d.phong ? 10 : 7)*sizeof(float);
+        if(need <= 200u*1024u) c->obj_smem_bytes = std::max<unsigned>(c->obj_smem_bytes, (unsigned)need);
+    }
     c->stats.Triangles = 0;
     for(u32 i = 0; i < n; ++i) c->stats.Triangles += objs[i].VertexCount/3;
     c->stats.Tiles = ntiles;

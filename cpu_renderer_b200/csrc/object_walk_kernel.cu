@@ -5,9 +5,9 @@
 // :584-592) and its exchanges (:562-583) relink nodes without updating ListHead / ListTail; the
 // images it produces for multi-triangle objects depend on both (0.1-1.2 % of the demo sphere's
 // pixels differ from per-triangle semantics).  Reproducing them needs the list itself, and the list
-// is order dependent from the first row to the last: ONE thread walks one object, on a device copy
-// of the object's sorted edge_info array (projekt.h:17-37) that it mutates in place exactly as
-// DrawModel does, with edge_info::Next holding an index (-1 = null).  For every pair it performs the
+// is order dependent from the first row to the last: ONE thread walks one object, on the object's
+// sorted edge_info array (projekt.h:17-37); the fields DrawModel mutates in place (running values
+// and Next, an index here with -1 = null) are kept in a structure of arrays beside it.  For every pair it performs the
 // span set-up (:306-412) and emits a span record plus a one-row segment whose owner is the span's
 // DRAW ORDER (the depth rule's tie-break: within an object, first drawn wins).  Pixels are filled by
 // the same binning and raster kernels as the per-triangle path.
@@ -38,62 +38,79 @@ __device__ __forceinline__ unsigned striped_slot(unsigned g, unsigned region_siz
     return (g % kSubAllocators)*region_size + g/kSubAllocators;
 }
 
+// Mutable per-edge state of the walk, structure of arrays: what DrawModel keeps updating inside the
+// edge records (XMin, ZMin, MinColor or -- textured -- u/z v/z 1/z, MinNormal, Next).  It lives in
+// shared memory when the object fits (28 / 40 bytes per edge), else in a global scratch area with
+// the same layout; everything DrawModel only reads (YMin, YMax, Left, the gradients) stays in the
+// edge_info array behind the read-only cache.  (First version: all of it in global memory, every
+// value re-read from L2 one row after it was written -- 3x slower.)
+struct WalkState
+{
+    float *x, *z, *c;           // c: 4 per edge
+    float *n;                   // 3 per edge, Phong only
+    int *next;
+};
+
 struct Walker
 {
     const ViewParams &v;
     const ObjectWalkParams &p;
     const ObjectDesc &o;
-    DevEdge *E;
+    const DevEdge *E;           // read-only fields
+    WalkState s;
     unsigned produced;          // spans emitted so far (draw order)
     unsigned pairs;             // tile pairs
     float wf, wf_m1;
 
     __device__ bool before(int a, int b) const      // projekt.cpp:212-216 / 229-233
     {
-        const DevEdge &A = E[a], &B = E[b];
-        return A.XMin < B.XMin || (A.XMin == B.XMin && (A.Gradient < B.Gradient || (A.Gradient == B.Gradient && A.Left < B.Left)));
+        const float ax = s.x[a], bx = s.x[b];
+        if(ax < bx) return true;
+        if(ax != bx) return false;
+        const float ag = __ldg(&E[a].Gradient), bg = __ldg(&E[b].Gradient);
+        return ag < bg || (ag == bg && __ldg(&E[a].Left) < __ldg(&E[b].Left));
     }
 
-    // span set-up of the pair (L, R) at row y, projekt.cpp:306-412, and its records
-    __device__ void emit(const DevEdge &L, const DevEdge &R, int y)
+    // span set-up of the pair (l, r) at row y, projekt.cpp:306-412, and its records
+    __device__ void emit(int l, int r, int y)
     {
         const bool tex = o.tex >= 0, phong = o.phong != 0;
         // textured objects interpolate u/z, v/z, 1/z in the colour words (MeshParams::uv)
-        const float Lc0 = tex ? L.UMin : L.MinColor[0], Lc1 = tex ? L.VMin : L.MinColor[1];
-        const float Lc2 = tex ? L.OneOverZMin : L.MinColor[2], Lc3 = tex ? 0.0f : L.MinColor[3];
-        const float Rc0 = tex ? R.UMin : R.MinColor[0], Rc1 = tex ? R.VMin : R.MinColor[1];
-        const float Rc2 = tex ? R.OneOverZMin : R.MinColor[2], Rc3 = tex ? 0.0f : R.MinColor[3];
-        const float xdiff = roundf(fsub(R.XMin, L.XMin));                     // :311-312
+        const float Lx = s.x[l], Rx = s.x[r], Lz = s.z[l], Rz = s.z[r];
+        const float Lc0 = s.c[4*l], Lc1 = s.c[4*l + 1], Lc2 = s.c[4*l + 2], Lc3 = s.c[4*l + 3];
+        const float Rc0 = s.c[4*r], Rc1 = s.c[4*r + 1], Rc2 = s.c[4*r + 2], Rc3 = s.c[4*r + 3];
+        float Ln0 = 0.0f, Ln1 = 0.0f, Ln2 = 0.0f, Rn0 = 0.0f, Rn1 = 0.0f, Rn2 = 0.0f;
+        if(phong)
+        {
+            Ln0 = s.n[3*l]; Ln1 = s.n[3*l + 1]; Ln2 = s.n[3*l + 2];
+            Rn0 = s.n[3*r]; Rn1 = s.n[3*r + 1]; Rn2 = s.n[3*r + 2];
+        }
+        const float xdiff = roundf(fsub(Rx, Lx));                             // :311-312
         float zi = 0.0f, i0 = 0.0f, i1 = 0.0f, i2 = 0.0f, i3 = 0.0f, ni0 = 0.0f, ni1 = 0.0f, ni2 = 0.0f;
         if(xdiff != 0.0f)                                                     // :333-363
         {
             i0 = fdiv_zn(fsub(Rc0, Lc0), xdiff); i1 = fdiv_zn(fsub(Rc1, Lc1), xdiff);
             i2 = fdiv_zn(fsub(Rc2, Lc2), xdiff); i3 = fdiv_zn(fsub(Rc3, Lc3), xdiff);
-            zi = fdiv_zn(fsub(R.ZMin, L.ZMin), xdiff);
+            zi = fdiv_zn(fsub(Rz, Lz), xdiff);
             if(phong)
             {
-                ni0 = fdiv_zn(fsub(R.MinNormal[0], L.MinNormal[0]), xdiff);
-                ni1 = fdiv_zn(fsub(R.MinNormal[1], L.MinNormal[1]), xdiff);
-                ni2 = fdiv_zn(fsub(R.MinNormal[2], L.MinNormal[2]), xdiff);
+                ni0 = fdiv_zn(fsub(Rn0, Ln0), xdiff); ni1 = fdiv_zn(fsub(Rn1, Ln1), xdiff);
+                ni2 = fdiv_zn(fsub(Rn2, Ln2), xdiff);
             }
         }
-        float xoff = 0.0f, leftx = L.XMin;                                    // :381-390
+        float xoff = 0.0f, leftx = Lx;                                        // :381-390
         if(leftx < 0.0f) { xoff = -leftx; leftx = 0.0f; }
         else if(leftx >= wf) { leftx = wf_m1; }
-        float rightx = R.XMin;                                                // :392-400
+        float rightx = Rx;                                                    // :392-400
         if(rightx < 0.0f) { rightx = 0.0f; }
         else if(rightx >= wf) { rightx = wf_m1; }
         const int minx = round_s32(leftx);                                    // :402-406
         int maxx = round_s32(rightx);
-        const float z = fadd(L.ZMin, fmul(xoff, zi));                         // :375, :408
+        const float z = fadd(Lz, fmul(xoff, zi));                             // :375, :408
         const float c0 = fadd(Lc0, fmul(xoff, i0)), c1 = fadd(Lc1, fmul(xoff, i1));
         const float c2 = fadd(Lc2, fmul(xoff, i2)), c3 = fadd(Lc3, fmul(xoff, i3));
         float sn0 = 0.0f, sn1 = 0.0f, sn2 = 0.0f;
-        if(phong)
-        {
-            sn0 = fadd(L.MinNormal[0], fmul(xoff, ni0)); sn1 = fadd(L.MinNormal[1], fmul(xoff, ni1));
-            sn2 = fadd(L.MinNormal[2], fmul(xoff, ni2));
-        }
+        if(phong) { sn0 = fadd(Ln0, fmul(xoff, ni0)); sn1 = fadd(Ln1, fmul(xoff, ni1)); sn2 = fadd(Ln2, fmul(xoff, ni2)); }
         // colours of a whole object are not range-checked by a set-up pass: always the guarded pack
         const uint32_t flags = kSpanNonFinite | (phong ? kSpanPhong : 0u) | (tex ? (kSpanTex | ((uint32_t)o.tex << 8)) : 0u);
         const unsigned prim = o.prim_base + produced;
@@ -157,23 +174,28 @@ struct Walker
         ++produced;
     }
 
-    __device__ void step(DevEdge &e) const                                   // projekt.cpp:542-560
+    __device__ void step(int i)                                              // projekt.cpp:542-560
     {
-        e.XMin = fadd(e.XMin, e.Gradient);
-        e.ZMin = fadd(e.ZMin, e.ZGradient);
-#pragma unroll
-        for(int i = 0; i < 4; ++i) e.MinColor[i] = fadd(e.MinColor[i], e.ColorGradient[i]);
-        if(o.phong)
-        {
-            float n0 = fadd(e.MinNormal[0], e.NormalGradient[0]), n1 = fadd(e.MinNormal[1], e.NormalGradient[1]);
-            float n2 = fadd(e.MinNormal[2], e.NormalGradient[2]);
-            normalize3f(n0, n1, n2);
-            e.MinNormal[0] = n0; e.MinNormal[1] = n1; e.MinNormal[2] = n2;
+        const DevEdge &e = E[i];
+        s.x[i] = fadd(s.x[i], __ldg(&e.Gradient));
+        s.z[i] = fadd(s.z[i], __ldg(&e.ZGradient));
+        if(o.tex >= 0)                                                       // :554-560 (the colours of a textured
+        {                                                                    //  object never reach the image)
+            s.c[4*i + 0] = fadd(s.c[4*i + 0], __ldg(&e.UGradient));
+            s.c[4*i + 1] = fadd(s.c[4*i + 1], __ldg(&e.VGradient));
+            s.c[4*i + 2] = fadd(s.c[4*i + 2], __ldg(&e.OneOverZGradient));
         }
-        if(o.tex >= 0)
+        else
         {
-            e.UMin = fadd(e.UMin, e.UGradient); e.VMin = fadd(e.VMin, e.VGradient);
-            e.OneOverZMin = fadd(e.OneOverZMin, e.OneOverZGradient);
+#pragma unroll
+            for(int k = 0; k < 4; ++k) s.c[4*i + k] = fadd(s.c[4*i + k], __ldg(&e.ColorGradient[k]));   // :548-549
+        }
+        if(o.phong)                                                          // :551-552
+        {
+            float n0 = fadd(s.n[3*i], __ldg(&e.NormalGradient[0])), n1 = fadd(s.n[3*i + 1], __ldg(&e.NormalGradient[1]));
+            float n2 = fadd(s.n[3*i + 2], __ldg(&e.NormalGradient[2]));
+            normalize3f(n0, n1, n2);
+            s.n[3*i] = n0; s.n[3*i + 1] = n1; s.n[3*i + 2] = n2;
         }
     }
 
@@ -182,32 +204,38 @@ struct Walker
     {
         const int n = (int)o.edge_count;
         if(n == 0) return true;
-        const int first_row = E[0].YMin;                                     // :173
-        int max_row = E[0].YMax;                                             // :176-185
-        for(int e = 1; e < n; ++e) max_row = max(max_row, E[e].YMax);
+        int *next = s.next;
+        const int first_row = __ldg(&E[0].YMin);                             // :173
+        int max_row = __ldg(&E[0].YMax);                                     // :176-185
+        for(int e = 1; e < n; ++e) max_row = max(max_row, __ldg(&E[e].YMax));
         const int max_y = min(max_row, v.height);                            // :187-196
         int head = -1, tail = -1;
         const long long fuse = 4ll*n + 64;
+        // The reference scans every edge on every row for YMin == RowIndex (:202-208).  The array is
+        // sorted by YMin (MergeSort, :4117) and rows advance by one from Edges[0].YMin, so those edges
+        // are the contiguous run at a cursor, visited in the same (array) order.
+        int cursor = 0;
         for(int row = first_row; row < max_y; ++row)                         // :198
         {
-            for(int cur = 0; cur < n; ++cur)                                 // :202-260
+            for(; cursor < n && __ldg(&E[cursor].YMin) <= row; ++cursor)     // :202-260
             {
-                if(E[cur].YMin != row) continue;
+                const int cur = cursor;
+                if(__ldg(&E[cur].YMin) != row) continue;
                 if(head >= 0)
                 {
-                    if(before(cur, head)) { E[cur].Next = head; head = cur; }
+                    if(before(cur, head)) { next[cur] = head; head = cur; }
                     else
                     {
                         int compared = head, previous = head;
                         long long steps = 0;
                         while(compared != tail)
                         {
-                            compared = (int)E[compared].Next;
+                            compared = next[compared];
                             if(compared < 0 || ++steps > fuse) return false;
-                            if(before(cur, compared)) { E[cur].Next = compared; E[previous].Next = cur; compared = tail; }
+                            if(before(cur, compared)) { next[cur] = compared; next[previous] = cur; compared = tail; }
                             else previous = compared;
                         }
-                        if(previous == compared) { E[tail].Next = cur; tail = cur; }
+                        if(previous == compared) { next[tail] = cur; tail = cur; }
                     }
                 }
                 else { head = cur; tail = head; }
@@ -215,53 +243,53 @@ struct Walker
             for(long long steps = 0;; ++steps)                                // :262-267
             {
                 if(head < 0 || steps > fuse) return false;
-                if(!(E[head].YMax <= row)) break;
-                const int removed = head; head = (int)E[head].Next; E[removed].Next = -1;
+                if(!(__ldg(&E[head].YMax) <= row)) break;
+                const int removed = head; head = next[head]; next[removed] = -1;
             }
             {
                 int previous = head, checked = head;                         // :269-296
                 long long steps = 0;
                 while(checked != tail)
                 {
-                    checked = (int)E[checked].Next;
+                    checked = next[checked];
                     if(checked < 0 || ++steps > fuse) return false;
-                    if(E[checked].YMax <= row)
+                    if(__ldg(&E[checked].YMax) <= row)
                     {
-                        if(checked == tail) { tail = previous; E[tail].Next = -1; checked = tail; }
-                        else { E[previous].Next = E[checked].Next; checked = previous; }
+                        if(checked == tail) { tail = previous; next[tail] = -1; checked = tail; }
+                        else { next[previous] = next[checked]; checked = previous; }
                     }
                     previous = checked;
                 }
             }
             int prev_cur = -1, prev_next = -1;                                // :298-303
-            int cur = head, nxt = (int)E[cur].Next;
+            int cur = head, nxt = next[cur];
             long long npairs = 0;
             while(nxt >= 0)
             {
                 if(++npairs > fuse) return false;
                 if(produced >= o.span_bound) return false;                   // cannot happen: the bound counts edge rows
-                emit(E[cur], E[nxt], row);                                   // :306-540
-                step(E[cur]); step(E[nxt]);                                  // :542-560
-                if(E[cur].XMin > E[nxt].XMin)                                // :562-572
+                emit(cur, nxt, row);                                         // :306-540
+                step(cur); step(nxt);                                        // :542-560
+                if(s.x[cur] > s.x[nxt])                                      // :562-572
                 {
-                    E[cur].Next = E[nxt].Next;
-                    E[nxt].Next = cur;
-                    if(prev_next >= 0) E[prev_next].Next = nxt;
+                    next[cur] = next[nxt];
+                    next[nxt] = cur;
+                    if(prev_next >= 0) next[prev_next] = nxt;
                     cur = nxt;
-                    nxt = (int)E[cur].Next;
+                    nxt = next[cur];
                 }
-                if(prev_next >= 0 && E[prev_next].XMin > E[cur].XMin)        // :574-584
+                if(prev_next >= 0 && s.x[prev_next] > s.x[cur])              // :574-584
                 {
-                    E[prev_next].Next = E[cur].Next;
-                    E[cur].Next = prev_next;
-                    E[prev_cur].Next = cur;
+                    next[prev_next] = next[cur];
+                    next[cur] = prev_next;
+                    next[prev_cur] = cur;
                     prev_next = cur;
-                    cur = (int)E[prev_next].Next;
+                    cur = next[prev_next];
                     if(cur < 0) return false;
                 }
                 prev_cur = cur; prev_next = nxt;                              // :586-587
                 if(nxt < 0) return false;
-                if(E[nxt].Next >= 0) { cur = (int)E[nxt].Next; nxt = (int)E[cur].Next; }   // :589-597
+                if(next[nxt] >= 0) { cur = next[nxt]; nxt = next[cur]; }     // :589-597
                 else nxt = -1;
             }
         }
@@ -269,13 +297,39 @@ struct Walker
     }
 };
 
-__global__ void __launch_bounds__(32)
+constexpr int kObjectThreads = 32;
+
+// One CTA per object: all lanes load the mutable state, lane 0 walks.
+__global__ void __launch_bounds__(kObjectThreads)
 object_walk_kernel(ViewParams v, ObjectWalkParams p)
 {
-    const unsigned oi = blockIdx.x*blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) float s_state[];
+    const unsigned oi = blockIdx.x;
     if(oi >= p.nobjects) return;
     const ObjectDesc o = p.objects[oi];
-    Walker w = { v, p, o, reinterpret_cast<DevEdge *>(p.edges) + o.first_edge, 0u, 0u, (float)v.width, fsub((float)v.width, 1.0f) };
+    const DevEdge *E = reinterpret_cast<const DevEdge *>(p.edges) + o.first_edge;
+    const unsigned n = o.edge_count;
+    const unsigned words = o.phong ? 10u : 7u;              // x, z, 4 interpolants, next (+ 3 normal)
+    // the object's state: shared memory if it fits, else its slice of the global scratch area
+    float *base = ((size_t)n*words*sizeof(float) <= p.state_smem_bytes) ? s_state
+                                                                         : p.state_scratch + (size_t)o.first_edge*10u;
+    WalkState st;
+    st.x = base; st.z = base + n; st.c = base + 2*n; st.next = reinterpret_cast<int *>(base + 6*n); st.n = base + 7*n;
+    const bool tex = o.tex >= 0;
+    for(unsigned e = threadIdx.x; e < n; e += kObjectThreads)
+    {
+        const DevEdge &d = E[e];
+        st.x[e] = d.XMin; st.z[e] = d.ZMin;
+        st.c[4*e + 0] = tex ? d.UMin : d.MinColor[0];
+        st.c[4*e + 1] = tex ? d.VMin : d.MinColor[1];
+        st.c[4*e + 2] = tex ? d.OneOverZMin : d.MinColor[2];
+        st.c[4*e + 3] = tex ? 0.0f : d.MinColor[3];
+        st.next[e] = -1;                                    // FillEdgeTable: Next = 0 (:4094)
+        if(o.phong) { st.n[3*e] = d.MinNormal[0]; st.n[3*e + 1] = d.MinNormal[1]; st.n[3*e + 2] = d.MinNormal[2]; }
+    }
+    __syncthreads();
+    if(threadIdx.x != 0) return;
+    Walker w = { v, p, o, E, st, 0u, 0u, (float)v.width, fsub((float)v.width, 1.0f) };
     const bool ok = w.walk();
     if(!ok) atomicAdd(p.stopped, 1u);
     // promised slots the object did not use
@@ -295,7 +349,8 @@ object_walk_kernel(ViewParams v, ObjectWalkParams p)
 void launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s)
 {
     if(p.nobjects == 0) return;
-    object_walk_kernel<<<(p.nobjects + 31)/32, 32, 0, s>>>(v, p);
+    cudaFuncSetAttribute(object_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.state_smem_bytes);
+    object_walk_kernel<<<p.nobjects, kObjectThreads, p.state_smem_bytes, s>>>(v, p);
 }
 
 } // namespace b200r

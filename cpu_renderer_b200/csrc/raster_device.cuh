@@ -244,7 +244,9 @@ struct ObjectDesc
 };
 struct ObjectWalkParams
 {
-    void *edges;                        // device copy of the edge_info arrays, mutated by the walk
+    const void *edges;                  // the objects' sorted edge_info arrays (read only)
+    float *state_scratch;               // 10 words per edge: mutable walk state of objects too large for shared memory
+    unsigned state_smem_bytes;          // dynamic shared memory per CTA (the largest object that fits, at most 200 KB)
     const ObjectDesc *objects;
     unsigned nobjects;
     uint32_t *spans; int span_words;

@@ -469,6 +469,22 @@ def test_whole_object_mode_differs_from_per_triangle_mode_like_the_reference(ren
     assert int((c0 != c1).sum()) == int(GOLD["c1_1080p_level01_color_diff"])
 
 
+def test_whole_object_mode_object_too_large_for_shared_memory(renderer):
+    """A 48-step sphere has ~13 k edges: its walk state (28 B per edge) exceeds the 200 KB the kernel
+    keeps in shared memory and lives in the global scratch area instead -- same image."""
+    pos, col, nrm, uvs = sc.construct_sphere(48)
+    s = sc.sphere_scene(pos, col, nrm, uvs, 1280, 720, 330.0)
+    want = ol.oracle_render_object(s)
+    assert want["status"] == 1
+    e, n = ol.oracle_edge_table(s)
+    assert n * 28 > 200 * 1024
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL)
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32))
+    assert np.array_equal(color, want["color"])
+
+
 def test_whole_object_mode_several_objects_one_call(renderer):
     """Three spheres (one textured, one Phong) as three objects of one call: the oracle draws them in
     the same order into the same targets; owners keep the submission order across objects."""
