@@ -132,7 +132,10 @@ __global__ void zrange_finish_kernel(unsigned *zkeys)
 
 // PHONG: the mesh is drawn with per-pixel Phong shading (render_entry_3d_object::PhongShading,
 // projekt.cpp:4012-4019): edge colours stay unlit, edges and spans carry interpolated normals.
-template<bool PHONG>
+// TEX: the mesh is textured (MeshParams::uv): the colour interpolants carry u/z, v/z, 1/z.  A
+// template parameter, not a run-time branch: the untextured kernel must not pay for the code (this
+// kernel is instruction-cache bound; the branches cost 6 % of its time when they were run-time).
+template<bool PHONG, bool TEX>
 __global__ void __launch_bounds__(kSetupThreads, 5)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
@@ -167,7 +170,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const float *gc = m.col + (size_t)base*12;
         const float *gn = m.nrm + (size_t)base*9;
         const bool aligned = ((((uintptr_t)gp) | ((uintptr_t)gc) | ((uintptr_t)gn)) & 15) == 0;
-        if(m.uv != nullptr)
+        if(TEX)
         {
             // textured mesh: the vertex colours never reach the image (MeshParams::uv); the colour
             // slots of the staging area take the UVs, two floats per vertex
@@ -321,7 +324,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     float4 c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
                     float col[4] = { c4.x, c4.y, c4.z, c4.w };
                     V3 nr = { s_nrm[tri*9 + 3*q + 0], s_nrm[tri*9 + 3*q + 1], s_nrm[tri*9 + 3*q + 2] };
-                    if(m.uv != nullptr) { lit[q][0] = s_col[tri*12 + 2*q]; lit[q][1] = s_col[tri*12 + 2*q + 1]; lit[q][2] = 0.0f; lit[q][3] = 0.0f; }
+                    if(TEX) { lit[q][0] = s_col[tri*12 + 2*q]; lit[q][1] = s_col[tri*12 + 2*q + 1]; lit[q][2] = 0.0f; lit[q][3] = 0.0f; }
                     else if(PHONG) { lit[q][0] = col[0]; lit[q][1] = col[1]; lit[q][2] = col[2]; lit[q][3] = col[3]; }   // :4014-4015
                     else
                     {
@@ -352,7 +355,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                     E[E_YMIN] = (uint32_t)ymin; E[E_YMAX] = (uint32_t)ymax;
                     E[E_X] = __float_as_uint(x); E[E_DX] = __float_as_uint(g);
                     E[E_Z] = __float_as_uint(z); E[E_DZ] = __float_as_uint(zg);
-                    if(m.uv != nullptr)
+                    if(TEX)
                     {
                         // projekt.cpp:4002-4008, 4078-4089.  z of a projected vertex is
                         // DistanceAboveTarget - camera z (:81, :89).  UMin is u/z, a true division; the
@@ -401,7 +404,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 
         have_walk = (nedges >= 2) && out.spans != nullptr;
         nonfinite = 0;
-        if(have_walk && m.uv == nullptr)
+        if(have_walk && !TEX)
         {
             // RoundR32ToU32 (cvtss2si) and cvt.rni.s32.f32 agree only for |c*255| < 2^31.  Colours of
             // finite scenes stay near [0,1]; a triangle whose edge colours could leave that range
@@ -551,7 +554,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const float *nrm = PHONG ? (s_nrm + tri*9) : nullptr;
         const int sw = out.span_words;
         const uint32_t span_flags = (nonfinite ? kSpanNonFinite : 0u) | (PHONG ? kSpanPhong : 0u) |
-                                    (m.tex >= 0 ? (kSpanTex | ((uint32_t)m.tex << 8)) : 0u);
+                                    (TEX ? (kSpanTex | ((uint32_t)m.tex << 8)) : 0u);
         const float wf = (float)v.width, wf_m1 = fsub(wf, 1.0f);
         ActiveEdge L, R;
         L.x = L.z = L.c0 = L.c1 = L.c2 = L.c3 = L.dx = L.dz = L.d0 = L.d1 = L.d2 = L.d3 = 0.0f;
@@ -749,8 +752,11 @@ void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &
 {
     if(m.ntri == 0) return;
     unsigned blocks = (m.ntri + kSetupThreads - 1)/kSetupThreads;
-    if(m.phong) setup_kernel<true><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
-    else setup_kernel<false><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
+    const bool tex = m.uv != nullptr;
+    if(m.phong) { if(tex) setup_kernel<true, true><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
+                  else setup_kernel<true, false><<<blocks, kSetupThreads, 0, s>>>(v, m, out); }
+    else        { if(tex) setup_kernel<false, true><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
+                  else setup_kernel<false, false><<<blocks, kSetupThreads, 0, s>>>(v, m, out); }
 }
 
 // ---------------------------------------------------------------- clear
