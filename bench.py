@@ -51,6 +51,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the JSON result.  Libraries write to fd 1 behind Python's back
+# (NCCL prints its version banner there when a process group comes up), so fd 1 is pointed at stderr
+# for the whole run and the result goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -177,7 +200,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count(), "model": cpu_model()},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def cpu_sample(config, scene, sc, sample=0, threads=0):
@@ -596,12 +619,13 @@ def run_ours(args):
         except Exception as e:  # the baseline is a reported number, never a reason to lose the line
             line["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port",
                                     "sample": f"failed: {e!r}"}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
