@@ -284,6 +284,8 @@ static int issue_frame(b200r_context *c)
                   (c->target.ColorPitch & 15) == 0 && ((c->target.DepthStride*4) & 15) == 0 &&
                   (c->target.Width & 3) == 0) ? 1 : 0;
     rp.textures = nullptr;
+    rp.texture_count = (unsigned)c->tex_host.size();
+    rp.mode = (c->span_words == kSpanWordsPhong) ? kRasterGeneral : (c->tex_host.empty() ? kRasterPlain : kRasterTextured);
     if(!c->tex_host.empty())
     {
         CU(c->tex_dev.reserve(c->tex_host.size()*sizeof(TexDesc)));
@@ -496,9 +498,11 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
     // first guesses (2.5 segments, 6 spans, 8 queue entries per triangle); all lists grow on demand
     if(c->segs.bytes == 0) CU(c->segs.reserve((size_t)std::max<uint64_t>(total*5/2, 1u << 16)*sizeof(SegInfo)));
-    // a frame with a Phong or a textured mesh uses the wider span record (and the raster kernel's
-    // general variant, which shades per span flag) for all its spans
-    c->span_words = (any_phong || any_tex) ? kSpanWordsPhong : kSpanWords;
+    // a frame with a Phong mesh uses the wider span record (normals) and the raster kernel's general
+    // variant for all its spans; textured frames without Phong keep the 16-word record (the colour
+    // words carry u/z, v/z, 1/z) and take the textured variant
+    c->span_words = any_phong ? kSpanWordsPhong : kSpanWords;
+    (void)any_tex;
     if(c->spans.bytes == 0) CU(c->spans.reserve((size_t)std::max<uint64_t>(total*6, 1u << 16)*c->span_words*sizeof(uint32_t)));
     // counts, cursors, offsets (+1 end entry), and the scan's chunk scratch
     CU(c->tiles.reserve(((size_t)ntiles*kDepthBuckets*3 + 1 + 2*((size_t)ntiles*kDepthBuckets/8192 + 2))*sizeof(unsigned)));
@@ -910,7 +914,7 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
     std::vector<TexDesc> texs;
     std::vector<edge_info> scratch;
     uint64_t slots = 0;
-    bool general = false;
+    bool general = false, any_phong_obj = false;
     size_t ntex = 0;
     for(u32 i = 0; i < n; ++i)
     {
@@ -954,6 +958,7 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
             d.tex = (int)k;
         }
         general |= d.phong != 0 || d.tex >= 0;
+        any_phong_obj |= d.phong != 0;
         all.insert(all.end(), scratch.begin(), scratch.begin() + ne);
         descs.push_back(d);
     }
@@ -985,7 +990,8 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
         CU(cudaStreamSynchronize(c->stream));           // `all` and `descs` are stack vectors
     }
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
-    c->span_words = general ? kSpanWordsPhong : kSpanWords;
+    c->span_words = any_phong_obj ? kSpanWordsPhong : kSpanWords;
+    (void)general;
     // exact needs are known: the promised slots, striped over the regions, plus room for alias pixels
     const size_t region = (size_t)(slots/kSubAllocators) + 2 + 1024;
     CU(c->segs.reserve(region*kSubAllocators*sizeof(SegInfo)));

@@ -98,6 +98,8 @@ struct SegInfo
     unsigned nrows;             // number of span records
 };
 
+enum { kRasterPlain = 0, kRasterGeneral = 1, kRasterTextured = 2 };
+
 struct RasterParams
 {
     ViewParams v;
@@ -117,6 +119,8 @@ struct RasterParams
     int depth_stride;           // floats per row
     int bulk_ok;                // rows may be moved with cp.async.bulk (16-byte aligned)
     const TexDesc *textures;    // device: the frame's texture table (null without textured meshes)
+    unsigned texture_count;
+    int mode;                   // kRasterPlain / kRasterGeneral / kRasterTextured (raster_kernel.cu)
     int refill_lanes;           // idle lanes of a warp that trigger a refill from the span queue
     int pend_lanes;             // parked lanes of a warp that trigger the depth-pass path
 };

@@ -153,11 +153,22 @@ struct TileLayout
     static constexpr int kBytes = kPix*16 + 16;     // pixels + mbarrier
 };
 
-// PHONG: the frame contains Phong meshes (24-word span records; per-span flag selects the shading)
-template<int TW, int TH, int WARPS, bool PHONG>
+// MODE (RasterParams::mode), one kernel per kind of frame so that the common one stays lean:
+//   kRasterPlain     Gouraud only: 16-word span records, 41 registers
+//   kRasterGeneral   the frame contains Phong meshes: 24-word records, per-span flags select per-pixel
+//                    Phong shading and / or texturing (80 registers: 3 instead of 5 CTAs per SM)
+//   kRasterTextured  textured meshes but no Phong mesh: 16-word records whose colour words carry
+//                    u/z, v/z, 1/z for textured spans; a candidate pixel fetches its texel inline
+// __grid_constant__: the shaders below take p.v by reference; without it the parameter struct is
+// copied to local memory first (440 bytes of stack in the general kernel).
+template<int TW, int TH, int WARPS, int MODE>
 __global__ void __launch_bounds__(WARPS*32)
-raster_kernel(const RasterParams p)
+raster_kernel(const __grid_constant__ RasterParams p)
 {
+    constexpr bool PHONG = MODE == kRasterGeneral;         // normals, lighting, 24-word records
+    constexpr bool TEX = MODE != kRasterPlain;             // spans may be textured
+    constexpr int kMaxSharedTex = 16;
+    __shared__ TexDesc s_tex[TEX ? kMaxSharedTex : 1];     // the first textures of the table, one load per CTA
     constexpr int NPIX = TW*TH;
     constexpr int NT = WARPS*32;
     constexpr int PPT = NPIX/NT;                           // pixels per thread when (un)packing
@@ -176,6 +187,7 @@ raster_kernel(const RasterParams p)
     uint32_t *cstage = reinterpret_cast<uint32_t *>(smem_raw + NPIX*8);
 
     if(tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if(TEX && tid < kMaxSharedTex && tid < p.texture_count) s_tex[tid] = p.textures[tid];
     __syncthreads();
     uint32_t phase = 0;
 
@@ -295,6 +307,16 @@ raster_kernel(const RasterParams p)
                     if(PHONG && tex_id >= 0)
                         mine.color = tex_pixel(p.v, p.textures, tex_id, c0, c1, c2, phong_span, n0, n1, n2,
                                                fadd((float)x, shade_dx), shade_row, z);
+                    else if(MODE == kRasterTextured && tex_id >= 0)
+                    {
+                        // projekt.cpp:427-446, unlit: the texel word itself (see tex_pixel)
+                        const TexDesc td = (tex_id < kMaxSharedTex) ? s_tex[tex_id] : p.textures[tex_id];
+                        const float inv = fdiv(1.0f, c2);
+                        const float tx = fmul(fmul(inv, c0), (float)(td.w - 1)), ty = fmul(fmul(inv, c1), (float)(td.h - 1));
+                        const int ix = min(max(round_s32(tx), 0), td.w - 1), iy = min(max(round_s32(ty), 0), td.h - 1);
+                        mine.color = __ldg(reinterpret_cast<const uint32_t *>(
+                            reinterpret_cast<const unsigned char *>(td.mem) + (size_t)iy*(size_t)td.pitch) + ix);
+                    }
                     else
                         mine.color = (PHONG && phong_span)
                                      ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
@@ -347,11 +369,15 @@ raster_kernel(const RasterParams p)
                             c3 = q2.x; zi = q2.y; i0 = q2.z; i1 = q2.w;
                             i2 = q3.x; i3 = q3.y;
                             guarded = (__float_as_uint(q3.z) & kSpanNonFinite) != 0;
+                            if(TEX)
+                            {
+                                const unsigned fl = __float_as_uint(q3.z);
+                                tex_id = (fl & kSpanTex) ? (int)((fl >> 8) & 0xffffu) : -1;
+                            }
                             if(PHONG)
                             {
                                 const unsigned fl = __float_as_uint(q3.z);
                                 phong_span = (fl & kSpanPhong) != 0;
-                                tex_id = (fl & kSpanTex) ? (int)((fl >> 8) & 0xffffu) : -1;
                                 shade_dx = 0.0f; shade_row = (float)y;
                                 if(phong_span)
                                 {
@@ -439,11 +465,11 @@ raster_kernel(const RasterParams p)
     bulk_wait_read();
 }
 
-template<int TW, int TH, int WARPS, bool PHONG>
+template<int TW, int TH, int WARPS, int MODE>
 static cudaError_t launch_one(const RasterParams &p, int sm_count, cudaStream_t s)
 {
     const int smem = TileLayout<TW, TH>::kBytes;
-    auto kern = raster_kernel<TW, TH, WARPS, PHONG>;
+    auto kern = raster_kernel<TW, TH, WARPS, MODE>;
     static bool configured = false;
     static int per_sm = 1;
     if(!configured)
@@ -461,21 +487,23 @@ static cudaError_t launch_one(const RasterParams &p, int sm_count, cudaStream_t 
     return cudaGetLastError();
 }
 
-template<bool PHONG>
+template<int MODE>
 static cudaError_t launch_mode(const RasterParams &p, int sm_count, cudaStream_t s)
 {
     const int tw = p.v.tile_w, th = p.v.tile_h;
-    if(tw == 64 && th == 32) return launch_one<64, 32, 8, PHONG>(p, sm_count, s);     // 32 KB tile
-    if(tw == 32 && th == 32) return launch_one<32, 32, 8, PHONG>(p, sm_count, s);     // 16 KB
-    if(tw == 128 && th == 16) return launch_one<128, 16, 8, PHONG>(p, sm_count, s);   // 32 KB
-    if(tw == 64 && th == 16) return launch_one<64, 16, 8, PHONG>(p, sm_count, s);     // 16 KB
-    if(tw == 128 && th == 32) return launch_one<128, 32, 8, PHONG>(p, sm_count, s);   // 64 KB
+    if(tw == 64 && th == 32) return launch_one<64, 32, 8, MODE>(p, sm_count, s);     // 32 KB tile
+    if(tw == 32 && th == 32) return launch_one<32, 32, 8, MODE>(p, sm_count, s);     // 16 KB
+    if(tw == 128 && th == 16) return launch_one<128, 16, 8, MODE>(p, sm_count, s);   // 32 KB
+    if(tw == 64 && th == 16) return launch_one<64, 16, 8, MODE>(p, sm_count, s);     // 16 KB
+    if(tw == 128 && th == 32) return launch_one<128, 32, 8, MODE>(p, sm_count, s);   // 64 KB
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_raster(const RasterParams &p, int sm_count, cudaStream_t s)
 {
-    return (p.span_words == kSpanWordsPhong) ? launch_mode<true>(p, sm_count, s) : launch_mode<false>(p, sm_count, s);
+    if(p.mode == kRasterGeneral) return launch_mode<kRasterGeneral>(p, sm_count, s);
+    if(p.mode == kRasterTextured) return launch_mode<kRasterTextured>(p, sm_count, s);
+    return launch_mode<kRasterPlain>(p, sm_count, s);
 }
 
 } // namespace b200r
