@@ -77,6 +77,11 @@ struct b200r_context
     size_t edges_bytes = 0;
     unsigned obj_total_slots = 0;       // sum of the objects' span bounds
     unsigned obj_smem_bytes = 0;        // walk state of the largest object that fits into shared memory
+    // three-phase path: chain offsets per edge, the value chains, the pair list, per-object counters
+    DeviceBuffer obj_chain_base, obj_chains, obj_pairs, obj_flags;
+    unsigned obj_chain_T = 0, obj_order_smem = 0, obj_max_bound = 0, obj_max_edges = 0;
+    bool obj_three_phase = false;
+    bool obj_force_serial = false;      // env B200R_OBJECT_SERIAL=1 (tests: keeps the fallback kernel covered)
     // textures of the last issued frame: distinct b200r_device_texture descriptors, uploaded as a table
     std::vector<TexDesc> tex_host;
     DeviceBuffer tex_dev;
@@ -216,6 +221,19 @@ static int issue_frame(b200r_context *c)
         op.extra_total = &words->extra_total;
         op.seg_capacity = seg_cap; op.span_capacity = span_cap; op.region_size = seg_cap/kSubAllocators;
         op.tile_count = tile_count; op.counters = words->counters; op.stopped = &words->stopped;
+        op.chain_base = nullptr; op.chains = nullptr; op.chain_T = 0; op.pair_list = nullptr;
+        op.produced = nullptr; op.fallback = nullptr; op.order_smem_bytes = 0;
+        op.max_bound = c->obj_max_bound; op.max_edges = c->obj_max_edges;
+        if(c->obj_three_phase)
+        {
+            op.chain_base = (const unsigned *)c->obj_chain_base.ptr;
+            op.chains = (float *)c->obj_chains.ptr; op.chain_T = c->obj_chain_T;
+            op.pair_list = (uint4 *)c->obj_pairs.ptr;
+            op.produced = (unsigned *)c->obj_flags.ptr; op.fallback = op.produced + op.nobjects;
+            op.order_smem_bytes = c->obj_order_smem;
+            CU(cudaMemsetAsync(c->obj_flags.ptr, 0, (size_t)op.nobjects*2*sizeof(unsigned), c->stream));
+            c->stats.KernelLaunches += 3;
+        }
         launch_object_walk(v, op, c->stream);
         c->stats.KernelLaunches += 1;
     }
@@ -376,6 +394,7 @@ int b200r_create(b200r_context **out, int device)
     memset(c->h_words, 0, sizeof(FrameWords));
     if(const char *e = getenv("B200R_REFILL")) c->refill_lanes = std::max(1, std::min(32, atoi(e)));
     if(const char *e = getenv("B200R_PEND")) c->pend_lanes = std::max(1, std::min(32, atoi(e)));
+    if(const char *e = getenv("B200R_OBJECT_SERIAL")) c->obj_force_serial = atoi(e) != 0;   // whole-object mode: serial walk only
     *out = c;
     return B200R_OK;
 }
@@ -388,6 +407,8 @@ void b200r_destroy(b200r_context *c)
     c->recs.release(); c->segs.release(); c->spans.release(); c->tiles.release(); c->pairs.release(); c->words.release();
     c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_uv.release(); c->d_color.release(); c->d_depth.release();
     c->tex_dev.release();
+    c->obj_dev.release(); c->edges_pristine.release(); c->edges_work.release();
+    c->obj_chain_base.release(); c->obj_chains.release(); c->obj_pairs.release(); c->obj_flags.release();
     for(b200r_context::HostTexture &ht : c->host_textures) ht.pixels.release();
     for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
     if(c->h_words) cudaFreeHost(c->h_words);
@@ -916,6 +937,9 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
     uint64_t slots = 0;
     bool general = false, any_phong_obj = false;
     size_t ntex = 0;
+    std::vector<unsigned> chain_base;
+    uint64_t chain_T = 0;
+    unsigned max_edges = 0, max_bound = 0;
     for(u32 i = 0; i < n; ++i)
     {
         const render_entry_3d_object &o = objs[i];
@@ -926,6 +950,20 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
         ObjectDesc d;
         d.first_edge = (unsigned)all.size(); d.edge_count = (unsigned)ne;
         d.phong = o.PhongShading ? 1 : 0; d.tex = -1;
+        // projekt.cpp:176-196: one past the object's last row
+        int max_row = ne ? scratch[0].YMax : 0;
+        for(int e = 1; e < ne; ++e) max_row = std::max<int>(max_row, scratch[e].YMax);
+        d.max_y = std::min(max_row, H);
+        // value chains: rows + 1 entries per edge (object_walk_kernel.cu, chain_entries)
+        d.chain_first = (unsigned)chain_T;
+        for(int e = 0; e < ne; ++e)
+        {
+            const int64_t rows = (int64_t)std::min<int>(scratch[e].YMax, d.max_y) - scratch[e].YMin;
+            chain_base.push_back((unsigned)chain_T);
+            chain_T += (uint64_t)std::max<int64_t>(rows, 0) + 1;
+        }
+        d.chain_total = (unsigned)(chain_T - d.chain_first);
+        max_edges = std::max<unsigned>(max_edges, (unsigned)ne);
         // every pair consumes one row of two active edges: half the edge rows bound the spans
         uint64_t edge_rows = 0;
         for(int e = 0; e < ne; ++e)
@@ -938,6 +976,7 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
         if(slots + bound > 0x7fffffffull) return fail(c, B200R_E_UNSUPPORTED, "more than 2^31-1 spans per call");
         d.span_base = d.prim_base = (unsigned)slots; d.span_bound = (unsigned)bound;
         slots += bound;
+        max_bound = std::max<unsigned>(max_bound, (unsigned)bound);
         if(o.Bitmap)
         {
             const loaded_bitmap *b = o.Bitmap;
@@ -987,7 +1026,19 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
         CU(c->obj_dev.reserve(descs.size()*sizeof(ObjectDesc)));
         if(c->edges_bytes) CU(cudaMemcpyAsync(c->edges_pristine.ptr, all.data(), c->edges_bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->obj_dev.ptr, descs.data(), descs.size()*sizeof(ObjectDesc), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaStreamSynchronize(c->stream));           // `all` and `descs` are stack vectors
+        // three-phase path unless the value chains would be unreasonably large (9 words per edge row)
+        c->obj_three_phase = !c->obj_force_serial && chain_T > 0 && chain_T*9*sizeof(float) <= (1ull << 30) &&
+                             chain_T < 0xffffffffull;
+        if(c->obj_three_phase)
+        {
+            CU(c->obj_chain_base.reserve(chain_base.size()*sizeof(unsigned)));
+            CU(c->obj_chains.reserve((size_t)chain_T*9*sizeof(float) + 64));
+            CU(c->obj_pairs.reserve((size_t)slots*sizeof(uint4)));
+            CU(c->obj_flags.reserve(descs.size()*2*sizeof(unsigned)));
+            CU(cudaMemcpyAsync(c->obj_chain_base.ptr, chain_base.data(), chain_base.size()*sizeof(unsigned),
+                               cudaMemcpyHostToDevice, c->stream));
+        }
+        CU(cudaStreamSynchronize(c->stream));           // `all`, `descs`, `chain_base` are stack vectors
     }
     const unsigned ntiles = (unsigned)(v.tiles_x*v.tiles_y);
     c->span_words = any_phong_obj ? kSpanWordsPhong : kSpanWords;
@@ -1008,10 +1059,16 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
     c->obj_host.swap(descs);
     c->obj_total_slots = (unsigned)slots;
     c->obj_smem_bytes = 0;
+    c->obj_order_smem = 0;
+    c->obj_chain_T = (unsigned)chain_T; c->obj_max_bound = max_bound; c->obj_max_edges = max_edges;
     for(const ObjectDesc &d : c->obj_host)
     {
         const size_t need = (size_t)d.edge_count*(d.phong ? 10 : 7)*sizeof(float);
         if(need <= 200u*1024u) c->obj_smem_bytes = std::max<unsigned>(c->obj_smem_bytes, (unsigned)need);
+        // order phase: links + step counts, and the x chains when they fit too
+        const size_t links = (size_t)d.edge_count*4*sizeof(int), all_ = links + (size_t)d.chain_total*sizeof(float);
+        if(all_ <= 200u*1024u) c->obj_order_smem = std::max<unsigned>(c->obj_order_smem, (unsigned)all_);
+        else if(links <= 200u*1024u) c->obj_order_smem = std::max<unsigned>(c->obj_order_smem, (unsigned)links);
     }
     c->stats.Triangles = 0;
     for(u32 i = 0; i < n; ++i) c->stats.Triangles += objs[i].VertexCount/3;

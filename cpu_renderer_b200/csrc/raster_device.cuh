@@ -245,6 +245,8 @@ struct ObjectDesc
     unsigned prim_base;                 // owner of its first span
     int phong;                          // render_entry_3d_object::PhongShading
     int tex;                            // texture table index, -1: untextured
+    int max_y;                          // min(largest YMax, Height): one past the object's last row (projekt.cpp:187-196)
+    unsigned chain_first, chain_total;  // its slice of the value chains (three-phase path)
 };
 struct ObjectWalkParams
 {
@@ -261,6 +263,16 @@ struct ObjectWalkParams
     unsigned *tile_count;
     unsigned long long *counters;
     unsigned *stopped;                  // objects that stopped where the reference dereferences null
+    // ---- three-phase path: value chains per edge, list order per object, span set-up per pair ----
+    const unsigned *chain_base;         // per edge: frame-wide index of its chain (rows + 1 entries); null: serial walk only
+    float *chains;                      // structure of arrays over chain_T entries: x | z | c[4] | n[3]
+    unsigned chain_T;
+    uint4 *pair_list;                   // per promised slot: chain index left, chain index right, row
+    unsigned *produced;                 // per object: pairs the order phase emitted
+    unsigned *fallback;                 // per object: 1 = a step ran past its chain, the serial walk redoes the object
+    unsigned order_smem_bytes;
+    unsigned max_bound;                 // largest span_bound (grid of the emit phase)
+    unsigned max_edges;                 // largest edge_count (grid of the chain phase)
 };
 void launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s);
 // zrange[0..1] start as {-inf as ordered key, +inf as ordered key}; zrange_finish turns them into

@@ -455,6 +455,26 @@ def test_whole_object_mode_against_verbatim_golden(renderer, name):
         assert int(ch.max()) <= PHONG_TOLERANCE_LSB
 
 
+@pytest.mark.parametrize("name", ["sphere", "sphere_tex_phong", "sphere_moved1", "soup_as_object1", "soup_as_object3"])
+def test_whole_object_mode_serial_fallback_kernel(name, monkeypatch):
+    """The three-phase path (value chains, list order, span set-up) falls back to a serial walk when a
+    step would run past an edge's chain.  B200R_OBJECT_SERIAL=1 forces that kernel for every object:
+    same golden images, same stop points."""
+    monkeypatch.setenv("B200R_OBJECT_SERIAL", "1")
+    r = Renderer(0)
+    try:
+        s, phong = LEVEL0_CASES[name]
+        color, z, _ = ol.new_targets(s)
+        r.set_tile(64, 32)
+        r.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL, phong=phong)
+        assert ol.fnv1a64_words(z) == str(LEVEL0[f"{name}_z_hash"])
+        assert r.stats()["StoppedObjects"] == (1 if int(LEVEL0[f"{name}_status"]) < 0 else 0)
+        if not phong:
+            assert ol.fnv1a64_words(color) == str(LEVEL0[f"{name}_color_hash"])
+    finally:
+        r.close()
+
+
 def test_whole_object_mode_differs_from_per_triangle_mode_like_the_reference(renderer):
     """C1 at 1080p: level 0 vs level 1 differ on exactly the pixels SURVEY.md probe P4 counted."""
     s = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], 1920, 1080, 500.0)
