@@ -39,11 +39,16 @@ struct DeviceBuffer
     void release() { if(ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
 };
 
+// The host-pointer call splits the frame into bands of tile rows: a band's targets are uploaded, the
+// band rastered and read back while the next band's targets are still on the bus (PCIe is full duplex).
+constexpr int kHostBands = 4;
+
 // control words that are zeroed once per frame with a single memset
 struct FrameWords
 {
     unsigned pair_total;
     unsigned work_counter;
+    unsigned band_counters[kHostBands]; // host-pointer path: one tile counter per raster band
     unsigned extra_total;
     unsigned overflow;                  // finalize_kernel: some list did not fit
     unsigned seg_max, span_max;         // finalize_kernel: largest region fill (incl. alias entries)
@@ -106,8 +111,11 @@ struct b200r_context
     // what they read -- the z-range pass for all positions, each chunk's set-up for that chunk's
     // colours and normals, the raster kernel for the targets -- so set-up and binning overlap the
     // rest of the upload instead of following it
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t pos_ready = nullptr, target_ready = nullptr;
+    cudaEvent_t band_ready[kHostBands] = {}, band_done[kHostBands] = {};
+    int host_bands = 1;                     // 1: whole frame at once (small targets)
+    struct { void *color; size_t color_pitch; void *depth; size_t depth_pitch; int W, H, wpad; } host_out = {};
     std::vector<cudaEvent_t> chunk_ready;   // pool, grown on demand
     bool host_path = false;                 // issue_frame: honour the events above
 };
@@ -293,6 +301,7 @@ static int issue_frame(b200r_context *c)
     rp.pair_total = &words->pair_total;
     rp.pair_capacity = pair_cap;
     rp.work_counter = &words->work_counter;
+    rp.tile_begin = 0; rp.tile_end = ntiles;
     rp.ntiles = ntiles;
     rp.color = c->target.Color;
     rp.depth = c->target.Depth;
@@ -313,10 +322,34 @@ static int issue_frame(b200r_context *c)
     }
     rp.refill_lanes = c->refill_lanes;
     rp.pend_lanes = c->pend_lanes;
-    if(c->host_path) CU(cudaStreamWaitEvent(c->stream, c->target_ready, 0));
-    cudaError_t e = launch_raster(rp, c->sm_count, c->stream);
-    if(e != cudaSuccess) return fail(c, B200R_E_CUDA, "raster_kernel launch", e);
-    c->stats.KernelLaunches += 1;
+    const int nbands = (c->host_path && c->host_bands > 1) ? c->host_bands : 1;
+    for(int b = 0; b < nbands; ++b)
+    {
+        const int tr0 = v.tiles_y*b/nbands, tr1 = v.tiles_y*(b + 1)/nbands;
+        rp.tile_begin = (unsigned)(tr0*v.tiles_x); rp.tile_end = (unsigned)(tr1*v.tiles_x);
+        if(rp.tile_end <= rp.tile_begin) continue;
+        rp.work_counter = (nbands == 1) ? &words->work_counter : &words->band_counters[b];
+        if(c->host_path) CU(cudaStreamWaitEvent(c->stream, nbands == 1 ? c->target_ready : c->band_ready[b], 0));
+        cudaError_t e = launch_raster(rp, c->sm_count, c->stream);
+        if(e != cudaSuccess) return fail(c, B200R_E_CUDA, "raster_kernel launch", e);
+        c->stats.KernelLaunches += 1;
+        if(nbands > 1)
+        {
+            // read the band back on the second copy stream while the next band is rastered.  (After an
+            // overflow verdict the kernel did nothing and this returns the caller's own pixels; the
+            // re-issued frame copies again.)
+            const int y0 = tr0*v.tile_h, y1 = std::min(tr1*v.tile_h, c->host_out.H);
+            const size_t dp = (size_t)c->host_out.wpad*4, rowbytes = (size_t)c->host_out.W*4;
+            CU(cudaEventRecord(c->band_done[b], c->stream));
+            CU(cudaStreamWaitEvent(c->d2h_stream, c->band_done[b], 0));
+            CU(cudaMemcpy2DAsync((char *)c->host_out.color + (size_t)y0*c->host_out.color_pitch, c->host_out.color_pitch,
+                                 (char *)c->d_color.ptr + (size_t)y0*dp, dp, rowbytes, (size_t)(y1 - y0),
+                                 cudaMemcpyDeviceToHost, c->d2h_stream));
+            CU(cudaMemcpy2DAsync((char *)c->host_out.depth + (size_t)y0*c->host_out.depth_pitch, c->host_out.depth_pitch,
+                                 (char *)c->d_depth.ptr + (size_t)y0*dp, dp, rowbytes, (size_t)(y1 - y0),
+                                 cudaMemcpyDeviceToHost, c->d2h_stream));
+        }
+    }
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[4], c->stream));
     CU(cudaGetLastError());
     c->pending = true;
@@ -414,6 +447,9 @@ void b200r_destroy(b200r_context *c)
     if(c->h_words) cudaFreeHost(c->h_words);
     if(c->total_ready) cudaEventDestroy(c->total_ready);
     if(c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if(c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    for(cudaEvent_t e : c->band_ready) if(e) cudaEventDestroy(e);
+    for(cudaEvent_t e : c->band_done) if(e) cudaEventDestroy(e);
     if(c->pos_ready) cudaEventDestroy(c->pos_ready);
     if(c->target_ready) cudaEventDestroy(c->target_ready);
     for(cudaEvent_t e : c->chunk_ready) if(e) cudaEventDestroy(e);
@@ -730,11 +766,30 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     const int wpad = (W + 63) & ~63;
     CU(c->d_color.reserve((size_t)wpad*H*4));
     CU(c->d_depth.reserve((size_t)wpad*H*4));
-    // 3. the targets, last: only the raster kernel reads them
-    CU(cudaMemcpy2DAsync(c->d_color.ptr, (size_t)wpad*4, out->Memory, (size_t)out->Pitch, (size_t)W*4, H,
-                         cudaMemcpyHostToDevice, c->copy_stream));
-    CU(cudaMemcpy2DAsync(c->d_depth.ptr, (size_t)wpad*4, cmd->ZBuffer, (size_t)cmd->Width*4, (size_t)W*4, H,
-                         cudaMemcpyHostToDevice, c->copy_stream));
+    // 3. the targets, last: only the raster kernel reads them -- band by band of tile rows, so that
+    //    the first band can be rastered and read back while the others are still being uploaded
+    const int tiles_y = (H + c->tile_h - 1)/c->tile_h;
+    c->host_bands = (tiles_y >= 2*kHostBands) ? kHostBands : 1;
+    c->host_out.color = out->Memory; c->host_out.color_pitch = (size_t)out->Pitch;
+    c->host_out.depth = cmd->ZBuffer; c->host_out.depth_pitch = (size_t)cmd->Width*4;
+    c->host_out.W = W; c->host_out.H = H; c->host_out.wpad = wpad;
+    if(!c->d2h_stream) CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for(int b = 0; b < c->host_bands; ++b)
+    {
+        if(!c->band_ready[b]) CU(cudaEventCreateWithFlags(&c->band_ready[b], cudaEventDisableTiming));
+        if(!c->band_done[b]) CU(cudaEventCreateWithFlags(&c->band_done[b], cudaEventDisableTiming));
+        const int y0 = std::min(tiles_y*b/c->host_bands*c->tile_h, H), y1 = std::min(tiles_y*(b + 1)/c->host_bands*c->tile_h, H);
+        if(y1 > y0)
+        {
+            CU(cudaMemcpy2DAsync((char *)c->d_color.ptr + (size_t)y0*wpad*4, (size_t)wpad*4,
+                                 (const char *)out->Memory + (size_t)y0*out->Pitch, (size_t)out->Pitch, (size_t)W*4, (size_t)(y1 - y0),
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaMemcpy2DAsync((char *)c->d_depth.ptr + (size_t)y0*wpad*4, (size_t)wpad*4,
+                                 (const char *)cmd->ZBuffer + (size_t)y0*cmd->Width*4, (size_t)cmd->Width*4, (size_t)W*4, (size_t)(y1 - y0),
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CU(cudaEventRecord(c->band_ready[b], c->copy_stream));
+    }
     CU(cudaEventRecord(c->target_ready, c->copy_stream));
     b200r_device_target t;
     t.Color = (u32 *)c->d_color.ptr; t.Depth = (r32 *)c->d_depth.ptr;
@@ -748,7 +803,14 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     {
         cudaStreamSynchronize(c->copy_stream);  // the caller may free its buffers once we return
         cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->d2h_stream);
         return rc;
+    }
+    if(c->host_bands > 1)
+    {
+        CU(cudaStreamSynchronize(c->d2h_stream));       // every band was read back as it finished
+        CU(cudaStreamSynchronize(c->stream));
+        return B200R_OK;
     }
     CU(cudaMemcpy2DAsync(out->Memory, (size_t)out->Pitch, c->d_color.ptr, (size_t)wpad*4, (size_t)W*4, H,
                          cudaMemcpyDeviceToHost, c->stream));

@@ -113,6 +113,7 @@ struct RasterParams
     unsigned pair_capacity;
     unsigned *work_counter;
     unsigned ntiles;
+    unsigned tile_begin, tile_end;  // this launch renders tiles [tile_begin, tile_end) (row-major: a band of tile rows)
     uint32_t *color;            // band rows
     float *depth;
     int color_pitch_words;      // u32 per row

@@ -197,8 +197,8 @@ raster_kernel(const __grid_constant__ RasterParams p)
     {
         if(tid == 0) { s_tile = atomicAdd(p.work_counter, 1u); s_ticket = 0; }
         __syncthreads();
-        const unsigned tile_id = s_tile;
-        if(tile_id >= p.ntiles) break;
+        const unsigned tile_id = p.tile_begin + s_tile;
+        if(tile_id >= p.tile_end) break;
         // the tile's queue = its kDepthBuckets sub-queues, contiguous and nearest bucket first
         const unsigned off = p.tile_offset[tile_id*kDepthBuckets];
         const unsigned cnt = p.tile_offset[(tile_id + 1)*kDepthBuckets] - off;
@@ -481,7 +481,7 @@ static cudaError_t launch_one(const RasterParams &p, int sm_count, cudaStream_t 
         configured = true;
     }
     unsigned grid = (unsigned)(sm_count*per_sm);           // persistent: a multiple of the SM count
-    if(grid > p.ntiles) grid = p.ntiles;
+    if(grid > p.tile_end - p.tile_begin) grid = p.tile_end - p.tile_begin;
     if(grid < 1) grid = 1;
     kern<<<grid, WARPS*32, smem, s>>>(p);
     return cudaGetLastError();
