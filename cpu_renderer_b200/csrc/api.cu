@@ -115,6 +115,7 @@ struct b200r_context
     cudaEvent_t pos_ready = nullptr, target_ready = nullptr;
     cudaEvent_t band_ready[kHostBands] = {}, band_done[kHostBands] = {};
     int host_bands = 1;                     // 1: whole frame at once (small targets)
+    int host_alias_rows = -1;               // host-pointer calls: rows of the caller's targets are contiguous (0/1); -1: device call
     struct { void *color; size_t color_pitch; void *depth; size_t depth_pitch; int W, H, wpad; } host_out = {};
     std::vector<cudaEvent_t> chunk_ready;   // pool, grown on demand
     bool host_path = false;                 // issue_frame: honour the events above
@@ -171,6 +172,10 @@ static int fill_view(b200r_context *c, const game_render_commands *cmd, const b2
     v.tiles_x = (t->Width + c->tile_w - 1)/c->tile_w;
     v.tiles_y = (t->BandRows + c->tile_h - 1)/c->tile_h;
     v.alias_rows = (t->ColorPitch == t->Width*4 && t->DepthStride == t->Width) ? 1 : 0;
+    // host-pointer calls render into a device mirror whose rows are padded to 64 pixels; whether a
+    // column == Width write lands in the next row (projekt.cpp:414-419) is a property of the CALLER's
+    // layout, not of the mirror's
+    if(c->host_alias_rows >= 0) v.alias_rows = c->host_alias_rows;
     if(v.tiles_x > 65535 || v.tiles_y > 65535) return fail(c, B200R_E_UNSUPPORTED, "more than 65535 tiles per axis");
     return B200R_OK;
 }
@@ -796,9 +801,11 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     t.Width = W; t.Height = H; t.ColorPitch = wpad*4; t.DepthStride = wpad;
     t.BandFirstRow = 0; t.BandRows = H;
     c->host_path = true;
+    c->host_alias_rows = (out->Pitch == W*4 && cmd->Width == (u32)W) ? 1 : 0;
     rc = b200r_render_device(c, meshes.data(), (u32)meshes.size(), cmd, &t, flags);
     if(rc == B200R_OK) rc = settle_pending(c);  // re-issue before the read-back if the list grew
     c->host_path = false;
+    c->host_alias_rows = -1;
     if(rc != B200R_OK)
     {
         cudaStreamSynchronize(c->copy_stream);  // the caller may free its buffers once we return
@@ -1077,7 +1084,9 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
     t.Width = W; t.Height = H; t.ColorPitch = wpad*4; t.DepthStride = wpad;
     t.BandFirstRow = 0; t.BandRows = H;
     ViewParams v;
+    c->host_alias_rows = (out->Pitch == W*4 && cmd->Width == (u32)W) ? 1 : 0;
     int rc = fill_view(c, cmd, &t, v, true);            // light-count rules were applied per object above
+    c->host_alias_rows = -1;
     if(rc != B200R_OK) return rc;
 
     if(!descs.empty())
@@ -1088,6 +1097,9 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
         CU(c->obj_dev.reserve(descs.size()*sizeof(ObjectDesc)));
         if(c->edges_bytes) CU(cudaMemcpyAsync(c->edges_pristine.ptr, all.data(), c->edges_bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->obj_dev.ptr, descs.data(), descs.size()*sizeof(ObjectDesc), cudaMemcpyHostToDevice, c->stream));
+        // the chain arrays are x | z | c[4] | n[3] over chain_T entries and c is read with 128-bit loads:
+        // every section must start 16-byte aligned
+        chain_T = (chain_T + 3) & ~(uint64_t)3;
         // three-phase path unless the value chains would be unreasonably large (9 words per edge row)
         c->obj_three_phase = !c->obj_force_serial && chain_T > 0 && chain_T*9*sizeof(float) <= (1ull << 30) &&
                              chain_T < 0xffffffffull;

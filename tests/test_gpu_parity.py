@@ -531,6 +531,100 @@ def test_whole_object_mode_several_objects_one_call(renderer):
     assert renderer.stats()["StoppedObjects"] == 0
 
 
+# ---- randomized sweep: every mode against the oracle on seeded random configurations ---------------
+def _random_case(seed):
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(97, 700)), int(rng.integers(65, 500))
+    s = sc.triangle_soup(f"fz{seed}", int(rng.integers(1, 1 << 30)), int(rng.integers(50, 4000)), w, h,
+                         float(rng.uniform(1.0, 6.0)), float(rng.uniform(8.0, 120.0)), jitter=float(rng.uniform(0.3, 2.5)))
+    t = s.transform
+    t.focal_length = float(rng.uniform(0.6, 2.5))
+    t.meters_to_pixels = float(rng.uniform(0.3, 1.2) * h)
+    t.screen_center = (float(rng.uniform(0.3, 0.7) * w), float(rng.uniform(0.3, 0.7) * h))
+    s.object_p = tuple(float(x) for x in rng.uniform(-0.8, 0.8, size=3))
+    s.ambient = tuple(float(x) for x in rng.uniform(0.0, 0.5, size=4))
+    s.lights = [sc.Light(P=tuple(float(x) for x in rng.uniform(-6, 8, size=3)),
+                         intensity=tuple(float(x) for x in rng.uniform(0.0, 1.0, size=4)))
+                for _ in range(int(rng.integers(1, 4)))]
+    tex = bool(rng.integers(0, 2))
+    if tex:
+        lo = float(rng.uniform(-0.2, 0.4))
+        s = sc.textured(s, int(rng.integers(1, 200)), int(rng.integers(1, 200)), seed=seed, lo=lo, hi=lo + float(rng.uniform(0.1, 0.9)))
+    phong = bool(rng.integers(0, 2))
+    tile = TILES[int(rng.integers(0, len(TILES)))]
+    pad = int(rng.integers(0, 3)) * 4          # extra pixels of row padding in the host targets
+    return s, phong, tex, tile, pad
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomized_configurations_against_the_oracle(renderer, seed):
+    """Random screen sizes (odd), transforms, object offsets, 1-3 lights, Gouraud / Phong, textured or
+    not (UVs partly outside [0,1]: the clamp is exercised), every tile shape, padded host rows."""
+    s, phong, tex, tile, pad = _random_case(seed)
+
+    def targets():
+        return (np.full((s.height, s.width + pad), s.clear_color, np.uint32)[:, :s.width],
+                np.full((s.height, s.width + pad), s.clear_depth, np.float32)[:, :s.width])
+    # the oracle gets targets of the same layout: row padding decides where a column == Width write lands
+    wc, wz = targets()
+    want = ol.oracle_render(s, phong=phong, targets=(wc, wz, None))
+    color, z = targets()
+    renderer.set_tile(*tile)
+    renderer.render_scene_host(s, color, z, phong=phong)
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)), (seed, phong, tex, tile)
+    if phong:
+        ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+        assert int(ch.max()) <= PHONG_TOLERANCE_LSB, (seed, int(ch.max()))
+    else:
+        assert np.array_equal(color, want["color"]), (seed, tex, tile, int((color != want["color"]).sum()))
+
+
+def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
+    """Regression: the host-pointer call renders into a device mirror whose rows are padded to 64 pixels.
+    Whether a span end in [Width-0.5, Width) lands in column 0 of the next row (projekt.cpp:402-419) depends
+    on the CALLER's rows being contiguous, not the mirror's: at width 565 the pixels used to be dropped."""
+    s, phong, tex, tile, _ = _random_case(10)
+    assert s.width % 64 != 0 and not phong and not tex
+    want = ol.oracle_render(s)
+    color, z, _ = ol.new_targets(s)                    # contiguous rows
+    renderer.set_tile(*tile)
+    renderer.render_scene_host(s, color, z)
+    assert renderer.stats()["AliasPixels"] > 0
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)) and np.array_equal(color, want["color"])
+    # the same scene into padded rows: the reference writes into the padding, nothing lands in column 0
+    cp = np.full((s.height, s.width + 4), s.clear_color, np.uint32)[:, :s.width]
+    zp = np.full((s.height, s.width + 4), s.clear_depth, np.float32)[:, :s.width]
+    renderer.render_scene_host(s, cp, zp)
+    assert renderer.stats()["AliasPixels"] == 0
+    assert (zp[:, 0] != z[:, 0]).sum() > 0
+
+
+@pytest.mark.parametrize("seed", range(100, 108))
+def test_randomized_whole_objects_against_the_oracle(renderer, seed):
+    """Random soups and moved spheres as ONE object with B200R_WHOLE_OBJECT_AEL: same image and the same
+    stop / no-stop verdict as the level-0 oracle (which is pinned to the verbatim build's crash points)."""
+    rng = np.random.default_rng(seed)
+    if seed % 2:
+        s, phong, tex, _, _ = _random_case(seed)
+        s = replace(s, positions=s.positions[:int(rng.integers(3, 200)) * 3], colors=s.colors[:600], normals=s.normals[:600], uvs=s.uvs[:600])
+        n = s.positions.shape[0]
+        s = replace(s, colors=s.colors[:n], normals=s.normals[:n], uvs=s.uvs[:n])
+    else:
+        phong = bool(rng.integers(0, 2))
+        s = sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], 640, 400, float(rng.uniform(40, 300)),
+                            object_p=tuple(float(x) for x in rng.uniform(-0.7, 0.7, size=3)))
+        if rng.integers(0, 2):
+            s = replace(s, texture=sc.make_texture(int(rng.integers(2, 90)), int(rng.integers(2, 90)), seed))
+    want = ol.oracle_render_object(s, phong=phong)
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, flags=api.WHOLE_OBJECT_AEL, phong=phong)
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)), seed
+    assert renderer.stats()["StoppedObjects"] == (1 if want["status"] & 2 else 0), seed
+    ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (seed, int(ch.max()))
+
+
 # ---- BASELINE.json sizes -------------------------------------------------------------------------
 def test_c2_full_size(renderer):
     """Config C2 at full size: 1 M ~10 px triangles, 1920x1080 -- whole frame against the oracle."""
