@@ -579,6 +579,54 @@ def test_randomized_configurations_against_the_oracle(renderer, seed):
         assert np.array_equal(color, want["color"]), (seed, tex, tile, int((color != want["color"]).sum()))
 
 
+@pytest.mark.parametrize("seed", range(200, 212))
+def test_randomized_mixed_objects_in_one_call(renderer, seed):
+    """2-5 objects per call at random split points, each with its own PhongShading / Bitmap choice; the
+    oracle draws the same objects in the same order into the same targets."""
+    s, _, _, tile, pad = _random_case(seed)
+    if s.texture is None:
+        s = sc.textured(s, 37, 21, seed=seed, lo=-0.1, hi=1.1)
+    rng = np.random.default_rng(seed + 7)
+    ntri = s.triangle_count
+    k = int(rng.integers(2, 6))
+    cuts = [0] + sorted(int(x) for x in rng.integers(0, ntri + 1, size=k - 1)) + [ntri]    # empty objects allowed
+    modes = [(bool(rng.integers(0, 2)), bool(rng.integers(0, 2))) for _ in range(k)]       # (phong, textured)
+    wc = np.full((s.height, s.width + pad), s.clear_color, np.uint32)[:, :s.width]
+    wz = np.full((s.height, s.width + pad), s.clear_depth, np.float32)[:, :s.width]
+    for i, (ph, tx) in enumerate(modes):
+        a, b = cuts[i] * 3, cuts[i + 1] * 3
+        if b == a:
+            continue
+        part = replace(s, positions=s.positions[a:b], colors=s.colors[a:b], normals=s.normals[a:b], uvs=s.uvs[a:b],
+                       texture=s.texture if tx else None)
+        ol.oracle_render(part, phong=ph, targets=(wc, wz, None), prim_base=cuts[i])
+    color = np.full((s.height, s.width + pad), s.clear_color, np.uint32)[:, :s.width]
+    z = np.full((s.height, s.width + pad), s.clear_depth, np.float32)[:, :s.width]
+    renderer.set_tile(*tile)
+    renderer.render_scene_host(s, color, z, splits=[(cuts[i + 1] - cuts[i]) * 3 for i in range(k)],
+                               phong=[p for p, _ in modes], textured=[t for _, t in modes])
+    assert np.array_equal(z.view(np.uint32), wz.view(np.uint32)), (seed, cuts, modes)
+    ch = np.abs(wc.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if any(p for p, _ in modes) else 0), (seed, int(ch.max()))
+
+
+@pytest.mark.parametrize("seed", range(300, 310))
+def test_randomized_edge_tables_against_the_oracle(renderer, seed):
+    """b200r_fill_edge_table on random objects (Gouraud / Phong, textured or not): every field the selected
+    path defines, in MergeSort order, bit for bit (NaN payloads aside: not part of the contract)."""
+    s, phong, tex, _, _ = _random_case(seed)
+    e_gpu = renderer.fill_edge_table(s, phong=phong)
+    e_orc, n = ol.oracle_edge_table(s, phong=phong)
+    assert len(e_gpu) == n
+    fields = (ol.PHONG_FIELDS if phong else ol.GOURAUD_FIELDS) + (ol.TEX_FIELDS if tex else [])
+    for f in fields:
+        a, b = np.ascontiguousarray(e_gpu[f]), np.ascontiguousarray(e_orc[f])
+        same = a.view(np.uint32) == b.view(np.uint32)
+        if a.dtype.kind == "f":
+            same |= (np.isnan(a) & np.isnan(b))
+        assert same.all(), (seed, f, int((~same).sum()))
+
+
 def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
     """Regression: the host-pointer call renders into a device mirror whose rows are padded to 64 pixels.
     Whether a span end in [Width-0.5, Width) lands in column 0 of the next row (projekt.cpp:402-419) depends
