@@ -627,6 +627,30 @@ def test_randomized_edge_tables_against_the_oracle(renderer, seed):
         assert same.all(), (seed, f, int((~same).sum()))
 
 
+@pytest.mark.parametrize("seed", range(400, 410))
+def test_randomized_row_bands_at_arbitrary_boundaries(renderer, seed):
+    """The multi-GPU row-band split on the device-resident call with 2-5 bands cut at arbitrary rows (not
+    tile aligned).  Even seeds round the width up to a multiple of 64: the band targets' rows are then
+    contiguous and a column == Width pixel of a band's last row belongs to the NEXT band's first row."""
+    s, _, _, tile, _ = _random_case(seed)
+    s = replace(s, texture=None)
+    if seed % 2 == 0:
+        s = replace(s, width=(s.width + 63) // 64 * 64)
+    wpad = (s.width + 63) // 64 * 64
+    wc = np.full((s.height, wpad), s.clear_color, np.uint32)[:, :s.width]      # the band targets' row pitch
+    wz = np.full((s.height, wpad), s.clear_depth, np.float32)[:, :s.width]
+    want = ol.oracle_render(s, targets=(wc, wz, None))
+    rng = np.random.default_rng(seed)
+    cuts = [0] + sorted(set(int(x) for x in rng.integers(1, s.height, size=int(rng.integers(1, 5))))) + [s.height]
+    colors, depths = [], []
+    for a, b in zip(cuts, cuts[1:]):
+        c, z = _device_render(renderer, s, tile, a, b - a)
+        colors.append(c); depths.append(z)
+    color, z = np.concatenate(colors), np.concatenate(depths)
+    d = diff(want["color"], want["z"], color, z, s.clear_depth)
+    assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), (seed, cuts, d)
+
+
 def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
     """Regression: the host-pointer call renders into a device mirror whose rows are padded to 64 pixels.
     Whether a span end in [Width-0.5, Width) lands in column 0 of the next row (projekt.cpp:402-419) depends
