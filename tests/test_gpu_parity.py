@@ -651,6 +651,45 @@ def test_randomized_row_bands_at_arbitrary_boundaries(renderer, seed):
     assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), (seed, cuts, d)
 
 
+@pytest.mark.parametrize("what", ["nan_pos", "inf_pos", "huge_pos", "near_plane", "nan_attr", "inf_attr"])
+@pytest.mark.parametrize("mode", ["gouraud", "phong", "textured"])
+def test_non_finite_and_extreme_vertex_data(renderer, what, mode):
+    """NaN / Inf / 1e30 positions, vertices around and behind the near plane (projekt.cpp:82-86), NaN / Inf
+    colours, normals and UVs: same image as the oracle, no device fault.  (A non-finite position never
+    reaches the rasterizer: the back-face test compares NaN and culls, projekt.cpp:3943.)"""
+    s = sc.triangle_soup("wild", 77, 400, 330, 200, 3.0, 40.0)
+    if mode == "textured":
+        s = sc.textured(s, 19, 23)
+    rng = np.random.default_rng(5)
+    pos, col, nrm, uv = s.positions.copy(), s.colors.copy(), s.normals.copy(), s.uvs.copy()
+    idx = rng.choice(pos.shape[0], 60, replace=False)
+    comp = rng.integers(0, 3, 60)
+    if what == "nan_pos":
+        pos[idx, comp] = np.nan
+    elif what == "inf_pos":
+        pos[idx, comp] = np.where(rng.integers(0, 2, 60) == 0, np.inf, -np.inf)
+    elif what == "huge_pos":
+        pos[idx, comp] = rng.choice([1e30, -1e30, 3e38, 1e12, -1e9], 60)
+    elif what == "near_plane":
+        pos[idx, 2] = rng.uniform(9.7, 10.5, 60)
+    else:
+        bad = np.nan if what == "nan_attr" else np.inf
+        col[idx[:20], rng.integers(0, 4, 20)] = bad
+        nrm[idx[20:40], rng.integers(0, 3, 20)] = bad
+        uv[idx[40:], rng.integers(0, 2, 20)] = bad
+    s = replace(s, positions=pos.astype(np.float32), colors=col.astype(np.float32), normals=nrm.astype(np.float32),
+                uvs=uv.astype(np.float32))
+    phong = mode == "phong"
+    want = ol.oracle_render(s, phong=phong)
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, phong=phong)
+    renderer.sync()
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)), (what, mode)
+    ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (what, mode, int(ch.max()), int((want["color"] != color).sum()))
+
+
 def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
     """Regression: the host-pointer call renders into a device mirror whose rows are padded to 64 pixels.
     Whether a span end in [Width-0.5, Width) lands in column 0 of the next row (projekt.cpp:402-419) depends
