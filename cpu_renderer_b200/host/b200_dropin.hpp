@@ -35,16 +35,19 @@ inline int FillEdgeTable(Context &C, render_entry_3d_object *Object, game_render
 }
 
 // The render-group walker's per-object body (FillEdgeTable + DrawModel) for a batch of objects.
+// Object->PhongShading and Object->Bitmap (+ UVData) select the shading exactly as in the reference.
+// Flags: 0 = every triangle is its own object (fast path); B200R_WHOLE_OBJECT_AEL = the reference's
+// whole-object active-edge list, pixel-identical to its images of multi-triangle objects (slow path).
 inline int DrawModels(Context &C, loaded_bitmap *Buffer, const render_entry_3d_object *Objects, u32 Count,
-                      game_render_commands *Commands)
+                      game_render_commands *Commands, u32 Flags = 0)
 {
-    return b200r_render_objects(C.Handle, Objects, Count, Commands, Buffer, 0);
+    return b200r_render_objects(C.Handle, Objects, Count, Commands, Buffer, Flags);
 }
 
 inline int DrawModel(Context &C, loaded_bitmap *Buffer, const render_entry_3d_object *Object,
-                     game_render_commands *Commands)
+                     game_render_commands *Commands, u32 Flags = 0)
 {
-    return DrawModels(C, Buffer, Object, 1, Commands);
+    return DrawModels(C, Buffer, Object, 1, Commands, Flags);
 }
 
 } // namespace b200
