@@ -690,6 +690,36 @@ def test_non_finite_and_extreme_vertex_data(renderer, what, mode):
     assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (what, mode, int(ch.max()), int((want["color"] != color).sum()))
 
 
+@pytest.mark.parametrize("phong,tex", [(False, True), (True, False), (True, True)])
+def test_list_growth_reissue_with_textures_and_phong(phong, tex):
+    """A fresh context sized by a tiny frame re-issues a big one after growing its lists.  On the
+    host-pointer call every issue reads its bands back into the caller's buffers (the skipped first
+    issue returns the caller's own pixels): the final image must be the oracle's, Reruns > 0."""
+    r = Renderer(0)
+    try:
+        tiny = sc.triangle_soup("tiny", 1, 10, 960, 540, 2.0, 4.0)
+        c0, z0, _ = ol.new_targets(tiny)
+        r.render_scene_host(tiny, c0, z0)
+        big = sc.triangle_soup("big", 2, 4000, 960, 540, 30.0, 90.0)
+        if tex:
+            big = sc.textured(big, 64, 64)
+        want = ol.oracle_render(big, phong=phong)
+        # pre-existing content in the targets takes part in the depth test and must survive the re-issue
+        color, z, _ = ol.new_targets(big)
+        z[100:200, :] = np.float32(20.0); color[100:200, :] = 0x00ABCDEF
+        wc, wz = color.copy(), z.copy()
+        want = ol.oracle_render(big, phong=phong, targets=(wc, wz, None))
+        r.set_tile(64, 32)
+        r.render_scene_host(big, color, z, phong=phong)
+        assert r.stats()["Reruns"] >= 1
+        assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32))
+        ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+        assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0)
+        assert (z[100:200, :] == np.float32(20.0)).mean() > 0.5      # most of the pre-filled band is in front
+    finally:
+        r.close()
+
+
 def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
     """Regression: the host-pointer call renders into a device mirror whose rows are padded to 64 pixels.
     Whether a span end in [Width-0.5, Width) lands in column 0 of the next row (projekt.cpp:402-419) depends
