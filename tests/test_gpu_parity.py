@@ -156,9 +156,9 @@ def test_odd_sizes_and_pitches(renderer, w, h):
     assert (cbuf[:, w:] == 0xDEADBEEF).all() and (zbuf[:, w:] == 123.0).all()    # padding untouched
 
 
-def _device_render(renderer, s, tile, first, rows, world=None):
+def _device_render(renderer, s, tile, first, rows, world=None, phong=False):
     """Render rows [first, first+rows) of scene s into a band-sized device target via the device
-    API (what one GPU of the C4 band split does)."""
+    API (what one GPU of the C4 band split does).  A scene with a texture is submitted textured."""
     import torch
     wpad = (s.width + 63) // 64 * 64
     dev = torch.device("cuda", 0)
@@ -167,9 +167,16 @@ def _device_render(renderer, s, tile, first, rows, world=None):
     d_nrm = torch.from_numpy(s.normals).to(dev)
     color = torch.full((max(rows, 1), wpad), s.clear_color, dtype=torch.int32, device=dev)
     depth = torch.full((max(rows, 1), wpad), s.clear_depth, dtype=torch.float32, device=dev)
+    uv_ptr, tex_ptr, keep_tex = None, None, None
+    if getattr(s, "texture", None) is not None:
+        d_uv = torch.from_numpy(s.uvs).to(dev)
+        t = np.ascontiguousarray(s.texture, dtype=np.uint32)
+        d_tex = torch.from_numpy(t.view(np.int32)).to(dev)
+        dtex = api.device_texture(d_tex.data_ptr(), t.shape[1], t.shape[0], t.shape[1] * 4)
+        uv_ptr, tex_ptr, keep_tex = d_uv.data_ptr(), C.pointer(dtex), (d_uv, d_tex, dtex)
     torch.cuda.synchronize()
     mesh = api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), s.triangle_count,
-                           api.v3(*s.object_p))
+                           api.v3(*s.object_p), api.MESH_PHONG if phong else 0, uv_ptr, tex_ptr)
     cmd, keep = api.make_commands(s)
     tgt = api.device_target(color.data_ptr(), depth.data_ptr(), s.width, s.height, wpad * 4, wpad, first, rows)
     renderer.set_tile(*tile)
@@ -718,6 +725,29 @@ def test_list_growth_reissue_with_textures_and_phong(phong, tex):
         assert (z[100:200, :] == np.float32(20.0)).mean() > 0.5      # most of the pre-filled band is in front
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("seed", range(500, 512))
+def test_randomized_device_resident_call_all_shading_modes(renderer, seed):
+    """b200r_render_device (what bench.py's `value` times) with Phong and / or textured meshes resident
+    on the device, whole frame or split into row bands at arbitrary rows, against the oracle."""
+    s, phong, tex, tile, _ = _random_case(seed)
+    wpad = (s.width + 63) // 64 * 64
+    wc = np.full((s.height, wpad), s.clear_color, np.uint32)[:, :s.width]
+    wz = np.full((s.height, wpad), s.clear_depth, np.float32)[:, :s.width]
+    want = ol.oracle_render(s, phong=phong, targets=(wc, wz, None))
+    rng = np.random.default_rng(seed)
+    cuts = [0, s.height]
+    if seed % 2:
+        cuts = [0] + sorted(set(int(x) for x in rng.integers(1, s.height, size=int(rng.integers(1, 4))))) + [s.height]
+    colors, depths = [], []
+    for a, b in zip(cuts, cuts[1:]):
+        c, z = _device_render(renderer, s, tile, a, b - a, phong=phong)
+        colors.append(c); depths.append(z)
+    color, z = np.concatenate(colors), np.concatenate(depths)
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)), (seed, phong, tex, cuts)
+    ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (seed, int(ch.max()))
 
 
 def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
