@@ -816,6 +816,25 @@ def test_host_path_upload_chunks_do_not_follow_object_boundaries(renderer):
     assert renderer.stats()["Triangles"] == 300_000
 
 
+def test_host_path_upload_chunks_with_textured_phong_objects(renderer):
+    """Chunked uploads of a textured Phong object spanning two chunks (UVs go up instead of colours, at
+    per-chunk offsets) followed by an untextured Gouraud object in the same call."""
+    s = sc.textured(sc.make_config("c2", 0.2), 128, 128, lo=0.2, hi=0.8)         # 200 000 triangles
+    n = s.positions.shape[0]
+    a = 150_000 * 3
+    wc, wz, _ = ol.new_targets(s)
+    first = replace(s, positions=s.positions[:a], colors=s.colors[:a], normals=s.normals[:a], uvs=s.uvs[:a])
+    second = replace(s, positions=s.positions[a:], colors=s.colors[a:], normals=s.normals[a:], uvs=s.uvs[a:], texture=None)
+    ol.oracle_render(first, phong=True, targets=(wc, wz, None))
+    ol.oracle_render(second, phong=False, targets=(wc, wz, None), prim_base=150_000)
+    color, z, _ = ol.new_targets(s)
+    renderer.set_tile(64, 32)
+    renderer.render_scene_host(s, color, z, splits=[a, n - a], phong=[True, False], textured=[True, False])
+    assert np.array_equal(z.view(np.uint32), wz.view(np.uint32))
+    ch = np.abs(wc.view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= PHONG_TOLERANCE_LSB
+
+
 def test_c3_full_size(renderer):
     """Config C3 at full size: 50 k large overlapping triangles, 3840x2160, ~35x overdraw."""
     s = sc.make_config("c3")
