@@ -42,6 +42,8 @@ struct DeviceBuffer
 // The host-pointer call splits the frame into bands of tile rows: a band's targets are uploaded, the
 // band rastered and read back while the next band's targets are still on the bus (PCIe is full duplex).
 constexpr int kHostBands = 4;
+// meshes smaller than this are not worth a pre-selection pass in front of a partial band
+constexpr unsigned kSelectMinTriangles = 1u << 16;
 
 // control words that are zeroed once per frame with a single memset
 struct FrameWords
@@ -75,6 +77,8 @@ struct b200r_context
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
+    // row-band pre-selection (select_kernel): one index list for the frame's meshes, one count per mesh
+    DeviceBuffer sel_list, sel_counts;
     // whole-object mode (B200R_WHOLE_OBJECT_AEL): the last issued frame's objects
     bool object_mode = false;
     std::vector<ObjectDesc> obj_host;
@@ -260,10 +264,29 @@ static int issue_frame(b200r_context *c)
     }
     launch_zrange_finish(words->zkeys, c->stream);
     c->stats.KernelLaunches += 1;
+    // A partial band of a big mesh (multi-GPU row bands): pre-select the triangles that can reach it
+    // from their positions alone, so that the set-up kernel's front end runs on those only.
+    const bool partial_band = v.band_y0 > 0 || v.band_y1 < v.height;
+    bool selecting = false;
+    if(partial_band && !c->host_path)
+        for(const MeshParams &m : c->meshes) selecting |= m.ntri >= kSelectMinTriangles;
+    if(selecting)
+    {
+        CU(c->sel_list.reserve((size_t)std::max<unsigned>(c->total_tris, 1)*sizeof(unsigned)));
+        CU(c->sel_counts.reserve(c->meshes.size()*sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->sel_counts.ptr, 0, c->meshes.size()*sizeof(unsigned), c->stream));
+    }
     for(size_t i = 0; i < c->meshes.size(); ++i)
     {
-        const MeshParams &m = c->meshes[i];
+        MeshParams m = c->meshes[i];
         if(c->host_path && i < c->chunk_ready.size()) CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
+        if(selecting && m.ntri >= kSelectMinTriangles)
+        {
+            unsigned *list = (unsigned *)c->sel_list.ptr + m.prim_base, *count = (unsigned *)c->sel_counts.ptr + i;
+            launch_select(v, m, list, count, c->stream);
+            c->stats.KernelLaunches += 1;
+            m.tri_list = list; m.tri_count = count;
+        }
         launch_setup(v, m, so, c->stream);
         if(m.ntri) c->stats.KernelLaunches += 1;
     }
@@ -446,6 +469,7 @@ void b200r_destroy(b200r_context *c)
     c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_uv.release(); c->d_color.release(); c->d_depth.release();
     c->tex_dev.release();
     c->obj_dev.release(); c->edges_pristine.release(); c->edges_work.release();
+    c->sel_list.release(); c->sel_counts.release();
     c->obj_chain_base.release(); c->obj_chains.release(); c->obj_pairs.release(); c->obj_flags.release();
     for(b200r_context::HostTexture &ht : c->host_textures) ht.pixels.release();
     for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
@@ -535,6 +559,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
         mp.prim_base = (unsigned)total;
         mp.phong = (m.Flags & B200R_MESH_PHONG) ? 1 : 0;
         mp.uv = nullptr; mp.tex = -1; mp.white = 0;
+        mp.tri_list = nullptr; mp.tri_count = nullptr;
         if(m.Texture)
         {
             const b200r_device_texture &t = *m.Texture;
@@ -898,6 +923,7 @@ static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     mp.ntri = tris; mp.px = obj->P.x; mp.py = obj->P.y; mp.pz = obj->P.z; mp.prim_base = 0;
     mp.phong = phong ? 1 : 0;
     mp.uv = nullptr; mp.tex = -1; mp.white = (textured && !phong) ? 1 : 0;
+    mp.tri_list = nullptr; mp.tri_count = nullptr;
     launch_setup(v, mp, so, c->stream);
     c->stats.KernelLaunches += 1;
     CU(cudaGetLastError());

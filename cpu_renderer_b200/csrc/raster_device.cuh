@@ -57,6 +57,11 @@ struct MeshParams
     // image, and u/z, v/z, 1/z are interpolated by exactly the operations the colour channels use
     // (edge step += gradient :554-560, span increment (R-L)/XDifference :336-342, start += XOffset*inc
     // :409-410): in tex mode the four colour interpolants CARRY (u/z, v/z, 1/z, 0).
+    // Row-band pre-selection (multi-GPU bands): when set, the set-up kernel processes only the
+    // triangles listed here (their ORIGINAL indices, in any order) -- the ones select_kernel found
+    // able to reach this GPU's band.  Owners stay prim_base + original index.
+    const unsigned *tri_list;   // device, or null: all ntri triangles in order
+    const unsigned *tri_count;  // device: number of listed triangles
     const float *uv;            // v2 x 3 per triangle, or null
     int tex;                    // index into the frame's texture table, -1: untextured
     int white;                  // b200r_fill_edge_table of a textured Gouraud object: light white vertices (:4034-4060)
@@ -237,6 +242,8 @@ struct SetupOutputs
 };
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
+// positions only: indices of the triangles whose projected rows can reach the band -> list, *count
+void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, cudaStream_t s);
 
 // ---- whole-object mode (object_walk_kernel.cu) ----
 struct ObjectDesc

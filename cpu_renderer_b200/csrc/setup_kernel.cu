@@ -130,12 +130,55 @@ __global__ void zrange_finish_kernel(unsigned *zkeys)
     reinterpret_cast<float *>(zkeys)[1] = inv;
 }
 
+// Can a triangle's rows reach this GPU's band (or the row just above it, which may drop an alias
+// pixel into the band)?  Rows lie in [Round(min y), Round(max y)), so two rows of margin are
+// conservative; NaN compares false and keeps the triangle.  ONE definition, used by the set-up
+// kernel's phase 1 and by select_kernel.
+__device__ __forceinline__ bool off_band_rows(float y0, float y1, float y2, const ViewParams &v)
+{
+    const float ymin_p = fminf(y0, fminf(y1, y2));
+    const float ymax_p = fmaxf(y0, fmaxf(y1, y2));
+    return ymax_p < (float)(v.band_y0 - 2) || ymin_p > (float)(v.band_y1 + 1);
+}
+
+// Row-band pre-selection.  With G GPUs rendering row bands of one frame, every GPU used to run the
+// set-up kernel's whole front end (120 B of attributes staged, three projections, the back-face
+// test) on every triangle although about 1/G of them can reach its band: C4's set-up scaled 1.65x
+// on 8 GPUs.  This pass reads the positions only (36 B), applies the same band test to the same
+// projected rows, and compacts the surviving indices; the set-up kernel then gathers just those.
+__global__ void __launch_bounds__(256)
+select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count)
+{
+    const unsigned tri = blockIdx.x*blockDim.x + threadIdx.x;
+    bool keep = false;
+    if(tri < m.ntri)
+    {
+        const float *gp = m.pos + (size_t)tri*9;
+        float y[3];
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+        {
+            V3 cam = { fadd(__ldg(gp + 3*k + 0), m.px), fadd(__ldg(gp + 3*k + 1), m.py), fadd(__ldg(gp + 3*k + 2), m.pz) };
+            y[k] = project_vertex(cam, v).y;
+        }
+        keep = !off_band_rows(y[0], y[1], y[2], v);
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    unsigned at = 0;
+    if(lane == 0 && bal) at = atomicAdd(count, (unsigned)__popc(bal));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if(keep) list[at + __popc(bal & ((1u << lane) - 1u))] = tri;
+}
+
 // PHONG: the mesh is drawn with per-pixel Phong shading (render_entry_3d_object::PhongShading,
 // projekt.cpp:4012-4019): edge colours stay unlit, edges and spans carry interpolated normals.
 // TEX: the mesh is textured (MeshParams::uv): the colour interpolants carry u/z, v/z, 1/z.  A
 // template parameter, not a run-time branch: the untextured kernel must not pay for the code (this
 // kernel is instruction-cache bound; the branches cost 6 % of its time when they were run-time).
-template<bool PHONG, bool TEX>
+// LISTED: the kernel processes the triangles of MeshParams::tri_list (row-band pre-selection) and
+// gathers their attributes; a template parameter for the same reason.
+template<bool PHONG, bool TEX, bool LISTED>
 __global__ void __launch_bounds__(kSetupThreads, 5)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
@@ -152,8 +195,12 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     __shared__ unsigned s_w_info[kSetupThreads], s_w_spans[kSetupThreads], s_w_seg_at[kSetupThreads], s_w_span_at[kSetupThreads];
     __shared__ unsigned s_warp_sum[kSetupThreads/32], s_warp_sum2[kSetupThreads/32];
 
+    __shared__ unsigned s_id[kSetupThreads];             // list mode: original index of each staged triangle
+    constexpr bool listed = LISTED;
+    const unsigned total = listed ? *m.tri_count : m.ntri;
     const unsigned base = blockIdx.x*kSetupThreads;
-    const unsigned n = min((unsigned)kSetupThreads, m.ntri - base);
+    if(base >= total) return;                              // list mode launches for ntri; the tail has nothing to do
+    const unsigned n = min((unsigned)kSetupThreads, total - base);
     const int t = threadIdx.x;
     if(t == 0) { s_binned = 0; s_pairs = 0; }
     int my_segs = 0, my_spans = 0, walk_end = 0, first_row = 0, max_y = 0, nedges = 0, nonfinite = 0;
@@ -170,7 +217,40 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         const float *gc = m.col + (size_t)base*12;
         const float *gn = m.nrm + (size_t)base*9;
         const bool aligned = ((((uintptr_t)gp) | ((uintptr_t)gc) | ((uintptr_t)gn)) & 15) == 0;
-        if(TEX)
+        if(listed)
+        {
+            // gather: thread t stages the triangle list[base + t] (36 + 48 + 36 contiguous bytes each)
+            if((unsigned)t < n)
+            {
+                const unsigned id = __ldg(m.tri_list + base + t);
+                s_id[t] = id;
+                const float *p9 = m.pos + (size_t)id*9, *n9 = m.nrm + (size_t)id*9;
+                float rp[9], rn[9];
+#pragma unroll
+                for(int i = 0; i < 9; ++i) { rp[i] = __ldg(p9 + i); rn[i] = __ldg(n9 + i); }
+                if(TEX)
+                {
+                    const float *u6 = m.uv + (size_t)id*6;
+                    float ru[6];
+#pragma unroll
+                    for(int i = 0; i < 6; ++i) ru[i] = __ldg(u6 + i);
+#pragma unroll
+                    for(int i = 0; i < 6; ++i) s_col[t*12 + i] = ru[i];
+                }
+                else
+                {
+                    const float *c12 = m.col + (size_t)id*12;
+                    float rc[12];
+#pragma unroll
+                    for(int i = 0; i < 12; ++i) rc[i] = __ldg(c12 + i);
+#pragma unroll
+                    for(int i = 0; i < 12; ++i) s_col[t*12 + i] = rc[i];
+                }
+#pragma unroll
+                for(int i = 0; i < 9; ++i) { s_pos[t*9 + i] = rp[i]; s_nrm[t*9 + i] = rn[i]; }
+            }
+        }
+        else if(TEX)
         {
             // textured mesh: the vertex colours never reach the image (MeshParams::uv); the colour
             // slots of the staging area take the UVs, two floats per vertex
@@ -239,10 +319,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         // which may drop an alias pixel into the band) needs nothing more here.  Rows lie in
         // [Round(min y), Round(max y)), so two rows of margin are conservative; NaN compares false
         // and keeps the triangle.
-        const float ymin_p = fminf(prj[0].y, fminf(prj[1].y, prj[2].y));
-        const float ymax_p = fmaxf(prj[0].y, fmaxf(prj[1].y, prj[2].y));
-        const bool off_band = out.recs == nullptr &&
-                              (ymax_p < (float)(v.band_y0 - 2) || ymin_p > (float)(v.band_y1 + 1));
+        const bool off_band = out.recs == nullptr && off_band_rows(prj[0].y, prj[1].y, prj[2].y, v);
         alive = facing > 0.0f && !off_band;
         // b200r_fill_edge_table only: default record header (no edges), overwritten in phase 2
         if(out.recs)
@@ -567,7 +644,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         int seg_minx = 0x7fffffff, seg_maxx = (int)0x80000000;
         unsigned seg_span0 = 0;
         unsigned pairs = 0;
-        const unsigned prim = m.prim_base + base + (unsigned)tri;
+        const unsigned prim = m.prim_base + (listed ? s_id[tri] : base + (unsigned)tri);
         // depth bucket of the whole triangle: 0 = nearest (largest camera z, projekt.cpp:525)
         unsigned bucket = 0;
         if(walking)
@@ -748,15 +825,29 @@ void launch_zrange_finish(unsigned *zkeys, cudaStream_t s)
     zrange_finish_kernel<<<1, 1, 0, s>>>(zkeys);
 }
 
+void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, cudaStream_t s)
+{
+    if(m.ntri == 0) return;
+    select_kernel<<<(m.ntri + 255)/256, 256, 0, s>>>(v, m, list, count);
+}
+
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s)
 {
     if(m.ntri == 0) return;
     unsigned blocks = (m.ntri + kSetupThreads - 1)/kSetupThreads;
-    const bool tex = m.uv != nullptr;
-    if(m.phong) { if(tex) setup_kernel<true, true><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
-                  else setup_kernel<true, false><<<blocks, kSetupThreads, 0, s>>>(v, m, out); }
-    else        { if(tex) setup_kernel<false, true><<<blocks, kSetupThreads, 0, s>>>(v, m, out);
-                  else setup_kernel<false, false><<<blocks, kSetupThreads, 0, s>>>(v, m, out); }
+    const bool tex = m.uv != nullptr, listed = m.tri_list != nullptr;
+#define B200R_LAUNCH_SETUP(P, T, L) setup_kernel<P, T, L><<<blocks, kSetupThreads, 0, s>>>(v, m, out)
+    if(listed)
+    {
+        if(m.phong) { if(tex) B200R_LAUNCH_SETUP(true, true, true); else B200R_LAUNCH_SETUP(true, false, true); }
+        else        { if(tex) B200R_LAUNCH_SETUP(false, true, true); else B200R_LAUNCH_SETUP(false, false, true); }
+    }
+    else
+    {
+        if(m.phong) { if(tex) B200R_LAUNCH_SETUP(true, true, false); else B200R_LAUNCH_SETUP(true, false, false); }
+        else        { if(tex) B200R_LAUNCH_SETUP(false, true, false); else B200R_LAUNCH_SETUP(false, false, false); }
+    }
+#undef B200R_LAUNCH_SETUP
 }
 
 // ---------------------------------------------------------------- clear

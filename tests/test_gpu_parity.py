@@ -750,6 +750,30 @@ def test_randomized_device_resident_call_all_shading_modes(renderer, seed):
     assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (seed, int(ch.max()))
 
 
+@pytest.mark.parametrize("mode", ["gouraud", "textured_phong"])
+def test_row_band_preselection_of_a_large_mesh(renderer, mode):
+    """Meshes of >= 65 536 triangles rendered into a partial band go through select_kernel first (positions
+    only -> indices of the triangles that can reach the band) and the set-up kernel gathers those: three
+    bands at arbitrary rows of a 100 000-triangle frame, reassembled, against the oracle."""
+    s = sc.make_config("c2", 0.1)
+    assert s.triangle_count == 100_000
+    phong = mode != "gouraud"
+    if phong:
+        s = sc.textured(s, 64, 64, lo=0.2, hi=0.8)
+    want = ol.oracle_render(s, phong=phong)
+    launches = renderer.stats()["KernelLaunches"]
+    cuts = [0, 333, 700, s.height]
+    colors, depths = [], []
+    for a, b in zip(cuts, cuts[1:]):
+        c, z = _device_render(renderer, s, (64, 32), a, b - a, phong=phong)
+        colors.append(c); depths.append(z)
+    assert renderer.stats()["KernelLaunches"] - launches == 3 * 8      # 7 kernels per frame + select_kernel
+    color, z = np.concatenate(colors), np.concatenate(depths)
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32))
+    ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0)
+
+
 def test_alias_pixels_when_the_width_is_not_a_multiple_of_64(renderer):
     """Regression: the host-pointer call renders into a device mirror whose rows are padded to 64 pixels.
     Whether a span end in [Width-0.5, Width) lands in column 0 of the next row (projekt.cpp:402-419) depends
