@@ -37,6 +37,48 @@ def test_struct_layouts_match_projekt_h():
     assert C.sizeof(api.loaded_bitmap) == 24 and C.sizeof(api.game_render_commands) == 104
 
 
+# ctypes mirror -> C type in include/b200_raster.h
+MIRRORS = {
+    "render_entry_3d_object": api.render_entry_3d_object, "loaded_bitmap": api.loaded_bitmap,
+    "game_render_commands": api.game_render_commands, "light_data": api.light_data, "light_info": api.light_info,
+    "projective_transform": api.projective_transform,
+    "b200r_device_mesh": api.device_mesh, "b200r_device_texture": api.device_texture,
+    "b200r_device_target": api.device_target, "b200r_frame_stats": api.frame_stats,
+}
+
+
+def test_ctypes_mirrors_match_the_header_field_by_field(tmp_path):
+    """Compile a C program against the real header and compare sizeof and every field offset of the
+    public structs with the hand-written ctypes mirrors in cpu_renderer_b200/api.py."""
+    import subprocess
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for cname, mirror in MIRRORS.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-o", str(exe), str(src)])
+    got = {}
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, value = line.split()
+        got[(cname, field)] = int(value)
+    for cname, mirror in MIRRORS.items():
+        assert got[(cname, "sizeof")] == C.sizeof(mirror), cname
+        for fname, _ in mirror._fields_:
+            assert got[(cname, fname)] == getattr(mirror, fname).offset, (cname, fname)
+    assert api.EDGE_INFO_DTYPE.itemsize == 120
+
+
+def test_stage_count_matches_the_header():
+    text = open(HEADER).read()
+    assert int(re.search(r"#define\s+B200R_STAGES\s+(\d+)", text).group(1)) == len(api.STAGES)
+    assert int(re.search(r"#define\s+B200R_WHOLE_OBJECT_AEL\s+(\d+)u", text).group(1)) == api.WHOLE_OBJECT_AEL
+    assert int(re.search(r"#define\s+B200R_MESH_PHONG\s+(\d+)u", text).group(1)) == api.MESH_PHONG
+
+
 def test_no_device_means_no_fallback():
     import torch
     if torch.cuda.is_available():
