@@ -243,7 +243,9 @@ int b200r_get_stats(b200r_context *Context, b200r_frame_stats *Stats);
 /* Per-kernel timing of the device path with CUDA events recorded on the launching stream
  * (the reference has no timers at all).  While enabled, every frame
  * records an event between stages; b200r_get_stage_ms syncs and returns the durations of the
- * last frame: [0] setup_kernel, [1] tile_scan_kernel, [2] scatter_kernel, [3] raster_kernel. */
+ * last frame: [0] setup_kernel (with zrange_kernel and, on partial bands, select_kernel; in
+ * whole-object mode the chain / order / emit kernels), [1] tile_scan_kernel + finalize_kernel,
+ * [2] scatter_kernel, [3] raster_kernel. */
 #define B200R_STAGES 4
 int b200r_set_profiling(b200r_context *Context, int Enable);
 int b200r_get_stage_ms(b200r_context *Context, float StageMs[B200R_STAGES]);
