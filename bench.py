@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the rasterization hot path (BASELINE.json metric) on 1..8 B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c1|c2|c3|c4|c5] [--phong] [--textured]
+                    [--impl ours|reference]
 
 A "step" is one frame: the whole hot path (setup -> bin -> raster) over one synthetic scene.
 Default workload = BASELINE.json configs[1] ("C2": 1 M ~10-pixel triangles, 1920x1080,
 depth-tested, Gouraud).  With N > 1 ranks (torchrun, one process per GPU) the path shards by
 FRAME: every rank renders its own 1 M-triangle frame (weak scaling, no data-path collective);
 the NCCL gather of the finished colour images to rank 0 is timed separately ("with_gather").
+The other configurations: c1 = the reference's demo sphere (with a whole-object leg), c3 = 50 k
+large triangles at 4K, c4 = 20 M triangles at 16K^2 split into row bands over the ranks (strong),
+c5 = 256 views of a 2 M-triangle mesh split over the ranks (strong).  --phong / --textured select
+the per-pixel Phong and the textured, perspective-correct path.  At least 3 warm-up steps always run.
 
 Prints ONE JSON line (see the contract in the task statement): value = device-resident
 throughput (CUDA events, max over ranks), e2e = same metric through the host-pointer C-ABI call
