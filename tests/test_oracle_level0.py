@@ -55,3 +55,32 @@ def test_level0_live_against_verbatim(name):
     assert bool(o["status"] & 2) == (r["status"] < 0)
     assert np.array_equal(o["z"].view(np.uint32), r["z"].view(np.uint32))
     assert np.array_equal(o["color"], r["color"])
+
+
+def test_single_triangle_objects_level0_equals_level1():
+    """Two independent restatements of DrawModel's walk live in the oracle: the per-triangle one (arrays,
+    <= 3 edges, defined behaviour where the reference dereferences null) and the whole-object one (the
+    pointer graph, link by link).  For an object that IS one triangle they must produce the same pixels
+    whenever the reference survives; where it does not, level 0 stops and level 1 goes on by definition."""
+    from dataclasses import replace
+    from cpu_renderer_b200 import scene as sc
+    soup = sc.triangle_soup("prop", 0xFEED, 3000, 400, 300, 1.0, 60.0, jitter=2.5)
+    agree = stopped = 0
+    for t in range(soup.triangle_count):
+        one = replace(soup, positions=soup.positions[3*t:3*t + 3], colors=soup.colors[3*t:3*t + 3],
+                      normals=soup.normals[3*t:3*t + 3], uvs=soup.uvs[3*t:3*t + 3])
+        l0 = ol.oracle_render_object(one)
+        l1 = ol.oracle_render(one)
+        if l0["status"] > 0 and (l0["status"] & 2):
+            stopped += 1
+            assert l1["would_crash"][0] == 1, t           # both predict the same crash
+            # level 0 drew a prefix of what level 1 draws
+            drawn0 = l0["z"] != np.float32(one.clear_depth)
+            assert np.array_equal(l0["z"][drawn0].view(np.uint32), l1["z"][drawn0].view(np.uint32)), t
+            continue
+        assert l1["would_crash"][0] == 0, t
+        assert np.array_equal(l0["z"].view(np.uint32), l1["z"].view(np.uint32)), t
+        assert np.array_equal(l0["color"], l1["color"]), t
+        agree += 1
+    assert agree > 2500 and stopped > 0, (agree, stopped)
+
