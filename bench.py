@@ -241,6 +241,23 @@ def cpu_model():
     return "unknown"
 
 
+def equivalent_zbuffer(ol, scene, tri_bytes, frame_ms, peak_gbs):
+    """B = tri_bytes x triangles + 4 B x depth-tested fragments + 8 B x depth passes -- the
+    z-buffer traffic of the REFERENCE's own algorithm for this frame (read the depth per fragment, write
+    depth + colour per pass, projekt.cpp:525-529) -- divided by OUR frame time.  Not a roofline: the tiles
+    live in shared memory and almost none of these bytes reach HBM; it is the figure the config label
+    "fill / z-buffer bandwidth bound" refers to.  Fragments and passes are counted by the oracle in
+    submission order on one thread; they do not depend on the shading mode."""
+    import dataclasses
+    plain = dataclasses.replace(scene, texture=None)
+    st = ol.oracle_render(plain)["stats"]
+    b = tri_bytes * scene.triangle_count + 4.0 * st["Fragments"] + 8.0 * st["DepthPasses"]
+    gbs = b / (frame_ms * 1e-3) / 1e9
+    return {"bytes": b, "fragments": st["Fragments"], "depth_passes": st["DepthPasses"], "GB/s": gbs,
+            "of_measured_hbm_peak": gbs / peak_gbs,
+            "what": "z-buffer traffic of the reference's own algorithm for this frame / our frame time (not HBM traffic)"}
+
+
 def time_cpu(ol, s, threads, steps, warmup, kind, phong=False):
     """Time the reference's scalar path (verbatim build if present, else the port) on scene s."""
     lib_o = ol.oracle()
@@ -621,6 +638,11 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit,
                                     "cores": threads, "kind": kind, "sample": res["sample"],
                                     "host": cpu_model()}
+            if cfgname in ("c1", "c2", "c3"):              # c4 / c5 frames are too large to count on one core here
+                try:
+                    line["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)
+                except Exception as e:
+                    line["roofline"]["equivalent_zbuffer"] = {"error": repr(e)}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the line
             line["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port",
                                     "sample": f"failed: {e!r}"}
