@@ -1,10 +1,13 @@
 // C ABI of libb200raster.so (include/b200_raster.h) and the host-side frame orchestration:
-//   setup_kernel -> tile_scan_kernel -> scatter_kernel -> raster_kernel
-// on one CUDA stream, no host synchronisation inside a frame.  The only host/device handshake
-// is the size of the (triangle, tile) pair list: it is copied back right after the scan and
-// looked at when the *next* call arrives (or at b200r_sync); if it exceeded the list's
-// capacity the scatter and raster kernels of that frame returned without touching the targets,
-// the list is grown and the frame is issued again.
+//   zrange_kernel -> [select_kernel] -> setup_kernel -> tile_scan_kernel -> finalize_kernel
+//   -> scatter_kernel -> raster_kernel
+// (whole-object mode: chain / order / emit kernels instead of the first three) on one CUDA stream,
+// no host synchronisation inside a frame.  The only host/device handshake is the fill of the span,
+// segment and queue lists: it is copied back right after the scan and looked at when the *next*
+// call arrives (or at b200r_sync); if a list overflowed, the scatter and raster kernels of that
+// frame returned without touching the targets, the lists are grown and the frame is issued again.
+// The host-pointer call adds two copy streams: chunked uploads in front of the set-up launches,
+// and targets that go up, are rastered and come back in bands of tile rows.
 //
 // There is no CPU fallback anywhere in this file: without a compute-capability-10 device every
 // entry point returns B200R_E_NO_DEVICE.

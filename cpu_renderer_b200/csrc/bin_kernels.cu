@@ -1,11 +1,13 @@
-// Sort-middle binner (sm_100a): per-tile lists of trapezoid segments from the set-up kernel's
-// exact per-segment tile columns.  The reference has no binning (its nearest analogue is MergeSort by YMin plus
+// Sort-middle binner (sm_100a): per-tile, per-depth-bucket queues of spans, built from the segments
+// (runs of a triangle's spans inside one tile-row band, with their exact tile columns) the set-up
+// kernel -- or, in whole-object mode, the emit kernel -- wrote.  The reference has no binning (its nearest analogue is MergeSort by YMin plus
 // one work item per scan line, projekt.cpp:2-72, 3509-3609); this stage exists because the
 // raster kernel keeps a screen tile on chip.
 //
-//   count   (inside setup_kernel)   tile_count[t] += 1 per tile a segment touches
-//   scan    tile_scan_kernel        exclusive prefix sum over tiles -> tile_offset, pair_total
-//   scatter scatter_kernel          list[tile_offset[t] + slot] = segment
+//   count    (inside setup_kernel)  tile_count[tile][bucket] += rows, per tile column a segment touches
+//   scan     tile_scan_kernel       exclusive prefix sum over the bins -> tile_offset, pair_total
+//   finalize finalize_kernel        one overflow verdict for the frame (lists too small: skip and re-issue)
+//   scatter  scatter_kernel         queue[tile_offset[bin] + slot .. + rows) = the segment's span indices
 //
 // List order inside a bin is NOT submission order (slots are handed out by atomics): the
 // raster kernel resolves depth with the order-independent rule

@@ -1,7 +1,8 @@
 // Tile raster kernel (sm_100a): per-pixel coverage, interpolation, depth test and colour write.
 //
-// Restates DrawModel's Gouraud pixel loop (projekt.cpp:423-425, 510-538) on the span records
-// the set-up kernel produced (span set-up, :306-412, is already done there, once per row).
+// Restates DrawModel's pixel loop -- Gouraud (projekt.cpp:423-425, 510-538), per-pixel Phong
+// (:450-509) and texturing (:427-446), one kernel variant per kind of frame (see MODE below) -- on
+// the span records the set-up kernel produced (span set-up, :306-412, is done there, once per row).
 //
 // "The reference's own arithmetic" is a chain of rounded binary32 additions: the value at pixel
 // k of a span is k sequential adds from the span's left end.  There is no
