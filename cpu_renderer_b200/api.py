@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200raster.so")
+# B200R_LIB: another build of the same library (kernel experiments: variants compiled with other -D flags)
+LIB_PATH = os.environ.get("B200R_LIB") or os.path.join(_HERE, "libb200raster.so")
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM, E_NO_DEVICE = 0, -1, -2, -3, -4, -5
 WHOLE_OBJECT_AEL = 1

@@ -76,7 +76,7 @@ struct b200r_context
     std::string error;
     int tile_w = 64, tile_h = 32;
     int span_words = kSpanWords;        // of the last issued frame (kSpanWordsPhong if it had a Phong mesh)
-    int refill_lanes = 8, pend_lanes = 4;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
+    int refill_lanes = 12, pend_lanes = 4;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
     FrameWords *h_words = nullptr;      // pinned
@@ -516,8 +516,8 @@ int b200r_set_tile(b200r_context *c, int w, int h)
 {
     if(!c) return B200R_E_INVALID;
     if(!((w == 64 && h == 32) || (w == 32 && h == 32) || (w == 128 && h == 16) || (w == 64 && h == 16) ||
-         (w == 128 && h == 32)))
-        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16, 64x16 or 128x32");
+         (w == 128 && h == 32) || (w == 256 && h == 8)))
+        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16, 64x16, 128x32 or 256x8");
     int rc = b200r_sync(c);
     if(rc != B200R_OK) return rc;
     c->tile_w = w; c->tile_h = h;

@@ -17,7 +17,10 @@ constexpr int kMaxLights = 8;
 // Every tile's span queue is split into kDepthBuckets sub-queues by the camera-space depth of the
 // owning triangle, nearest first.  Processing order never changes the image (the depth rule is
 // order independent); near-to-far order only makes the cheap early depth test fail more often.
-constexpr int kDepthBuckets = 8;
+#ifndef B200R_BUCKETS
+#define B200R_BUCKETS 8
+#endif
+constexpr int kDepthBuckets = B200R_BUCKETS;
 // The span and segment arrays are carved into kSubAllocators equal regions, each with its own
 // fill counter; CTA b of the set-up kernel allocates from region b % kSubAllocators.  One global
 // counter pair was the set-up kernel's bottleneck: every CTA does one returning atomicAdd on it

@@ -8,21 +8,28 @@
 // k of a span is k sequential adds from the span's left end.  There is no
 // closed form, so the unit of parallel work is the SPAN, not the pixel:
 //
-//   * a CTA owns one screen tile at a time, staged in shared memory as ONE 128-bit word per
-//     pixel: { depth bits, owner (submission index), ARGB colour, 0 }.  Tile rows enter and
-//     leave with TMA bulk copies (cp.async.bulk + mbarrier) and 128-bit shared accesses;
+//   * a CTA owns one screen tile at a time, staged in shared memory as TWO arrays: a plane of
+//     4-byte depths that the early test reads (32 consecutive pixels = 32 banks), and one 128-bit
+//     word per pixel { depth bits, owner (submission index), ARGB colour, 0 } that only the update
+//     path touches.  Tile rows enter and leave with TMA bulk copies (cp.async.bulk + mbarrier);
 //   * the tile's queue is a flat list of spans.  Lanes are persistent: a lane that runs out of
 //     pixels waits until kRefill lanes of its warp are idle, then the idle lanes take new spans
 //     with ONE warp-aggregated ticket (ballot + popc + shuffle) on a shared-memory counter;
-//   * lanes with pixels advance in lock step, one pixel per iteration; pixels left of the tile
-//     are the same iteration with the memory part predicated off (adds only, in registers);
+//   * lanes with pixels advance in lock step, kRound pixels between two warp votes: the round's
+//     depths are loaded up front (independent loads), then the adds of :534-535 and the early
+//     test run as one predicated chain.  Pixels left of the tile are the same steps with the
+//     load predicated off (adds only, in registers);
 //   * a pixel whose depth test may pass parks its lane; as soon as kPend lanes are parked they run
 //     the update together: pack ARGB (:520-523) and one 128-bit compare-and-swap (ATOMS.CAS.128)
 //     under the rule   z > zold || (z == zold && prim < primold)
 //     which is the reference's strict '>' with first-submitted-wins (:525) made order
 //     independent.  Depth, owner and colour change together, so no ordering between lanes or
-//     warps is needed and the pixel loop contains no barrier.
+//     warps is needed and the pixel loop contains no barrier.  The depth plane is a conservative
+//     copy (never above the word's depth: every value written to it was in the word at some time
+//     and depths only rise), so the early test can only err towards a needless exact test.
 #include "raster_device.cuh"
+
+#include <mutex>
 
 namespace b200r {
 
@@ -41,6 +48,21 @@ __device__ __forceinline__ float lds_depth(uint32_t addr)
     float z;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z) : "r"(addr) : "memory");
     return z;
+}
+// the early test's load: predicated off (and NaN, which no depth compares >= to) outside the tile / span
+__device__ __forceinline__ float lds_depth_if(uint32_t addr, bool on)
+{
+    float z;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.u32 p, %2, 0;\n\t"
+                 "mov.b32 %0, 0x7fc00000;\n\t"
+                 "@p ld.shared.f32 %0, [%1];\n\t}"
+                 : "=f"(z) : "r"(addr), "r"((unsigned)on) : "memory");
+    return z;
+}
+__device__ __forceinline__ void sts_depth(uint32_t addr, float z)
+{
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(z) : "memory");
 }
 // 128-bit compare-and-swap on a shared-memory pixel (SASS: ATOMS.CAS.128)
 __device__ __forceinline__ Pixel cas_pixel(uint32_t addr, const Pixel &cmp, const Pixel &val)
@@ -147,17 +169,28 @@ __device__ __noinline__ uint32_t tex_pixel(const ViewParams &v, const TexDesc *t
     return phong_pixel(v, sr, sg, sb, sa, n0, n1, n2, X, Row, Z, true);
 }
 
+// Pixels a lane walks between two warp votes.  The round's depths are loaded before the chain
+// of adds starts, so a lane's per-pixel latency is one FADD, not one shared-memory round trip.
+// A lane that parks idles for the rest of its round: on C3 (11 % of the fragments pass at the time
+// they are tested) rounds of 8 / 6 / 4 / 2 pixels give 0.75 / 0.70 / 0.67 / 0.66 ms.
+#ifndef B200R_ROUND
+#define B200R_ROUND 4
+#endif
+constexpr int kRound = B200R_ROUND;
+
 template<int TW, int TH>
 struct TileLayout
 {
     static constexpr int kPix = TW*TH;
-    static constexpr int kBytes = kPix*16 + 16;     // pixels + mbarrier
+    static constexpr int kPlane = kPix*16;                      // byte offset of the depth plane
+    static constexpr int kBar = kPix*20 + 64;                   // mbarrier, behind the plane's over-read pad
+    static constexpr int kBytes = kBar + 16;
 };
 
 // MODE (RasterParams::mode), one kernel per kind of frame so that the common one stays lean:
-//   kRasterPlain     Gouraud only: 16-word span records, 41 registers
+//   kRasterPlain     Gouraud only: 16-word span records
 //   kRasterGeneral   the frame contains Phong meshes: 24-word records, per-span flags select per-pixel
-//                    Phong shading and / or texturing (80 registers: 3 instead of 5 CTAs per SM)
+//                    Phong shading and / or texturing
 //   kRasterTextured  textured meshes but no Phong mesh: 16-word records whose colour words carry
 //                    u/z, v/z, 1/z for textured spans; a candidate pixel fetches its texel inline
 // __grid_constant__: the shaders below take p.v by reference; without it the parameter struct is
@@ -174,6 +207,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
     constexpr int NT = WARPS*32;
     constexpr int PPT = NPIX/NT;                           // pixels per thread when (un)packing
     static_assert(NPIX % NT == 0, "tile must divide evenly over the CTA");
+    using Layout = TileLayout<TW, TH>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned s_tile, s_ticket;
     __shared__ float s_rowmin[TH];                        // lower bound of the depth of each tile row
@@ -182,10 +216,11 @@ raster_kernel(const __grid_constant__ RasterParams p)
 
     const int tid = threadIdx.x, lane = tid & 31;
     Pixel *tile = reinterpret_cast<Pixel *>(smem_raw);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + NPIX*16);
-    // staging inside the pixel area: packed depth rows at byte 12*NPIX, packed colour rows at 8*NPIX
-    float *zstage = reinterpret_cast<float *>(smem_raw + NPIX*12);
-    uint32_t *cstage = reinterpret_cast<uint32_t *>(smem_raw + NPIX*8);
+    float *zplane = reinterpret_cast<float *>(smem_raw + Layout::kPlane);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + Layout::kBar);
+    // colour rows are staged inside the pixel area (bytes [12N, 16N)) until they are expanded;
+    // on the way out the colours are packed to bytes [0, 4N) and the depths into the plane
+    uint32_t *cstage = reinterpret_cast<uint32_t *>(smem_raw + NPIX*12);
 
     if(tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     if(TEX && tid < kMaxSharedTex && tid < p.texture_count) s_tex[tid] = p.textures[tid];
@@ -211,7 +246,8 @@ raster_kernel(const __grid_constant__ RasterParams p)
         const int rows = min(TH, band_rows - yb);
         if(cnt == 0) { __syncthreads(); continue; }
 
-        // ---------------- stage the tile: depth -> zstage, colour -> cstage ------------------
+        // ---------------- stage the tile: depth -> plane, colour -> cstage ------------------
+        bulk_wait_read();                                  // the previous tile's stores have read the plane and [0, 4N)
         fence_proxy_async();                               // generic writes above -> async-proxy writes below
         __syncthreads();                                   // (also: everyone has read s_tile)
         if(p.bulk_ok)
@@ -220,7 +256,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
             __syncthreads();
             for(int r = tid; r < rows; r += NT)
             {
-                bulk_g2s(zstage + r*TW, p.depth + (size_t)(yb + r)*p.depth_stride + x0, (uint32_t)(cols*4), bar);
+                bulk_g2s(zplane + r*TW, p.depth + (size_t)(yb + r)*p.depth_stride + x0, (uint32_t)(cols*4), bar);
                 bulk_g2s(cstage + r*TW, p.color + (size_t)(yb + r)*p.color_pitch_words + x0, (uint32_t)(cols*4), bar);
             }
             mbar_wait(bar, phase);
@@ -231,7 +267,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
             for(int i = tid; i < rows*cols; i += NT)
             {
                 const int r = i / cols, c = i % cols;
-                zstage[r*TW + c] = p.depth[(size_t)(yb + r)*p.depth_stride + x0 + c];
+                zplane[r*TW + c] = p.depth[(size_t)(yb + r)*p.depth_stride + x0 + c];
                 cstage[r*TW + c] = p.color[(size_t)(yb + r)*p.color_pitch_words + x0 + c];
             }
             __syncthreads();
@@ -240,8 +276,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
         {
             float zr[PPT]; uint32_t cr[PPT];
 #pragma unroll
-            for(int k = 0; k < PPT; ++k) { zr[k] = zstage[tid + k*NT]; cr[k] = cstage[tid + k*NT]; }
-            bulk_wait_read();                              // the previous tile's stores have left [0, 8N)
+            for(int k = 0; k < PPT; ++k) { zr[k] = zplane[tid + k*NT]; cr[k] = cstage[tid + k*NT]; }
             __syncthreads();
 #pragma unroll
             for(int k = 0; k < PPT; ++k)
@@ -265,7 +300,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
                 float m = __int_as_float(0x7f800000);
                 for(int c = lane; c < TW; c += 32)
                 {
-                    const float zz = lds_depth(smem_addr(tile + r*TW + c));
+                    const float zz = lds_depth(smem_addr(zplane + r*TW + c));
                     if(c < cols && zz < m) m = zz;                // a NaN depth never lets anything pass: no constraint
                 }
 #pragma unroll
@@ -281,74 +316,74 @@ raster_kernel(const __grid_constant__ RasterParams p)
             const int kRefill = p.refill_lanes;            // idle lanes that trigger a refill
             const int kPend = p.pend_lanes;                // parked lanes that trigger the update path
             constexpr unsigned FULL = 0xffffffffu;
-            const uint32_t tile_addr = smem_addr(tile);
+            const uint32_t tile_addr = smem_addr(tile), plane_addr = smem_addr(zplane);
             const int xlast = x0 + cols - 1;
             float z = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, zi = 0, i0 = 0, i1 = 0, i2 = 0, i3 = 0;
             float n0 = 0, n1 = 0, n2 = 0, ni0 = 0, ni1 = 0, ni2 = 0;       // Phong: normal and its per-pixel increment
             float shade_dx = 0, shade_row = 0;                             // Phong: X = x + shade_dx, Row for UnprojectVertex
             bool phong_span = false;
             int tex_id = -1;                                               // textured span: c0..c2 carry u/z, v/z, 1/z
-            int prim = 0, n_left = 0, x = 0;
-            uint32_t rowaddr = tile_addr;                  // shared address of column 0 of the span's row
+            int prim = 0, n_left = 0;                      // n_left: pixels still to visit, the parked one included
+            uint32_t zrow = plane_addr;                    // shared address of the depth of the row's first pixel IN the tile
+            uint32_t zaddr = plane_addr;                   // ... of the lane's current pixel; below zrow: left of the tile
             bool guarded = false, exhausted = false, pending = false;
             while(true)
             {
-                const bool need = !pending && n_left == 0 && !exhausted;
-                const unsigned need_mask = __ballot_sync(FULL, need);
-                const unsigned busy_mask = __ballot_sync(FULL, n_left > 0 && !pending);
                 const unsigned pend_mask = __ballot_sync(FULL, pending);
+                const unsigned busy_mask = __ballot_sync(FULL, n_left > 0 && !pending);
+                const unsigned need_mask = __ballot_sync(FULL, n_left == 0 && !exhausted);
                 if((need_mask | busy_mask | pend_mask) == 0) break;
 
-                // depth-test passes, projekt.cpp:520-529: pack + one 128-bit compare-and-swap
-                auto resolve_pending = [&]()
+                if(pend_mask && (busy_mask == 0 || __popc(pend_mask) >= kPend))
                 {
-                    const uint32_t pa = rowaddr + (uint32_t)x*16u;
-                    Pixel mine;
-                    mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
-                    if(PHONG && tex_id >= 0)
-                        mine.color = tex_pixel(p.v, p.textures, tex_id, c0, c1, c2, phong_span, n0, n1, n2,
-                                               fadd((float)x, shade_dx), shade_row, z);
-                    else if(MODE == kRasterTextured && tex_id >= 0)
+                    // ---- depth-test passes, projekt.cpp:520-529: pack + one 128-bit compare-and-swap ----
+                    if(pending)
                     {
-                        // projekt.cpp:427-446, unlit: the texel word itself (see tex_pixel)
-                        const TexDesc td = (tex_id < kMaxSharedTex) ? s_tex[tex_id] : p.textures[tex_id];
-                        const float inv = fdiv(1.0f, c2);
-                        const float tx = fmul(fmul(inv, c0), (float)(td.w - 1)), ty = fmul(fmul(inv, c1), (float)(td.h - 1));
-                        const int ix = min(max(round_s32(tx), 0), td.w - 1), iy = min(max(round_s32(ty), 0), td.h - 1);
-                        mine.color = __ldg(reinterpret_cast<const uint32_t *>(
-                            reinterpret_cast<const unsigned char *>(td.mem) + (size_t)iy*(size_t)td.pitch) + ix);
+                        const uint32_t pa = tile_addr + (zaddr - plane_addr)*4u;
+                        const int x = x0 + ((int)(zaddr - zrow) >> 2);
+                        Pixel mine;
+                        mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
+                        if(PHONG && tex_id >= 0)
+                            mine.color = tex_pixel(p.v, p.textures, tex_id, c0, c1, c2, phong_span, n0, n1, n2,
+                                                   fadd((float)x, shade_dx), shade_row, z);
+                        else if(MODE == kRasterTextured && tex_id >= 0)
+                        {
+                            // projekt.cpp:427-446, unlit: the texel word itself (see tex_pixel)
+                            const TexDesc td = (tex_id < kMaxSharedTex) ? s_tex[tex_id] : p.textures[tex_id];
+                            const float inv = fdiv(1.0f, c2);
+                            const float tx = fmul(fmul(inv, c0), (float)(td.w - 1)), ty = fmul(fmul(inv, c1), (float)(td.h - 1));
+                            const int ix = min(max(round_s32(tx), 0), td.w - 1), iy = min(max(round_s32(ty), 0), td.h - 1);
+                            mine.color = __ldg(reinterpret_cast<const uint32_t *>(
+                                reinterpret_cast<const unsigned char *>(td.mem) + (size_t)iy*(size_t)td.pitch) + ix);
+                        }
+                        else
+                            mine.color = (PHONG && phong_span)
+                                         ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
+                                         : pack_argb(c0, c1, c2, c3, guarded);
+                        mine.pad = 0;
+                        Pixel old = lds_pixel(pa);
+                        float now = z;                                              // the word's depth when we leave
+                        while(true)
+                        {
+                            const float oz = __uint_as_float(old.z);
+                            const int op = (int)old.prim;
+                            if(!(z > oz || (z == oz && prim < op))) { now = oz; break; }   // :525 + tie rule
+                            const Pixel prev = cas_pixel(pa, old, mine);
+                            if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
+                            old = prev;
+                        }
+                        sts_depth(zaddr, now);                                      // never above the word's depth
+                        if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
+                        c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
+                        z = fadd(z, zi);                                                              // :535
+                        zaddr += 4u; --n_left;
+                        pending = false;
                     }
-                    else
-                        mine.color = (PHONG && phong_span)
-                                     ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
-                                     : pack_argb(c0, c1, c2, c3, guarded);
-                    mine.pad = 0;
-                    Pixel old = lds_pixel(pa);
-                    while(true)
-                    {
-                        const float oz = __uint_as_float(old.z);
-                        const int op = (int)old.prim;
-                        if(!(z > oz || (z == oz && prim < op))) break;            // :525 + tie rule
-                        const Pixel prev = cas_pixel(pa, old, mine);
-                        if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
-                        old = prev;
-                    }
-                    if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
-                    c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
-                    z = fadd(z, zi);                                                              // :535
-                    ++x; --n_left;
-                    pending = false;
-                };
-
-                if(pend_mask && busy_mask == 0)
-                {
-                    if(pending) resolve_pending();          // nobody else can make progress: flush the parked lanes
-                    continue;
                 }
-
-                if(need_mask && (busy_mask == 0 || __popc(need_mask) >= kRefill))
+                else if(need_mask && (busy_mask == 0 || __popc(need_mask) >= kRefill))
                 {
                     // ---- idle lanes take the next spans of the queue: one ticket per warp ----
+                    const bool need = n_left == 0 && !exhausted;
                     const int leader = __ffs(need_mask) - 1;
                     unsigned base = 0;
                     const unsigned take = (unsigned)__popc(need_mask);
@@ -388,10 +423,10 @@ raster_kernel(const __grid_constant__ RasterParams p)
                                 }
                             }
                             const int xe = min(maxx, xlast);
-                            x = minx;
                             n_left = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
                             if(q3.w < s_rowmin[y - ys0]) n_left = 0;          // cannot win or tie anywhere in its row
-                            rowaddr = tile_addr + (uint32_t)(((y - ys0)*TW - x0)*16);
+                            zrow = plane_addr + (uint32_t)((y - ys0)*TW*4);
+                            zaddr = zrow + (uint32_t)((minx - x0)*4);         // wraps below zrow for pixels left of the tile
                         }
                         else
                         {
@@ -401,45 +436,45 @@ raster_kernel(const __grid_constant__ RasterParams p)
                     continue;
                 }
 
-                // ---- pixel steps, projekt.cpp:423-425, 525, 534-535 (a few per ballot round) ----
-                // A lane whose depth test may pass parks; as soon as kPend lanes of the warp are
-                // parked they run the update together, right here (low-overdraw scenes pass on
+                // ---- kRound pixel steps, projekt.cpp:423-425, 525, 534-535 ----
+                // A lane whose depth test may pass parks at that pixel (pending); the votes at the top of
+                // the loop run the update path once kPend lanes are parked (low-overdraw scenes pass on
                 // nearly every pixel, high-overdraw scenes rarely: both stay converged).
-#pragma unroll
-                for(int u = 0; u < 4; ++u)
                 {
-                    if(n_left > 0 && !pending && x >= x0)
+                    const int m = pending ? 0 : n_left;                       // pixels this lane may visit in this round
+                    const int lo = max((int)(zrow - zaddr), 0);               // bytes until the lane's first pixel IN the tile
+                    float zo[kRound];
+#pragma unroll
+                    for(int k = 0; k < kRound; ++k)
+                        zo[k] = lds_depth_if(zaddr + 4u*k, k < m && 4*k >= lo);   // NaN when not loaded: never >= anything
+                    const int before = n_left;
+#pragma unroll
+                    for(int k = 0; k < kRound; ++k)
                     {
-                        const float zo = lds_depth(rowaddr + (uint32_t)x*16u);
-                        pending = (z >= zo);
+                        pending = pending || (z >= zo[k]);                    // sticky: a parked lane's z no longer moves
+                        if(k < m && !pending)
+                        {
+                            if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
+                            c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
+                            z = fadd(z, zi);                                                              // :535
+                            --n_left;
+                        }
                     }
-                    const bool flush = __popc(__ballot_sync(FULL, pending)) >= kPend;
-                    if(pending)
-                    {
-                        if(flush) resolve_pending();
-                    }
-                    else if(n_left > 0)
-                    {
-                        if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
-                        c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
-                        z = fadd(z, zi);                                                              // :535
-                        ++x; --n_left;
-                    }
+                    zaddr += 4u*(uint32_t)(before - n_left);
                 }
             }
         }
         __syncthreads();
 
-        // ---------------- write the tile back: pack depth to [0,4N), colour to [4N,8N) -----------
+        // ---------------- write the tile back: depth into the plane, colour packed to [0, 4N) ------
         {
             Pixel px[PPT];
 #pragma unroll
             for(int k = 0; k < PPT; ++k) px[k] = tile[tid + k*NT];
             __syncthreads();
-            float *zout = reinterpret_cast<float *>(smem_raw);
-            uint32_t *cout_ = reinterpret_cast<uint32_t *>(smem_raw + NPIX*4);
+            uint32_t *cout_ = reinterpret_cast<uint32_t *>(smem_raw);
 #pragma unroll
-            for(int k = 0; k < PPT; ++k) { zout[tid + k*NT] = __uint_as_float(px[k].z); cout_[tid + k*NT] = px[k].color; }
+            for(int k = 0; k < PPT; ++k) { zplane[tid + k*NT] = __uint_as_float(px[k].z); cout_[tid + k*NT] = px[k].color; }
             __syncthreads();
             if(p.bulk_ok)
             {
@@ -447,7 +482,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
                 __syncthreads();
                 for(int r = tid; r < rows; r += NT)
                 {
-                    bulk_s2g(p.depth + (size_t)(yb + r)*p.depth_stride + x0, zout + r*TW, (uint32_t)(cols*4));
+                    bulk_s2g(p.depth + (size_t)(yb + r)*p.depth_stride + x0, zplane + r*TW, (uint32_t)(cols*4));
                     bulk_s2g(p.color + (size_t)(yb + r)*p.color_pitch_words + x0, cout_ + r*TW, (uint32_t)(cols*4));
                 }
                 bulk_commit();
@@ -457,7 +492,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
                 for(int i = tid; i < rows*cols; i += NT)
                 {
                     const int r = i / cols, c = i % cols;
-                    p.depth[(size_t)(yb + r)*p.depth_stride + x0 + c] = zout[r*TW + c];
+                    p.depth[(size_t)(yb + r)*p.depth_stride + x0 + c] = zplane[r*TW + c];
                     p.color[(size_t)(yb + r)*p.color_pitch_words + x0 + c] = cout_[r*TW + c];
                 }
             }
@@ -466,20 +501,33 @@ raster_kernel(const __grid_constant__ RasterParams p)
     bulk_wait_read();
 }
 
+// cudaFuncSetAttribute and the occupancy answer are per DEVICE: keep them per device ordinal
+// (a process may hold contexts on several GPUs).
 template<int TW, int TH, int WARPS, int MODE>
 static cudaError_t launch_one(const RasterParams &p, int sm_count, cudaStream_t s)
 {
+    constexpr int kMaxDevices = 64;
     const int smem = TileLayout<TW, TH>::kBytes;
     auto kern = raster_kernel<TW, TH, WARPS, MODE>;
-    static bool configured = false;
-    static int per_sm = 1;
-    if(!configured)
+    static std::mutex mu;
+    static int per_sm_of[kMaxDevices] = {};                // 0: not configured on that device yet
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if(e != cudaSuccess) return e;
+    if(dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    int per_sm;
     {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if(e != cudaSuccess) return e;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS*32, smem);
-        if(per_sm < 1) per_sm = 1;
-        configured = true;
+        std::lock_guard<std::mutex> lock(mu);
+        if(per_sm_of[dev] == 0)
+        {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if(e != cudaSuccess) return e;
+            int n = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, WARPS*32, smem);
+            if(e != cudaSuccess) return e;
+            per_sm_of[dev] = n < 1 ? 1 : n;
+        }
+        per_sm = per_sm_of[dev];
     }
     unsigned grid = (unsigned)(sm_count*per_sm);           // persistent: a multiple of the SM count
     if(grid > p.tile_end - p.tile_begin) grid = p.tile_end - p.tile_begin;
@@ -492,11 +540,12 @@ template<int MODE>
 static cudaError_t launch_mode(const RasterParams &p, int sm_count, cudaStream_t s)
 {
     const int tw = p.v.tile_w, th = p.v.tile_h;
-    if(tw == 64 && th == 32) return launch_one<64, 32, 8, MODE>(p, sm_count, s);     // 32 KB tile
-    if(tw == 32 && th == 32) return launch_one<32, 32, 8, MODE>(p, sm_count, s);     // 16 KB
-    if(tw == 128 && th == 16) return launch_one<128, 16, 8, MODE>(p, sm_count, s);   // 32 KB
-    if(tw == 64 && th == 16) return launch_one<64, 16, 8, MODE>(p, sm_count, s);     // 16 KB
-    if(tw == 128 && th == 32) return launch_one<128, 32, 8, MODE>(p, sm_count, s);   // 64 KB
+    if(tw == 64 && th == 32) return launch_one<64, 32, 8, MODE>(p, sm_count, s);     // 40 KB tile
+    if(tw == 32 && th == 32) return launch_one<32, 32, 8, MODE>(p, sm_count, s);     // 20 KB
+    if(tw == 128 && th == 16) return launch_one<128, 16, 8, MODE>(p, sm_count, s);   // 40 KB
+    if(tw == 64 && th == 16) return launch_one<64, 16, 8, MODE>(p, sm_count, s);     // 20 KB
+    if(tw == 128 && th == 32) return launch_one<128, 32, 8, MODE>(p, sm_count, s);   // 80 KB
+    if(tw == 256 && th == 8) return launch_one<256, 8, 8, MODE>(p, sm_count, s);     // 40 KB
     return cudaErrorInvalidValue;
 }
 
