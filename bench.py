@@ -167,13 +167,9 @@ def build_scene(config, rank, scale=1.0):
 
 
 def c5_view(i):
-    """View i of config C5: the reference API has no camera rotation, only Object->P and the
-    pin-hole distance (projekt.cpp:3900, 74-93), so a view is a (P, DistanceAboveTarget) pair on a
-    fixed spiral."""
-    import math
-    a = 2.0 * math.pi * i / 32.0
-    r = 0.15 + 0.45 * i / C5_VIEWS
-    return (r * math.cos(a), 0.6 * r * math.sin(a), 0.0), 3.0 + 1.5 * i / C5_VIEWS
+    """View i of config C5 (cpu_renderer_b200.scene.c5_view)."""
+    from cpu_renderer_b200 import scene as sc
+    return sc.c5_view(i)
 
 
 # ------------------------------------------------------------------------------ reference arm

@@ -135,50 +135,86 @@ def triangle_soup(name, seed, count, width, height, rmin, rmax, chunk=1 << 20, j
     return Scene(name, width, height, tr, pos, col, nrm, uvs)
 
 
+def _libm_table(fn_name: str, angles: np.ndarray) -> np.ndarray:
+    """libm's sinf / cosf on a (small) float32 array -- the functions the reference's Sin / Cos are pinned
+    to.  numpy's own float32 sin/cos are SIMD kernels that may differ in the last
+    bit; the mesh is an INPUT shared bit for bit with the CPU checkers, so it uses the same libm."""
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    fn = getattr(libm, fn_name)
+    fn.argtypes = [ctypes.c_float]
+    fn.restype = ctypes.c_float
+    return np.array([fn(float(a)) for a in angles], dtype=np.float32)
+
+
 def construct_sphere(step_count: int = 24, radius: float = 0.5):
     """Host-side restatement of ConstructSphere (projekt.cpp:4123-4289) with a parametric
-    StepCount (the reference hard-codes 24, :4129).  4*S*S - 4*S triangles.  Used for the
-    C5 mesh; config C1 uses the verbatim sphere stored in tests/golden/."""
+    StepCount (the reference hard-codes 24, :4129).  4*S*S - 4*S triangles.  Bit-identical to the
+    verbatim function at StepCount 24 -- positions, colours, normals and UVs
+    (tests/test_oracle_golden.py) -- and to the oracle's C restatement at the C5 size: the
+    sines and cosines of the 3S + 2 distinct angles come from libm's sinf / cosf, the colour ramp is
+    accumulated row by row (:4286), every product and sum is one binary32 operation."""
     f32 = np.float32
     S = step_count
-    inc_incl = f32(np.pi) / f32(S)
-    inc_azim = f32(2.0 * np.pi) / f32(S * 2)
+    pi32 = f32(3.14159265359)
+    inc_incl = pi32 / f32(S)                                         # :4143
+    inc_azim = (f32(2.0) * pi32) / f32(S * 2)                        # :4144
+    incl = np.arange(S + 1, dtype=f32) * inc_incl                    # (r32)Index*Increment
+    azim = np.arange(2 * S + 1, dtype=f32) * inc_azim
+    si, ci = _libm_table("sinf", incl), _libm_table("cosf", incl)
+    sa, ca = _libm_table("sinf", azim), _libm_table("cosf", azim)
 
-    def point(incl, azim):
-        si, ci = np.sin(incl).astype(f32), np.cos(incl).astype(f32)
-        return np.stack([si * np.cos(azim).astype(f32), ci, si * np.sin(azim).astype(f32)], -1)
+    def point(i, a):                                                 # [len(i), len(a), 3]
+        return np.stack([si[i][:, None] * ca[a][None, :], np.broadcast_to(ci[i][:, None], (len(i), len(a))),
+                         si[i][:, None] * sa[a][None, :]], -1).astype(f32)
 
-    ii, aa = np.meshgrid(np.arange(S, dtype=f32), np.arange(2 * S, dtype=f32), indexing="ij")
-    incl, nincl = ii * inc_incl, (ii + 1) * inc_incl
-    azim, nazim = aa * inc_azim, (aa + 1) * inc_azim
-    p1, p2 = point(incl, azim), point(nincl, azim)
-    p3, p4 = point(nincl, nazim), point(incl, nazim)
-    up = np.zeros_like(p1); up[..., 1] = 1.0
-    down = np.zeros_like(p1); down[..., 1] = -1.0
-    blue = ((f32(1.0) + np.cos(azim).astype(f32)) / f32(2.0))
-    nblue = ((f32(1.0) + np.cos(nazim).astype(f32)) / f32(2.0))
-    cur_r = f32(1.0) + ii * (f32(-1.0) / f32(S))      # red 1 -> 0, green 0 -> 1 (:4131-4141)
-    cur_g = ii * (f32(1.0) / f32(S))
-    nxt_r = cur_r + f32(-1.0) / f32(S)
-    nxt_g = cur_g + f32(1.0) / f32(S)
+    I, A = np.arange(S), np.arange(2 * S)
+    p1, p2, p3, p4 = point(I, A), point(I + 1, A), point(I + 1, A + 1), point(I, A + 1)
+    blue = ((f32(1.0) + ca[A]) / f32(2.0)).astype(f32)               # :4165
+    nblue = ((f32(1.0) + ca[A + 1]) / f32(2.0)).astype(f32)
+    # colour ramp: CurrentColor += ColorIncrement after every inclination row (:4286), sequentially
+    up, down = np.array([1, 0, 0, 1], f32), np.array([0, 1, 0, 1], f32)
+    inc = ((down - up) / f32(S)).astype(f32)                         # :4135-4141
+    cur = np.empty((S, 4), f32)
+    c = up.copy()
+    for i in range(S):
+        cur[i] = c
+        c = (c + inc).astype(f32)
+    nxt = (cur + inc[None, :]).astype(f32)                           # CurrentColor + ColorIncrement
 
-    def colour(r, g, b):
-        return np.stack([r, g, b, np.ones_like(r)], -1).astype(f32)
+    def colour(base, b):                                             # base [S,4], b [2S] -> [S, 2S, 4]
+        out = np.broadcast_to(base[:, None, :], (S, 2 * S, 4)).copy()
+        out = (out + f32(0.0)).astype(f32)
+        out[..., 2] = (base[:, None, 2] + b[None, :]).astype(f32)
+        return out
 
-    c_cur_b, c_nxt_b = colour(cur_r, cur_g, blue), colour(nxt_r, nxt_g, blue)
-    c_nxt_nb, c_cur_nb = colour(nxt_r, nxt_g, nblue), colour(cur_r, cur_g, nblue)
-    top_p = np.stack([up[0], p2[0], p3[0]], 1)                       # [2S, 3, 3]   (:4156-4189)
-    top_c = np.stack([c_cur_b[0], c_nxt_b[0], c_nxt_nb[0]], 1)
-    bot_p = np.stack([p1[S - 1], down[S - 1], p4[S - 1]], 1)        # (:4190-4223)
-    bot_c = np.stack([c_cur_b[S - 1], c_nxt_b[S - 1], c_nxt_nb[S - 1]], 1)
+    c_cb, c_nb, c_nnb, c_cnb = colour(cur, blue), colour(nxt, blue), colour(nxt, nblue), colour(cur, nblue)
+
+    def uv_mid(p):
+        return np.stack([(p[..., 0] + f32(1.0)) / f32(2.0), (p[..., 1] + f32(1.0)) / f32(2.0)], -1).astype(f32)
+
+    def uv_pole(p):
+        return np.stack([p[..., 0], p[..., 2]], -1).astype(f32)
+
+    half = np.full((2 * S, 2), 0.5, f32)
+    north = np.broadcast_to(np.array([0, 1, 0], f32), (2 * S, 3))
+    south = np.broadcast_to(np.array([0, -1, 0], f32), (2 * S, 3))
+    top_p = np.stack([north, p2[0], p3[0]], 1)                       # [2S, 3, 3]   (:4156-4189)
+    top_c = np.stack([c_cb[0], c_nb[0], c_nnb[0]], 1)
+    top_u = np.stack([half, uv_pole(p2[0]), uv_pole(p3[0])], 1)
+    bot_p = np.stack([p1[S - 1], south, p4[S - 1]], 1)               # (:4190-4223)
+    bot_c = np.stack([c_cb[S - 1], c_nb[S - 1], c_nnb[S - 1]], 1)
+    bot_u = np.stack([half, uv_pole(south), uv_pole(p4[S - 1])], 1)
     m = slice(1, S - 1)                                              # (:4224-4281) two per cell
     mid_p = np.stack([np.stack([p1[m], p2[m], p3[m]], 2), np.stack([p1[m], p3[m], p4[m]], 2)], 2)
-    mid_c = np.stack([np.stack([c_cur_b[m], c_nxt_b[m], c_nxt_nb[m]], 2),
-                      np.stack([c_cur_b[m], c_nxt_nb[m], c_cur_nb[m]], 2)], 2)
+    mid_c = np.stack([np.stack([c_cb[m], c_nb[m], c_nnb[m]], 2),
+                      np.stack([c_cb[m], c_nnb[m], c_cnb[m]], 2)], 2)
+    mid_u = uv_mid(mid_p)
     nrm = np.concatenate([top_p.reshape(-1, 3), mid_p.reshape(-1, 3), bot_p.reshape(-1, 3)]).astype(f32)
     col = np.concatenate([top_c.reshape(-1, 4), mid_c.reshape(-1, 4), bot_c.reshape(-1, 4)]).astype(f32)
+    uvs = np.concatenate([top_u.reshape(-1, 2), mid_u.reshape(-1, 2), bot_u.reshape(-1, 2)]).astype(f32)
     pos = (f32(radius) * nrm).astype(f32)
-    uvs = np.zeros((pos.shape[0], 2), dtype=f32)
     return pos, col, nrm, uvs
 
 
@@ -198,6 +234,28 @@ CONFIGS = {
     "c3": dict(seed=0xB2000003, count=50_000, width=3840, height=2160, rmin=32.0, rmax=96.0),
     "c4": dict(seed=0xB2000004, count=20_000_000, width=16384, height=16384, rmin=2.0, rmax=10.0),
 }
+
+
+C5_VIEWS = 256
+C5_STEP_COUNT = 708            # ConstructSphere at StepCount 708: 2 002 224 triangles
+
+
+def c5_view(i: int):
+    """View i of config C5 -> (Object->P, DistanceAboveTarget).  The reference API has no camera
+    rotation, only Object->P and the pin-hole distance (projekt.cpp:3900, 74-93), so a view is a
+    (P, DistanceAboveTarget) pair on a fixed spiral."""
+    import math
+    a = 2.0 * math.pi * i / 32.0
+    r = 0.15 + 0.45 * i / C5_VIEWS
+    return (r * math.cos(a), 0.6 * r * math.sin(a), 0.0), 3.0 + 1.5 * i / C5_VIEWS
+
+
+def c5_scene(mesh, view: int, width: int = 1920, height: int = 1080) -> "Scene":
+    """The C5 frame of one view: the sphere mesh (construct_sphere output) at that view's P and distance."""
+    P, D = c5_view(view)
+    s = sphere_scene(*mesh, width, height, 500.0, name=f"c5_view{view}", object_p=P)
+    s.transform.distance_above_target = D
+    return s
 
 
 def make_texture(width: int, height: int, seed: int = 0x7E57) -> np.ndarray:

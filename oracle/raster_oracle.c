@@ -813,3 +813,75 @@ void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
     render_one_tex(Ctx->Pos, Ctx->Col, Ctx->Nrm, Ctx->UV, TriangleIndex, Ctx->P, Ctx->Scene, Ctx->Phong,
                    Ctx->Texture, &T, (int32_t)TriangleIndex, 0);
 }
+
+
+/* ---- ConstructSphere, projekt.cpp:4123-4289, with StepCount as a parameter (the reference
+ * hard-codes 24, :4129).  Same operations in the same order on binary32: Sin/Cos are libm's
+ * sinf/cosf (ref_shim.h pins them the same way), the colour ramp is accumulated row by row
+ * (:4286), pole UVs are (x, z) of the unit vertex (:4180, :4186), the others (x+1)/2, (y+1)/2.
+ * Pinned at StepCount 24 against the verbatim function (tests/test_oracle_golden.py); config C5
+ * uses StepCount 708.  Returns the vertex count: 3*(4*S*S - 4*S) for S >= 2. */
+static void sphere_vertex(float Sx, float Sy, float Sz, float Radius, float U, float V, const float Color[4],
+                          float *Pos, float *Col, float *Nrm, float *UV, uint32_t At)
+{
+    Pos[3*At + 0] = Radius*Sx; Pos[3*At + 1] = Radius*Sy; Pos[3*At + 2] = Radius*Sz;
+    Nrm[3*At + 0] = Sx; Nrm[3*At + 1] = Sy; Nrm[3*At + 2] = Sz;
+    UV[2*At + 0] = U; UV[2*At + 1] = V;
+    for(int i = 0; i < 4; ++i) Col[4*At + i] = Color[i];
+}
+
+uint32_t orc_construct_sphere(uint32_t StepCount, float *Pos, float *Col, float *Nrm, float *UV)
+{
+    uint32_t N = 0;
+    const float Radius = 0.5f;
+    const float Pi32 = 3.14159265359f;
+    const float Up[4] = {1.0f, 0.0f, 0.0f, 1.0f}, Down[4] = {0.0f, 1.0f, 0.0f, 1.0f};
+    float Inc[4], Cur[4];
+    for(int i = 0; i < 4; ++i) { Inc[i] = (Down[i] - Up[i])/(float)StepCount; Cur[i] = Up[i]; }   /* :4135-4141 */
+    const float InclInc = Pi32/StepCount;                                   /* :4143 */
+    const float AzimInc = (2.0f*Pi32)/(StepCount*2);                        /* :4144 */
+    for(uint32_t Ii = 0; Ii < StepCount; ++Ii)
+    {
+        for(uint32_t Ai = 0; Ai < StepCount*2; ++Ai)
+        {
+            const float Incl = (float)Ii*InclInc, NIncl = (float)(Ii + 1)*InclInc;
+            const float Azim = (float)Ai*AzimInc, NAzim = (float)(Ai + 1)*AzimInc;
+            const float Blue = (1.0f + cosf(Azim))/2.0f, NBlue = (1.0f + cosf(NAzim))/2.0f;
+            float CB[4], NB[4], NNB[4], CNB[4];     /* Cur+Blue, Cur+Inc+Blue, Cur+Inc+NextBlue, Cur+NextBlue */
+            for(int i = 0; i < 4; ++i)
+            {
+                const float b = (i == 2) ? Blue : 0.0f, nb = (i == 2) ? NBlue : 0.0f;
+                CB[i] = Cur[i] + b; NB[i] = (Cur[i] + Inc[i]) + b; NNB[i] = (Cur[i] + Inc[i]) + nb; CNB[i] = Cur[i] + nb;
+            }
+            const float P1[3] = { sinf(Incl)*cosf(Azim), cosf(Incl), sinf(Incl)*sinf(Azim) };
+            const float P2[3] = { sinf(NIncl)*cosf(Azim), cosf(NIncl), sinf(NIncl)*sinf(Azim) };
+            const float P3[3] = { sinf(NIncl)*cosf(NAzim), cosf(NIncl), sinf(NIncl)*sinf(NAzim) };
+            const float P4[3] = { sinf(Incl)*cosf(NAzim), cosf(Incl), sinf(Incl)*sinf(NAzim) };
+            if(Ii == 0)                                                     /* :4156-4189 */
+            {
+                sphere_vertex(0.0f, 1.0f, 0.0f, Radius, 0.5f, 0.5f, CB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P2[0], P2[1], P2[2], Radius, P2[0], P2[2], NB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P3[0], P3[1], P3[2], Radius, P3[0], P3[2], NNB, Pos, Col, Nrm, UV, N++);
+            }
+            else if(Ii == StepCount - 1)                                    /* :4190-4223 */
+            {
+                sphere_vertex(P1[0], P1[1], P1[2], Radius, 0.5f, 0.5f, CB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(0.0f, -1.0f, 0.0f, Radius, 0.0f, 0.0f, NB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P4[0], P4[1], P4[2], Radius, P4[0], P4[2], NNB, Pos, Col, Nrm, UV, N++);
+            }
+            else                                                            /* :4224-4281 */
+            {
+#define ORC_UV(P) ((P)[0] + 1.0f)/2.0f, ((P)[1] + 1.0f)/2.0f
+                sphere_vertex(P1[0], P1[1], P1[2], Radius, ORC_UV(P1), CB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P2[0], P2[1], P2[2], Radius, ORC_UV(P2), NB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P3[0], P3[1], P3[2], Radius, ORC_UV(P3), NNB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P1[0], P1[1], P1[2], Radius, ORC_UV(P1), CB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P3[0], P3[1], P3[2], Radius, ORC_UV(P3), NNB, Pos, Col, Nrm, UV, N++);
+                sphere_vertex(P4[0], P4[1], P4[2], Radius, ORC_UV(P4), CNB, Pos, Col, Nrm, UV, N++);
+#undef ORC_UV
+            }
+        }
+        for(int i = 0; i < 4; ++i) Cur[i] = Cur[i] + Inc[i];               /* :4286 */
+    }
+    return N;
+}

@@ -173,6 +173,10 @@ typedef struct orc_fallback_ctx {
 void orc_ref_fallback(void *User, uint32_t TriangleIndex, void *RefLoadedBitmap,
                       void *RefGameRenderCommands);
 
+/* ConstructSphere (projekt.cpp:4123-4289) with StepCount as a parameter; arrays sized for
+ * 3*(4*S*S - 4*S) vertices.  Returns the vertex count. */
+uint32_t orc_construct_sphere(uint32_t StepCount, float *Pos, float *Col, float *Nrm, float *UV);
+
 #ifdef __cplusplus
 }
 #endif

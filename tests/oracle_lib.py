@@ -194,6 +194,8 @@ def oracle():
                                                 C.POINTER(OrcScene), C.POINTER(OrcTarget),
                                                 C.c_uint32, C.POINTER(OrcStats)]
         lib.orc_render_triangles_mt.restype = C.c_int32
+        lib.orc_construct_sphere.argtypes = [C.c_uint32, f32p, f32p, f32p, f32p]
+        lib.orc_construct_sphere.restype = C.c_uint32
         _oracle = lib
     return _oracle
 
@@ -455,6 +457,18 @@ def ref_sphere():
     n = lib.ref_construct_sphere(pos.ctypes.data_as(f32p), col.ctypes.data_as(f32p),
                                  nrm.ctypes.data_as(f32p), uvs.ctypes.data_as(f32p))
     return pos[:n].copy(), col[:n].copy(), nrm[:n].copy(), uvs[:n].copy()
+
+
+def oracle_sphere(step_count: int):
+    """The oracle's C restatement of ConstructSphere with a StepCount parameter (projekt.cpp:4123-4289)."""
+    lib = oracle()
+    nv = 3 * (4 * step_count * step_count - 4 * step_count)
+    pos = np.zeros((nv, 3), np.float32); col = np.zeros((nv, 4), np.float32)
+    nrm = np.zeros((nv, 3), np.float32); uvs = np.zeros((nv, 2), np.float32)
+    n = lib.orc_construct_sphere(step_count, pos.ctypes.data_as(f32p), col.ctypes.data_as(f32p),
+                                 nrm.ctypes.data_as(f32p), uvs.ctypes.data_as(f32p))
+    assert n == nv, (n, nv)
+    return pos, col, nrm, uvs
 
 
 def fnv1a64_words(a: np.ndarray) -> str:

@@ -867,6 +867,60 @@ def test_c3_full_size(renderer):
     check(renderer, s, tile=(128, 16), want=want)
 
 
+def test_c4_full_geometry_in_eight_row_bands(renderer):
+    """Config C4's geometry at full size -- a 16384 x 16384 target split into the 8 row bands of an 8-GPU run
+    (shard.band_rows) -- with 1/50 of its triangles (400 000, same generator and seed): every band rendered
+    on its own through the device-resident call (BandFirstRow / BandRows; meshes of this size go through the
+    row-band pre-selection), compared with the matching rows of the oracle's single full-frame image."""
+    s = sc.make_config("c4", 0.02)
+    assert (s.width, s.height, s.triangle_count) == (16384, 16384, 400_000)
+    want = ol.oracle_render(s, threads=4)              # every oracle worker owns a private 2 GiB target pair
+    assert want["stats"]["Fragments"] > 20e6
+    covered = 0
+    for rank in range(8):
+        first, rows = shard.band_rows(s.height, 8, rank, 32)
+        assert rows == 2048
+        c, z = _device_render(renderer, s, (64, 32), first, rows)
+        d = diff(want["color"][first:first + rows], want["z"][first:first + rows], c, z, s.clear_depth)
+        assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), (rank, d)
+        covered += int((z != np.float32(s.clear_depth)).sum())
+    assert covered == int((want["z"] != np.float32(s.clear_depth)).sum()) > 15e6
+
+
+@pytest.mark.parametrize("steps,views", [(96, (0, 85, 170, 255)), (sc.C5_STEP_COUNT, (37,))])
+def test_c5_views_of_the_sphere_mesh(renderer, steps, views):
+    """Config C5: views (Object->P, DistanceAboveTarget pairs, scene.c5_view) of the ConstructSphere mesh --
+    four views of the StepCount-96 mesh and one of the full 2 002 224-triangle mesh -- through the
+    device-resident call, one frame per view as a rank of the frame-parallel split renders them, against the
+    oracle (one triangle = one object).  The mesh itself is a pinned input (test_c5_mesh_is_a_pinned_input)."""
+    mesh = sc.construct_sphere(steps)
+    for view in views:
+        s = sc.c5_scene(mesh, view)
+        want = ol.oracle_render(s, threads=8)
+        c, z = _device_render(renderer, s, (64, 32), 0, s.height)
+        d = diff(want["color"], want["z"], c, z, s.clear_depth)
+        assert d == dict(zdiff=0, covdiff=0, cdiff=0, maxlsb=0), (view, d)
+        assert int((z != np.float32(s.clear_depth)).sum()) > 30_000
+
+
+@pytest.mark.skipif(not ol.ref_available(), reason="no verbatim reference build")
+def test_the_oracle_port_is_the_verbatim_reference_here_too():
+    """The GPU tests compare against the port (oracle/raster_oracle.c).  Its pin to the verbatim reference
+    build is re-checked on this machine as part of the GPU suite: per-triangle FillEdgeTable + DrawModel of
+    the prebuilt oracle/_ref against the port, bit for bit, and the same crash prediction."""
+    s = sc.triangle_soup("pin", 0x9173, 30_000, 1280, 720, 1.0, 24.0, jitter=2.5)
+    o = ol.oracle_render(s)
+    r = ol.ref_render_triangles(s)
+    assert np.array_equal(r["status"] == -2, o["would_crash"].astype(bool))
+    r2 = ol.ref_render_triangles(s, skip=o["would_crash"], use_fallback=True)
+    assert np.array_equal(r2["z"].view(np.uint32), o["z"].view(np.uint32)) and np.array_equal(r2["color"], o["color"])
+    e_ref, n_ref = ol.ref_edge_table(s)
+    e_orc, n_orc = ol.oracle_edge_table(s)
+    assert n_ref == n_orc
+    for f in ol.GOURAUD_FIELDS:
+        assert np.array_equal(np.ascontiguousarray(e_ref[f]).view(np.uint32), np.ascontiguousarray(e_orc[f]).view(np.uint32)), f
+
+
 def test_idempotence_and_order_independence_properties(renderer):
     """Size-independent properties: rendering the same scene twice changes nothing (equal depth
     never replaces, projekt.cpp:525), and two disjoint halves submitted as two objects equal one."""

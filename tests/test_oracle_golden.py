@@ -23,14 +23,52 @@ def sphere(tag):
     return sc.sphere_scene(MESH["pos"], MESH["col"], MESH["nrm"], MESH["uvs"], w, h, m2p)
 
 
-def test_sphere_mesh_matches_construct_sphere_shape():
-    # ConstructSphere, projekt.cpp:4123: 6 624 vertices / 2 208 triangles
+def _same_bits(a, b):
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_sphere_mesh_matches_construct_sphere_bit_for_bit():
+    """ConstructSphere, projekt.cpp:4123-4289: 6 624 vertices / 2 208 triangles.  The
+    verbatim mesh (golden), the oracle's C restatement and the product-side generator (scene.construct_sphere)
+    agree on every bit of positions, colours, normals AND UVs at the reference's StepCount 24."""
     assert MESH["pos"].shape == (6624, 3)
-    pos, col, nrm, _ = sc.construct_sphere(24)
-    assert pos.shape == (6624, 3)
-    # the numpy restatement follows the same construction (libm sin/cos may differ in the last bit)
-    assert np.allclose(pos, MESH["pos"], atol=1e-6) and np.allclose(col, MESH["col"], atol=1e-6)
-    assert np.allclose(nrm, MESH["nrm"], atol=1e-6)
+    for name, mesh in (("oracle", ol.oracle_sphere(24)), ("scene", sc.construct_sphere(24))):
+        for arr, key in zip(mesh, ("pos", "col", "nrm", "uvs")):
+            assert _same_bits(arr, MESH[key]), (name, key)
+    # pole UVs are (x, z) of the unit vertex, i.e. outside [0, 1] (projekt.cpp:4180, SURVEY.md Appendix B)
+    assert MESH["uvs"].min() < 0.0
+
+
+# mesh_digest of the C5 mesh (StepCount 708: 2 002 224 triangles) and of a smaller one
+C5_MESH_DIGEST = {96: "4683801acab0ae35", 708: "83120bd33810cd83"}
+
+
+@pytest.mark.parametrize("steps", [96, 708])
+def test_c5_mesh_is_a_pinned_input(steps):
+    """Config C5's mesh is ConstructSphere at StepCount 708 (the reference hard-codes 24): the product-side
+    generator and the oracle's C restatement -- the one pinned to the verbatim function above -- produce the
+    same bits, and the committed hash pins them across machines."""
+    a, b = sc.construct_sphere(steps), ol.oracle_sphere(steps)
+    assert a[0].shape[0] == 3 * (4 * steps * steps - 4 * steps)
+    for x, y, key in zip(a, b, ("pos", "col", "nrm", "uvs")):
+        assert _same_bits(x, y), key
+    assert mesh_digest(a) == C5_MESH_DIGEST[steps]
+
+
+def mesh_digest(mesh):
+    """Order-sensitive 64-bit digest of the four vertex streams: per stream a position-weighted xor and a
+    plain sum of its 32-bit words, folded FNV-style (a word-by-word Python loop over 60 M words is too slow)."""
+    acc = []
+    with np.errstate(over="ignore"):
+        for m in mesh:
+            w = np.ascontiguousarray(m).view(np.uint32).ravel().astype(np.uint64)
+            idx = np.arange(w.size, dtype=np.uint64)
+            acc.append(int(np.bitwise_xor.reduce((w + np.uint64(1)) * (idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1)))))
+            acc.append(int(w.sum(dtype=np.uint64)))
+    h = 0xcbf29ce484222325
+    for v in acc:
+        h = ((h ^ v) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
 
 
 @pytest.mark.parametrize("tag", ["c1_1080p", "c1_540p"])
