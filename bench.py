@@ -48,7 +48,7 @@ METRICS = {
 # c2/c3: every rank renders its own frame (weak).  c4: one frame split in row bands, c5: a fixed
 # set of 256 views split over the ranks (strong: the total work does not grow with N).
 SCALING = {"c1": "weak", "c2": "weak", "c3": "weak", "c4": "strong", "c5": "strong"}
-C5_VIEWS = 256
+C5_VIEWS = 256             # cpu_renderer_b200.scene.C5_VIEWS
 TEX_SIZE = 1024                # --textured: the objects' Bitmap is TEX_SIZE x TEX_SIZE ARGB8
 
 
@@ -308,45 +308,74 @@ def time_cpu(ol, s, threads, steps, warmup, kind, phong=False):
 
 
 # ------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from cpu_renderer_b200 import api
+PASSES = 5                     # timed passes of exactly K steps each; the line reports median and best
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
-    from cpu_renderer_b200 import shard
+class Ctx:
+    """What every leg of one bench process shares: rank geometry, device, stream, one renderer."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from cpu_renderer_b200 import api
+        self.torch, self.dist, self.api, self.args = torch, dist, api, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.r = api.Renderer(self.local_rank)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+
+def expected_hashes():
+    p = os.path.join(ROOT, "tests", "golden", "bench_image_hashes.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textured=False, tile=None,
+            e2e_steps=10, cpu_baseline=False, c1_whole_object=False):
+    """One configuration, measured three ways: device-resident frames (CUDA events, `passes` passes of
+    exactly K steps, max over ranks per pass), per-kernel durations, and end to end with host buffers."""
+    torch, dist, api = ctx.torch, ctx.dist, ctx.api
+    from cpu_renderer_b200 import imagehash, shard
+    from cpu_renderer_b200 import scene as sc
     import copy
-    unit, workload = METRICS[args.config]
-    cfgname = args.config
-    scene = build_scene(cfgname, rank, args.scale)
-    if args.textured:
-        from cpu_renderer_b200 import scene as sc_
-        scene = sc_.textured(scene, TEX_SIZE, TEX_SIZE, lo=0.05, hi=0.95)
+    rank, world, dev, stream, r, args = ctx.rank, ctx.world, ctx.dev, ctx.stream, ctx.r, ctx.args
+    unit, workload = METRICS[cfgname]
+    scene = build_scene(cfgname, rank, scale)
+    if textured:
+        scene = sc.textured(scene, TEX_SIZE, TEX_SIZE, lo=0.05, hi=0.95)
     ntri, W, H = scene.triangle_count, scene.width, scene.height
-    K, Wm = args.steps, args.warmup
     wpad = (W + 63) // 64 * 64
-
-    stream = torch.cuda.Stream(device=dev)
-    r = api.Renderer(local_rank)
-    tile = args.tile or {"c3": "128x16", "c4": "64x32"}.get(cfgname, "64x32")
+    tile = tile or {"c3": "128x16", "c4": "64x32"}.get(cfgname, "64x32")
     tw, th = (int(x) for x in tile.split("x"))
-    r.set_tile(tw, th)
     r.set_stream(stream.cuda_stream)
+    r.set_tile(tw, th)
+    flags = api.DEFER_VERDICT if args.defer_verdict else 0
 
     d_pos = torch.from_numpy(scene.positions).to(dev)
     d_col = torch.from_numpy(scene.colors).to(dev)
     d_nrm = torch.from_numpy(scene.normals).to(dev)
     mesh_uv, mesh_tex = None, None
-    if args.textured:
+    if textured:
         d_uv = torch.from_numpy(scene.uvs).to(dev)
         d_tex = torch.from_numpy(scene.texture.view(np.int32)).to(dev)
         dtex = api.device_texture(d_tex.data_ptr(), scene.texture.shape[1], scene.texture.shape[0], scene.texture.shape[1] * 4)
@@ -354,7 +383,7 @@ def run_ours(args):
 
     # ---- the frames this rank renders in one step ------------------------------------------
     band_first, band_rows = 0, H
-    mesh_flags = api.MESH_PHONG if args.phong else 0
+    mesh_flags = api.MESH_PHONG if phong else 0
     frames = []                                   # (device_mesh, game_render_commands, keepalive)
     if cfgname == "c4":
         band_first, band_rows = shard.band_rows(H, world, rank, th)
@@ -371,8 +400,7 @@ def run_ours(args):
         cmd0, keep0 = api.make_commands(scene)
         frames.append((api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri,
                                        api.v3(*scene.object_p), mesh_flags, mesh_uv, mesh_tex), cmd0, keep0))
-    mesh, cmd, keep = frames[0]
-    # c2/c3: one pre-cleared target pair per timed frame (clear outside the timed region).
+    # c1/c2/c3: one pre-cleared target pair per timed frame (clear outside the timed region).
     # c4/c5: one pair, cleared inside the step (a 16K^2 pair is 2 GiB; a real frame clears anyway).
     clear_in_step = cfgname in ("c4", "c5")
     nsets = 1 if clear_in_step else max(K, Wm, 1)
@@ -391,59 +419,63 @@ def run_ours(args):
         for (m_, c_, _) in frames:
             if clear_in_step:
                 r.clear_device(t, scene.clear_color, scene.clear_depth)
-            r.render_device([m_], c_, t)
+            r.render_device([m_], c_, t, flags)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-
-    # ---- device-resident throughput: W warm-up frames, then exactly K timed frames ----------
+    # ---- device-resident throughput: W warm-up steps, then `passes` passes of exactly K steps ----
     clear_all()
     with torch.cuda.stream(stream):
         for i in range(Wm):
             step(i)
         r.sync()
-    clear_all()                                   # every timed frame starts from cleared targets
-    launches0 = r.stats()["KernelLaunches"]
-    barrier(); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        for i in range(K):
-            step(i)
-        ev1.record(stream)
-        r.sync()
-    torch.cuda.synchronize(); barrier()
-    ms_local = ev0.elapsed_time(ev1) / K
-    launches = r.stats()["KernelLaunches"] - launches0
+    pass_ms, launches = [], 0
+    for _ in range(passes):
+        clear_all()                               # every timed frame starts from cleared targets
+        launches0 = r.stats()["KernelLaunches"]
+        ctx.barrier(); torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for i in range(K):
+                step(i)
+            ev1.record(stream)
+            r.sync()
+        torch.cuda.synchronize(); ctx.barrier()
+        pass_ms.append(ev0.elapsed_time(ev1) / K)
+        launches = r.stats()["KernelLaunches"] - launches0
     stats = r.stats()
-    ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms = float(ms_t.item())
+    pass_ms = ctx.max_over_ranks(pass_ms)         # per pass: the slowest rank
+    ms, ms_best = float(np.median(pass_ms)), float(min(pass_ms))
+
+    # ---- the frame itself: hash of what rank 0 holds after one step (c4: gathered below) ------
+    clear_all()
+    with torch.cuda.stream(stream):
+        step(0)
+        r.sync()
+    torch.cuda.synchronize()
+    image_fnv = imagehash.image_fnv_torch(colors[0], W) if (world == 1 or cfgname != "c4") else None
 
     # ---- per-kernel durations (CUDA events on the launching stream, separate pass) ---------
     clear_all()
     r.set_profiling(True)
     stage = {k: [] for k in api.STAGES}
-    t_end = time.time() + 1.0
+    t_end = time.time() + (1.0 if not clear_in_step else 0.3)
     with torch.cuda.stream(stream):
         i = 0
         while i < min(K, 8) or (time.time() < t_end and i < 64 * K):
             if i % nsets == 0 and i:
                 clear_all()
             m_, c_, _ = frames[i % len(frames)]
+            if clear_in_step:
+                r.clear_device(targets[0], scene.clear_color, scene.clear_depth)
             r.render_device([m_], c_, targets[i % nsets])
             for k, v in r.stage_ms().items():
                 stage[k].append(v)
             i += 1
     r.set_profiling(False)
-    stage_ms = {k: float(np.mean(v)) for k, v in stage.items()}
+    stage_ms = {k: float(np.median(v)) for k, v in stage.items()}
     dominant = max(stage_ms, key=stage_ms.get)
 
-    # ---- optional: NCCL gather of the finished colour images to rank 0 ----------------------
+    # ---- NCCL gather of the finished colour images to rank 0 (the path's only exchange step) ----
     with_gather = None
     if world > 1:
         clear_all()
@@ -452,49 +484,58 @@ def run_ours(args):
         else:
             gl = [torch.empty_like(colors[0]) for _ in range(world)] if rank == 0 else None
             gather = lambda t: dist.gather(t, gl, dst=0)                             # noqa: E731
+        gathered = None
         with torch.cuda.stream(stream):
             for _ in range(2):                         # communicator set-up and warm-up, untimed
-                gather(colors[0])
-        barrier(); torch.cuda.synchronize()
+                step(0)
+                gathered = gather(colors[0])
+        ctx.barrier(); torch.cuda.synchronize()
+        if cfgname == "c4" and rank == 0:
+            image_fnv = imagehash.image_fnv_torch(gathered, W)      # the image the bands reassemble to
+        del gathered
         kg = min(K, 10)
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            for i in range(kg):
-                step(i)
-                gather(colors[i % nsets])              # stream-ordered after this step's kernels
-            ev1.record(stream)
-        torch.cuda.synchronize(); barrier()
-        g = torch.tensor([ev0.elapsed_time(ev1) / kg], dtype=torch.float64, device=dev)
-        dist.all_reduce(g, op=dist.ReduceOp.MAX)
-        with_gather = {"ms_per_step": float(g.item()), "what": "NCCL gather of the finished colour image(s) to rank 0 after every step",
+        g_ms = []
+        for _ in range(3):
+            with torch.cuda.stream(stream):
+                ev0.record(stream)
+                for i in range(kg):
+                    step(i)
+                    gather(colors[i % nsets])          # stream-ordered after this step's kernels
+                ev1.record(stream)
+            torch.cuda.synchronize(); ctx.barrier()
+            g_ms.append(ev0.elapsed_time(ev1) / kg)
+        g_ms = ctx.max_over_ranks(g_ms)
+        with_gather = {"ms_per_step": float(np.median(g_ms)), "ms_per_step_best": float(min(g_ms)),
+                       "what": "NCCL gather of the finished colour image(s) to rank 0 after every step (torch.distributed.gather)",
                        "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1))}
 
     whole_object = None
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region ---------
     pin = lambda a: torch.from_numpy(a).pin_memory()              # noqa: E731
-    from cpu_renderer_b200 import scene as sc
-    if not clear_in_step:
-        # c2/c3: the reference-facing call b200r_render_objects (H2D vertices + targets, kernels, D2H targets)
+    e2e = None
+    if e2e_steps > 0 and not clear_in_step:
+        # c1/c2/c3: the reference-facing call b200r_render_objects (H2D vertices + targets, kernels, D2H targets)
         r.set_stream(0)
-        e2e_steps = min(K, 10)
+        e2e_steps = min(K, e2e_steps)
         hs = sc.Scene(scene.name, W, H, scene.transform, pin(scene.positions).numpy(), pin(scene.colors).numpy(),
-                      pin(scene.normals).numpy(), pin(scene.uvs).numpy() if args.textured else scene.uvs,
+                      pin(scene.normals).numpy(), pin(scene.uvs).numpy() if textured else scene.uvs,
                       scene.object_p, scene.ambient, scene.lights,
-                      texture=pin(scene.texture.view(np.int32)).numpy().view(np.uint32) if args.textured else None)
+                      texture=pin(scene.texture.view(np.int32)).numpy().view(np.uint32) if textured else None)
         hcol = [torch.full((H, W), scene.clear_color, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
                 for _ in range(e2e_steps + 1)]
         hz = [torch.full((H, W), scene.clear_depth, dtype=torch.float32).pin_memory().numpy()
               for _ in range(e2e_steps + 1)]
-        r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps], phong=args.phong)       # warm-up (allocations)
-        barrier(); torch.cuda.synchronize()
+        r.render_scene_host(hs, hcol[e2e_steps], hz[e2e_steps], phong=phong)       # warm-up (allocations)
+        ctx.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            r.render_scene_host(hs, hcol[i], hz[i], phong=args.phong)
+            r.render_scene_host(hs, hcol[i], hz[i], phong=phong)
         torch.cuda.synchronize()
         e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
         covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
+        e2e_fnv = imagehash.image_fnv_numpy(hcol[0])
         e2e_api = "b200r_render_objects (host pointers, pinned)"
-        if cfgname == "c1" and rank == 0:
+        if c1_whole_object and rank == 0:
             # the same frame as ONE object through the whole-object mode, beside the
             # verbatim reference's own call pair on one host core (it is a single-threaded path)
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -503,10 +544,10 @@ def run_ours(args):
             wo_z = [z_.copy() for z_ in hz[:3]]
             for c_, z_ in zip(wo_c, wo_z):
                 c_.fill(scene.clear_color); z_.fill(scene.clear_depth)
-            r.render_scene_host(hs, wo_c[2], wo_z[2], flags=api.WHOLE_OBJECT_AEL, phong=args.phong)   # warm-up
+            r.render_scene_host(hs, wo_c[2], wo_z[2], flags=api.WHOLE_OBJECT_AEL, phong=phong)   # warm-up
             t0 = time.perf_counter()
             for i in range(2):
-                r.render_scene_host(hs, wo_c[i], wo_z[i], flags=api.WHOLE_OBJECT_AEL, phong=args.phong)
+                r.render_scene_host(hs, wo_c[i], wo_z[i], flags=api.WHOLE_OBJECT_AEL, phong=phong)
             wo_ms = (time.perf_counter() - t0) / 2 * 1e3
             whole_object = {"e2e_ms": wo_ms, "api": "b200r_render_objects + B200R_WHOLE_OBJECT_AEL",
                             "stopped_objects": r.stats()["StoppedObjects"]}
@@ -514,7 +555,7 @@ def run_ours(args):
                 ref_t = []
                 for i in range(3):
                     t0 = time.perf_counter()
-                    ref = ol.ref_render_object(scene, phong=args.phong)
+                    ref = ol.ref_render_object(scene, phong=phong)
                     ref_t.append((time.perf_counter() - t0) * 1e3)
                 whole_object["cpu_reference_ms"] = min(ref_t)
                 whole_object["cpu_reference"] = "verbatim FillEdgeTable + DrawModel on the whole object, 1 thread, incl. clearing the targets"
@@ -522,20 +563,34 @@ def run_ours(args):
                 whole_object["colour_max_lsb_vs_reference"] = int(np.abs(ref["color"].view(np.uint8).astype(np.int16) -
                                                                          wo_c[0].view(np.uint8).astype(np.int16)).max())
         # a textured object's vertex colours are not uploaded (they never reach the image); its UVs and Bitmap are
-        h2d_bytes = int(ntri * (96 if args.textured else 120) + 2 * W * H * 4 + (scene.texture.nbytes if args.textured else 0))
+        h2d_bytes = int(ntri * (96 if textured else 120) + 2 * W * H * 4 + (scene.texture.nbytes if textured else 0))
         d2h_bytes = int(2 * W * H * 4)
-    else:
-        # c4/c5: vertices from pinned host memory every step, b200r_clear_device + b200r_render_device
-        # per frame (band / view), colour and depth of every frame read back to pinned host memory
-        e2e_steps = min(K, 3)
-        h_pos, h_col, h_nrm = pin(scene.positions), pin(scene.colors), pin(scene.normals)
+        del hcol, hz
+    elif e2e_steps > 0:
+        # c4/c5: vertices from pinned host memory every step, b200r_clear_device + b200r_render_device per
+        # frame (band / view), colour and depth of every frame read back to pinned host memory.
+        # c4 on N ranks: every rank uploads 1/N of the triangle list over PCIe and the ranks exchange their
+        # slices over NVLink (all_gather) -- the host link carries the mesh once, not once per GPU.
+        e2e_steps = min(K, e2e_steps, 3)
+        sharded_upload = cfgname == "c4" and world > 1 and ntri % world == 0
         h_c = torch.empty((band_rows, wpad), dtype=torch.int32).pin_memory()
         h_z = torch.empty((band_rows, wpad), dtype=torch.float32).pin_memory()
+        if sharded_upload:
+            per = ntri // world * 3                                   # vertices per rank
+            sl = slice(rank * per, (rank + 1) * per)
+            h_pos, h_col, h_nrm = pin(scene.positions[sl]), pin(scene.colors[sl]), pin(scene.normals[sl])
+        else:
+            h_pos, h_col, h_nrm = pin(scene.positions), pin(scene.colors), pin(scene.normals)
 
         def e2e_once():
             with torch.cuda.stream(stream):
-                d_pos.copy_(h_pos, non_blocking=True); d_col.copy_(h_col, non_blocking=True)
-                d_nrm.copy_(h_nrm, non_blocking=True)
+                if sharded_upload:
+                    for d_all, h_part in ((d_pos, h_pos), (d_col, h_col), (d_nrm, h_nrm)):
+                        d_all[sl].copy_(h_part, non_blocking=True)
+                        dist.all_gather_into_tensor(d_all, d_all[sl])
+                else:
+                    d_pos.copy_(h_pos, non_blocking=True); d_col.copy_(h_col, non_blocking=True)
+                    d_nrm.copy_(h_nrm, non_blocking=True)
                 for (m_, c_, _) in frames:
                     r.clear_device(targets[0], scene.clear_color, scene.clear_depth)
                     r.render_device([m_], c_, targets[0])
@@ -543,30 +598,27 @@ def run_ours(args):
                 r.sync()
             stream.synchronize()
         e2e_once()
-        barrier(); torch.cuda.synchronize()
+        ctx.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             e2e_once()
         torch.cuda.synchronize()
         e2e_local = (time.perf_counter() - t0) / e2e_steps * 1e3
         covered = int((h_z.numpy()[:, :W] != np.float32(scene.clear_depth)).sum())
-        e2e_api = "pinned H2D of the vertex streams + b200r_clear_device/b200r_render_device per frame + D2H of colour and depth"
-        h2d_bytes, d2h_bytes = int(ntri * 120), int(len(frames) * 2 * band_rows * wpad * 4)
-    e_t = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e_t.item())
-
-    clocks = sampler.stop() if sampler else None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        e2e_fnv = None
+        e2e_api = ("pinned H2D of the vertex streams" +
+                   (f" (1/{world} per rank + NCCL all_gather over NVLink)" if sharded_upload else "") +
+                   " + b200r_clear_device/b200r_render_device per frame + D2H of colour and depth")
+        h2d_bytes = int(ntri * 120 // (world if sharded_upload else 1))
+        d2h_bytes = int(len(frames) * 2 * band_rows * wpad * 4)
+        del h_c, h_z, h_pos, h_col, h_nrm
+    if e2e_steps > 0:
+        e2e_ms = ctx.max_over_ranks([e2e_local])[0]
 
     def to_value(ms_step, n_ranks):
         if cfgname == "c2":
             units = n_ranks * ntri                      # every rank: its own 1M-triangle frame
-        elif cfgname == "c3":
+        elif cfgname in ("c1", "c3"):
             units = n_ranks * W * H
         elif cfgname == "c4":
             units = W * H                               # one frame, its bands spread over the ranks
@@ -579,24 +631,27 @@ def run_ours(args):
     # algorithmic bytes of what THIS rank does in one step: read every vertex
     # attribute once per frame, load + store colour and depth once per pixel of its target
     # (textured: positions + normals + UVs = 96 B per triangle -- the vertex colours never reach the image)
-    tri_bytes = 96.0 if args.textured else 120.0
+    tri_bytes = 96.0 if textured else 120.0
     a_frame = nframes * (tri_bytes * ntri + 16.0 * W * band_rows)
-    own_bytes = {"setup_kernel": 120.0 * ntri, "raster_kernel": 16.0 * W * band_rows,
+    own_bytes = {"setup_kernel": tri_bytes * ntri, "raster_kernel": 16.0 * W * band_rows,
                  "tile_scan_kernel": 0.0, "scatter_kernel": 0.0}[dominant]
     achieved = own_bytes / (stage_ms[dominant] * 1e-3) / 1e9
     frame_achieved = a_frame / (ms * 1e-3) / 1e9
-    traffic = ncu_traffic(args.config, dominant)
-    line = {
+    traffic = ncu_traffic(cfgname, dominant)
+    want = expected_hashes().get(cfgname, {}).get("color") if (scale == 1.0 and not phong and not textured) else None
+    rec = {
         "metric": unit, "value": to_value(ms, world), "unit": unit, "n_gpus": world, "steps": K,
-        "warmup": Wm, "ms_per_step": ms, "higher_is_better": True, "scaling": SCALING[cfgname],
+        "warmup": Wm, "ms_per_step": ms, "ms_per_step_best": ms_best, "ms_per_step_passes": pass_ms, "passes": passes,
+        "higher_is_better": True, "scaling": SCALING[cfgname],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload + (" -- per-pixel Phong shading" if args.phong else "") +
-                               (f" -- textured, {TEX_SIZE}x{TEX_SIZE} ARGB8, perspective correct" if args.textured else ""),
-                   "shading": ("phong" if args.phong else "gouraud") + ("+texture" if args.textured else ""), "triangles": ntri, "width": W, "height": H,
+        "config": {"workload": workload + (" -- per-pixel Phong shading" if phong else "") +
+                               (f" -- textured, {TEX_SIZE}x{TEX_SIZE} ARGB8, perspective correct" if textured else ""),
+                   "shading": ("phong" if phong else "gouraud") + ("+texture" if textured else ""), "triangles": ntri, "width": W, "height": H,
                    "parallelism": ({"c4": f"screen-space row bands x{world}", "c5": f"{C5_VIEWS} views over {world} ranks"}
                                    .get(cfgname, f"frame-parallel x{world}") if world > 1 else "1 GPU"),
-                   "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": args.scale,
+                   "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": scale,
                    "tile": tile,
+                   "timing": f"median of {passes} passes of exactly {K} steps, per pass the max over ranks (CUDA events)",
                    "l2": "each timed frame streams >126 MB (vertices + records + pair lists + its own "
                          "pre-cleared target), i.e. inputs larger than L2; no explicit flush",
                    "targets": ("one target pair, b200r_clear_device inside every timed frame" if clear_in_step else
@@ -607,6 +662,9 @@ def run_ours(args):
         "stage_ms": stage_ms,
         "binner": {"binned_triangles": stats["Binned"], "segments": stats["Segments"], "spans": stats["Spans"],
                    "queue_entries": stats["TilePairs"], "tiles": stats["Tiles"], "reruns": stats["Reruns"]},
+        "image_fnv": image_fnv,
+        "image_fnv_oracle": want,
+        "image_ok": (image_fnv == want) if (want and image_fnv) else None,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": own_bytes,
@@ -614,37 +672,77 @@ def run_ours(args):
                      "kernel_share_of_step": stage_ms[dominant] / max(sum(stage_ms.values()), 1e-9),
                      "frame": {"algorithmic_bytes": a_frame, "achieved": frame_achieved,
                                "frac": frame_achieved / peak}},
-        "e2e": {"value": to_value(e2e_ms, world), "unit": unit, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "steps": e2e_steps, "covered_pixels": covered, "api": e2e_api},
-        "clocks": clocks,
     }
+    if e2e_steps > 0:
+        rec["e2e"] = {"value": to_value(e2e_ms, world), "unit": unit, "ms_per_step": e2e_ms,
+                      "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                      "steps": e2e_steps, "covered_pixels": covered, "api": e2e_api,
+                      **({"image_fnv": e2e_fnv, "image_ok": (e2e_fnv == want) if want else None} if e2e_fnv else {})}
     if with_gather:
         with_gather["value"] = to_value(with_gather["ms_per_step"], world)
-        line["with_gather"] = with_gather
-    if world == 1 and not args.no_cpu_baseline:
+        rec["with_gather"] = with_gather
+    if cpu_baseline and world == 1 and rank == 0:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as ol
-            from cpu_renderer_b200 import scene as sc2
-            s, sample, threads = cpu_sample(cfgname, scene, sc2)
+            s, sample, threads = cpu_sample(cfgname, scene, sc)
             kind = "reference" if ol.ref_available() else "port"
-            res = time_cpu(ol, s, threads, 3, 1, kind, args.phong)
+            res = time_cpu(ol, s, threads, 3, 1, kind, phong)
             units = sample if unit == "Mtriangles/s" else W * H * (sample / ntri)
-            line["cpu_baseline"] = {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit,
-                                    "cores": threads, "kind": kind, "sample": res["sample"],
-                                    "host": cpu_model()}
+            rec["cpu_baseline"] = {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit,
+                                   "cores": threads, "kind": kind, "sample": res["sample"],
+                                   "host": cpu_model()}
             if cfgname in ("c1", "c2", "c3"):              # c4 / c5 frames are too large to count on one core here
                 try:
-                    line["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)
+                    rec["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)
                 except Exception as e:
-                    line["roofline"]["equivalent_zbuffer"] = {"error": repr(e)}
+                    rec["roofline"]["equivalent_zbuffer"] = {"error": repr(e)}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the line
-            line["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port",
-                                    "sample": f"failed: {e!r}"}
-    emit_line(line)
-    if world > 1:
-        dist.destroy_process_group()
+            rec["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port",
+                                   "sample": f"failed: {e!r}"}
+    # release this leg's device memory before the next one
+    del colors, depths, targets, frames, d_pos, d_col, d_nrm
+    torch.cuda.empty_cache()
+    return rec
+
+
+def leg_summary(rec):
+    """The sub-record of a secondary leg inside the one JSON line."""
+    keep = ("metric", "value", "unit", "ms_per_step", "ms_per_step_best", "passes", "steps", "scaling", "stage_ms",
+            "gpu_launches", "image_fnv", "image_fnv_oracle", "image_ok", "with_gather", "binner")
+    out = {k: rec[k] for k in keep if k in rec}
+    out["config"] = {k: rec["config"][k] for k in ("workload", "triangles", "width", "height", "parallelism", "band_rows", "tile")}
+    out["roofline"] = {k: rec["roofline"][k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",
+                                                        "algorithmic_bytes_per_launch", "kernel_ms", "frame")}
+    if "e2e" in rec:
+        out["e2e"] = rec["e2e"]
+    return out
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
+    K, Wm = args.steps, args.warmup
+    main_leg = run_leg(ctx, args.config, K, Wm, scale=args.scale, phong=args.phong, textured=args.textured,
+                       tile=args.tile, cpu_baseline=not args.no_cpu_baseline, c1_whole_object=args.config == "c1")
+    legs = {}
+    default_run = (args.config == "c2" and args.scale == 1.0 and not args.phong and not args.textured
+                   and not args.tile and not args.no_legs)
+    if default_run:
+        # north_star's two numeric targets sit on C3 (4K fill, 1 GPU) and C4 (16K^2 row bands, every N):
+        # short legs of both ride in the default line so that the driver's own runs carry them
+        if ctx.world == 1:
+            legs["c3"] = leg_summary(run_leg(ctx, "c3", min(K, 10), 3, passes=3, e2e_steps=5))
+        legs["c4_bands"] = leg_summary(run_leg(ctx, "c4", min(K, 3), 3, passes=3, e2e_steps=2))
+    clocks = sampler.stop() if sampler else None
+    if ctx.rank == 0:
+        line = main_leg
+        if legs:
+            line["legs"] = legs
+        line["clocks"] = clocks
+        emit_line(line)
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -660,6 +758,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", default=None, help="WxH: 64x32 (default), 32x32, 128x16, 64x16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="default run without the short c3 / c4_bands legs")
+    ap.add_argument("--defer-verdict", action="store_true",
+                    help="device-resident frames with B200R_DEFER_VERDICT (no host wait for the binning verdict)")
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--ref-threads", type=int, default=0)
     args = ap.parse_args()

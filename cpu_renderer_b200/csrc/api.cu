@@ -138,6 +138,25 @@ static int fail(b200r_context *c, int code, const char *what, cudaError_t e = cu
     return code;
 }
 
+// Makes the context's device current and restores the caller's on scope exit (a host process may
+// drive several GPUs from one thread, with other CUDA libraries in between).
+struct DeviceGuard
+{
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if(err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if(err == cudaSuccess) prev = -1;             // nothing to restore
+    }
+    ~DeviceGuard() { if(prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define ENTER(c) DeviceGuard guard_((c)->device); \
+                 if(guard_.err != cudaSuccess) return fail((c), B200R_E_CUDA, "cudaSetDevice", guard_.err)
+
 #define CU(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(c, B200R_E_CUDA, #call, e_); } while(0)
 
 static int fill_view(b200r_context *c, const game_render_commands *cmd, const b200r_device_target *t, ViewParams &v,
@@ -254,7 +273,7 @@ static int issue_frame(b200r_context *c)
             CU(cudaMemsetAsync(c->obj_flags.ptr, 0, (size_t)op.nobjects*2*sizeof(unsigned), c->stream));
             c->stats.KernelLaunches += 3;
         }
-        launch_object_walk(v, op, c->stream);
+        CU(launch_object_walk(v, op, c->stream));
         c->stats.KernelLaunches += 1;
     }
     else
@@ -395,7 +414,6 @@ static int settle_pending(b200r_context *c)
         CU(cudaEventSynchronize(c->total_ready));
         const FrameWords &hw = *c->h_words;
         const unsigned total = hw.pair_total;
-        const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
         uint64_t nseg = hw.extra_total, nspan = hw.extra_total;
         for(int r = 0; r < kSubAllocators; ++r) { nseg += hw.seg_fill[r]; nspan += hw.span_fill[r]; }
         c->stats.Binned = hw.counters[0];
@@ -445,7 +463,8 @@ int b200r_create(b200r_context **out, int device)
     if(!c) return B200R_E_NOMEM;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if(cudaSetDevice(device) != cudaSuccess ||
+    DeviceGuard guard(device);
+    if(guard.err != cudaSuccess ||
        cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
        cudaEventCreateWithFlags(&c->total_ready, cudaEventDisableTiming) != cudaSuccess ||
        cudaMallocHost((void **)&c->h_words, sizeof(FrameWords)) != cudaSuccess ||
@@ -466,7 +485,7 @@ int b200r_create(b200r_context **out, int device)
 void b200r_destroy(b200r_context *c)
 {
     if(!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     if(c->stream) cudaStreamSynchronize(c->stream);
     c->recs.release(); c->segs.release(); c->spans.release(); c->tiles.release(); c->pairs.release(); c->words.release();
     c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_uv.release(); c->d_color.release(); c->d_depth.release();
@@ -494,7 +513,7 @@ const char *b200r_last_error(const b200r_context *c) { return c ? c->error.c_str
 int b200r_set_stream(b200r_context *c, void *s)
 {
     if(!c) return B200R_E_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -505,7 +524,7 @@ int b200r_set_stream(b200r_context *c, void *s)
 int b200r_sync(b200r_context *c)
 {
     if(!c) return B200R_E_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -531,7 +550,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     if(flags & B200R_WHOLE_OBJECT_AEL)
         return fail(c, B200R_E_UNSUPPORTED, "whole-object mode needs the host-pointer call (b200r_render_objects)");
     if(mesh_count && !meshes) return fail(c, B200R_E_INVALID, "null Meshes");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = settle_pending(c);                 // the previous frame must be complete in the stream
     if(rc != B200R_OK) return rc;
 
@@ -607,13 +626,18 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     c->ntiles = ntiles;
     c->stats.Triangles = total;
     c->stats.Tiles = ntiles;
-    return issue_frame(c);
+    rc = issue_frame(c);
+    // The frame's overflow verdict is known once set-up, scan and finalize have run (the raster kernel
+    // is still in flight): resolve it now, so that whatever the caller enqueues next on this stream
+    // reads a finished frame.  B200R_DEFER_VERDICT leaves it to the next call / b200r_sync.
+    if(rc == B200R_OK && !(flags & B200R_DEFER_VERDICT) && !c->host_path) rc = settle_pending(c);
+    return rc;
 }
 
 int b200r_clear_device(b200r_context *c, const b200r_device_target *t, u32 color, r32 depth)
 {
     if(!c || !t || !t->Color || !t->Depth || t->Width <= 0 || t->BandRows <= 0) return fail(c, B200R_E_INVALID, "bad clear target");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
     launch_clear(t->Color, t->ColorPitch/4, t->Depth, t->DepthStride, t->Width, t->BandRows, color, depth, c->stream);
@@ -625,7 +649,7 @@ int b200r_clear_device(b200r_context *c, const b200r_device_target *t, u32 color
 int b200r_set_profiling(b200r_context *c, int enable)
 {
     if(!c) return B200R_E_INVALID;
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = b200r_sync(c);
     if(rc != B200R_OK) return rc;
     if(enable && !c->stage_ev[0])
@@ -780,7 +804,7 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     if(!cmd || !out || !out->Memory || !cmd->ZBuffer || (n && !objs)) return fail(c, B200R_E_INVALID, "null argument");
     if(out->Width <= 0 || out->Height <= 0 || out->Pitch < out->Width*4 || cmd->Width < (u32)out->Width)
         return fail(c, B200R_E_INVALID, "bad OutputTarget / Commands->Width");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
     if(flags & B200R_WHOLE_OBJECT_AEL) return render_objects_whole(c, objs, n, cmd, out);
@@ -882,7 +906,7 @@ static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
 {
     const bool textured = obj->Bitmap != nullptr;
     if(textured && obj->VertexCount >= 3 && !obj->UVData) return fail(c, B200R_E_INVALID, "textured object without UVData");
-    CU(cudaSetDevice(c->device));
+    ENTER(c);
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
     // A textured object takes two passes of the set-up kernel: colours (lit white on the Gouraud
@@ -1082,6 +1106,7 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
             for(; k < ntex; ++k) if(c->host_textures[k].host == b) break;
             if(k == ntex)
             {
+                if(k >= 65536) return fail(c, B200R_E_UNSUPPORTED, "more than 65536 distinct textures per call");
                 if(c->host_textures.size() <= ntex) c->host_textures.emplace_back();
                 b200r_context::HostTexture &ht = c->host_textures[ntex];
                 CU(ht.pixels.reserve((size_t)b->Width*b->Height*4));
@@ -1098,6 +1123,8 @@ static int render_objects_whole(b200r_context *c, const render_entry_3d_object *
         any_phong_obj |= d.phong != 0;
         all.insert(all.end(), scratch.begin(), scratch.begin() + ne);
         descs.push_back(d);
+        // chain and emit kernels put the objects on gridDim.y
+        if(descs.size() > 65535) return fail(c, B200R_E_UNSUPPORTED, "whole-object mode: more than 65535 objects per call");
     }
 
     // targets (as in the per-triangle call): device mirrors with rows padded to 64 pixels

@@ -671,20 +671,25 @@ emit_kernel(ViewParams v, ObjectWalkParams p)
     if((threadIdx.x & 31) == 0 && pairs) atomicAdd(&p.counters[1], (unsigned long long)pairs);
 }
 
-void launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s)
+cudaError_t launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s)
 {
-    if(p.nobjects == 0) return;
+    if(p.nobjects == 0) return cudaSuccess;
+    if(p.nobjects > 65535u) return cudaErrorInvalidConfiguration;      // objects sit on gridDim.y (api.cu rejects earlier)
+    cudaError_t e;
     if(p.chain_base != nullptr)
     {
         // grid.x covers the largest object; smaller ones leave CTAs idle (objects are few)
         chain_kernel<<<dim3((p.max_edges + 127)/128, p.nobjects), 128, 0, s>>>(p);
-        cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.order_smem_bytes);
+        e = cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.order_smem_bytes);
+        if(e != cudaSuccess) return e;
         order_kernel<<<p.nobjects, kObjectThreads, p.order_smem_bytes, s>>>(p);
         emit_kernel<<<dim3((p.max_bound + 127)/128, p.nobjects), 128, 0, s>>>(v, p);
     }
     // the serial walk: every object without the three-phase path, only the flagged ones with it
-    cudaFuncSetAttribute(object_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.state_smem_bytes);
+    e = cudaFuncSetAttribute(object_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.state_smem_bytes);
+    if(e != cudaSuccess) return e;
     object_walk_kernel<<<p.nobjects, kObjectThreads, p.state_smem_bytes, s>>>(v, p);
+    return cudaGetLastError();
 }
 
 } // namespace b200r

@@ -285,7 +285,7 @@ struct ObjectWalkParams
     unsigned max_bound;                 // largest span_bound (grid of the emit phase)
     unsigned max_edges;                 // largest edge_count (grid of the chain phase)
 };
-void launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s);
+cudaError_t launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, cudaStream_t s);
 // zrange[0..1] start as {-inf as ordered key, +inf as ordered key}; zrange_finish turns them into
 // {zmax, 1/(zmax - zmin)}
 void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s);

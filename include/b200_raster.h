@@ -14,12 +14,26 @@
  * is included from inside the reference's own unity build, define B200R_NO_REFERENCE_TYPES
  * first so the renderer's own definitions are used.
  *
- * Semantics: untextured objects (Bitmap == 0), Gouraud (PhongShading == 0) or
- * per-pixel Phong (PhongShading != 0, projekt.cpp:450-509); one triangle = one object ("level 1",
- * SURVEY.md section 0); coverage and depth bit-exact with the reference's scalar arithmetic,
- * Gouraud colour bit-exact, Phong colour within +-1 LSB per channel (pow(x,16) in double);
- * equal depth resolved as in the reference (first submitted wins, projekt.cpp:525).  There is no CPU fallback: every entry point fails with
- * B200R_E_NO_DEVICE when no sm_100 device is usable.
+ * Semantics: Gouraud (PhongShading == 0) or per-pixel Phong (PhongShading != 0,
+ * projekt.cpp:450-509) objects, untextured (Bitmap == 0) or textured with nearest-texel,
+ * perspective-correct sampling (Bitmap != 0, projekt.cpp:427-446; texel coordinates that leave the
+ * bitmap are clamped where the reference reads outside it).  One triangle = one object ("level 1",
+ * SURVEY.md section 0) unless B200R_WHOLE_OBJECT_AEL asks for the reference's whole-object
+ * active-edge list.  Coverage and depth are bit-exact with the reference's scalar arithmetic,
+ * Gouraud and unlit textured colour bit-exact, Phong colour within +-1 LSB per channel (pow(x,16)
+ * in double); equal depth is resolved as in the reference (first submitted wins, projekt.cpp:525).
+ *
+ * Internal lists (segments, spans, per-tile queues) are sized from earlier frames and grow on
+ * demand: a frame whose lists did not fit is not drawn at all (one device-side verdict word makes
+ * its binning and raster kernels return at once), the lists are grown and the frame is issued again
+ * (b200r_frame_stats::Reruns).  Every render call resolves that verdict before it returns, so
+ * work enqueued on the same stream afterwards sees the finished frame; B200R_DEFER_VERDICT opts out.
+ *
+ * Every entry point makes the context's device current for the duration of the call and restores
+ * the calling thread's current device before it returns.
+ *
+ * There is no CPU fallback: every entry point fails with B200R_E_NO_DEVICE when no sm_100 device
+ * is usable.
  */
 #ifndef B200_RASTER_H
 #define B200_RASTER_H
@@ -120,7 +134,8 @@ typedef struct edge_info                   /* projekt.h:17-37, 120 bytes */
 #define B200R_OK             0
 #define B200R_E_INVALID     (-1)   /* null / inconsistent arguments                           */
 #define B200R_E_CUDA        (-2)   /* a CUDA call failed; see b200r_last_error                 */
-#define B200R_E_UNSUPPORTED (-3)   /* textured object, > 8 lights, LightCount == 0 on the Gouraud path */
+#define B200R_E_UNSUPPORTED (-3)   /* > 8 lights, LightCount == 0 on the Gouraud path, > 65535 tiles per axis,
+                                      > 65536 textures or (whole-object mode) > 65535 objects per call    */
 #define B200R_E_NOMEM       (-4)
 #define B200R_E_NO_DEVICE   (-5)   /* no CUDA device of compute capability 10.x                */
 
@@ -135,6 +150,12 @@ typedef struct edge_info                   /* projekt.h:17-37, 120 bytes */
                                       a null list pointer the object stops drawing (b200r_frame_stats::
                                       StoppedObjects).  b200r_render_device: B200R_E_UNSUPPORTED.          */
 
+#define B200R_DEFER_VERDICT 2u     /* b200r_render_device: return without waiting for the binning verdict of this
+                                      frame.  The frame is then final only after the NEXT call on the context or
+                                      b200r_sync: if a list overflowed, the frame's raster kernel did nothing and
+                                      the frame is re-issued at that later point, reading the mesh and target
+                                      pointers again.  For pipelines that re-submit frames of known size.       */
+
 typedef struct b200r_context b200r_context;
 
 /* One context per GPU.  Device < 0 keeps the calling thread's current device. */
@@ -147,7 +168,7 @@ int b200r_set_stream(b200r_context *Context, void *CudaStream);
 int b200r_sync(b200r_context *Context);
 
 /* Screen tile staged in shared memory by the raster kernel: 64x32 (default), 32x32, 128x16,
- * 64x16 or 128x32 pixels. */
+ * 64x16, 128x32 or 256x8 pixels. */
 int b200r_set_tile(b200r_context *Context, int TileWidth, int TileHeight);
 
 /* ------------------------------------------------------------------------------------------
@@ -174,7 +195,9 @@ int b200r_fill_edge_table(b200r_context *Context, const render_entry_3d_object *
 
 /* ------------------------------------------------------------------------------------------
  * Device-resident path (what the host-pointer call is built from).  All pointers below are
- * device pointers; calls are asynchronous on the context's stream.
+ * device pointers; the kernels run asynchronously on the context's stream.  b200r_render_device
+ * returns once the frame's binning verdict is known (its set-up and scan kernels have finished;
+ * the raster kernel is still running) -- see "Internal lists" above and B200R_DEFER_VERDICT.
  * ------------------------------------------------------------------------------------------ */
 /* render_entry_3d_object::Bitmap (projekt.h:13) resident on the device: nearest-texel, perspective
  * correct sampling at Round(uv * (dim - 1)) (projekt.cpp:427-446).  The reference does not
@@ -232,7 +255,7 @@ typedef struct b200r_frame_stats
     uint64_t TilePairs;        /* (span, tile) queue entries produced by the binner             */
     uint64_t Tiles;            /* screen tiles of the band                                      */
     uint64_t KernelLaunches;   /* kernels launched by this context since creation               */
-    uint64_t Reruns;           /* frames re-issued because the pair list had to grow            */
+    uint64_t Reruns;           /* frames re-issued because a segment, span or queue list had to grow */
     uint64_t StoppedObjects;   /* B200R_WHOLE_OBJECT_AEL: objects that stopped drawing where the
                                   reference dereferences a null list pointer (it crashes there)  */
 } b200r_frame_stats;
