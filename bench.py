@@ -194,8 +194,11 @@ def run_reference(args):
         "impl": "reference", "metric": unit, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": SCALING[args.config], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "triangles_per_step": sample, "width": scene.width,
-                   "height": scene.height},
+        "config": {"workload": workload + (" -- per-pixel Phong shading" if args.phong else "") +
+                               (f" -- textured, {TEX_SIZE}x{TEX_SIZE} ARGB8, perspective correct" if args.textured else ""),
+                   "shading": ("phong" if args.phong else "gouraud") + ("+texture" if args.textured else ""),
+                   "triangles": scene.triangle_count, "width": scene.width, "height": scene.height,
+                   "triangles_per_step": sample, "whole_frame": sample == scene.triangle_count, "scale": args.scale},
         "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind,
                          "sample": res["sample"]},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -207,7 +210,8 @@ def run_reference(args):
 def cpu_sample(config, scene, sc, sample=0, threads=0):
     """Bounded CPU sample of a config: a prefix of the frame's triangle list (for c5: of view 0)."""
     import copy
-    default = {"c1": 1 << 20, "c2": 250_000, "c3": 4000, "c4": 250_000, "c5": 250_000}[config]
+    # c1/c2/c3: the whole frame (same configuration as the GPU arm); c4/c5: a stated prefix / stride sample
+    default = {"c1": 1 << 30, "c2": 1 << 30, "c3": 1 << 30, "c4": 250_000, "c5": 250_000}[config]
     sample = min(scene.triangle_count, sample or default)
     if config == "c5":
         # a mesh is ordered: take every k-th triangle so the sample covers the whole sphere
@@ -252,6 +256,64 @@ def equivalent_zbuffer(ol, scene, tri_bytes, frame_ms, peak_gbs):
     return {"bytes": b, "fragments": st["Fragments"], "depth_passes": st["DepthPasses"], "GB/s": gbs,
             "of_measured_hbm_peak": gbs / peak_gbs,
             "what": "z-buffer traffic of the reference's own algorithm for this frame / our frame time (not HBM traffic)"}
+
+
+def avx_scenes(sc):
+    """The two inputs the reference's multithreaded AVX path is timed on (it only
+    handles textured + Phong convex objects that do not overlap on screen): the demo sphere at 1080p (config C1)
+    and a 4K frame tiled with 10 x 5 such spheres (the 'C3-like scene of non-overlapping convex objects')."""
+    from dataclasses import replace
+    m = np.load(os.path.join(ROOT, "tests", "golden", "sphere_mesh.npz"))
+    uv = np.clip(m["uvs"], 0.0, 1.0).astype(np.float32)       # that path fetches texels without a range check
+    tex = sc.make_texture(256, 256)
+    c1 = replace(sc.sphere_scene(m["pos"], m["col"], m["nrm"], uv, 1920, 1080, 500.0, name="c1_tex_phong"), texture=tex)
+    grid = replace(sc.sphere_scene(m["pos"], m["col"], m["nrm"], uv, 3840, 2160, 500.0, name="convex_grid_4k"), texture=tex)
+    step = 360.0 / (500.0 * 2.0 / 3.0)                          # 360 px between centres, spheres are ~334 px wide
+    ps = [((i - 4.5) * step, (j - 2.0) * step, 0.0) for j in range(5) for i in range(10)]
+    return [("c1_textured_phong", c1, [(0.0, 0.0, 0.0)]), ("convex_grid_4k_textured_phong", grid, ps)]
+
+
+def avx_baseline(renderer=None, threads=0, reps=5):
+    """cpu_baseline.avx_mt: DrawModelOptimizedLines + FillLinesOptimized (projekt.cpp:3362-3613, 629-1490) with
+    `threads` workers behind Platform.AddEntry, best and median of `reps` frames; beside it the same frames
+    through b200r_render_objects (host buffers in and out) when a renderer is given."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from cpu_renderer_b200 import scene as sc
+    if not ol.avx_available():
+        return {"unavailable": "oracle/_ref/libprojekt_avx.so has not been built"}
+    threads = threads or (os.cpu_count() or 1)
+    out = {"kind": "reference", "path": "FillEdgeTable + DrawModelOptimizedLines on the submitting thread, FillLinesOptimized "
+                                        "on the workers (oracle/_ref/libprojekt_avx.so: the reference text through 5 sed rules)",
+           "cores": threads, "host": cpu_model(), "unit": "Mpixels/s", "scenes": {}}
+    for name, scene, ps in avx_scenes(sc):
+        f = ol.AvxFrame(scene, ps, threads)
+        tot, main = [], []
+        rc = 0
+        for i in range(reps + 1):
+            f.clear()
+            rc, t_main, t_all = f.render()
+            if i:
+                tot.append(t_all * 1e3); main.append(t_main * 1e3)
+        px = scene.width * scene.height
+        rec = {"objects": len(ps), "triangles": scene.triangle_count * len(ps), "width": scene.width, "height": scene.height,
+               "covered_pixels": f.covered(), "status": rc, "ms_median": float(np.median(tot)), "ms_best": float(min(tot)),
+               "ms_submitting_thread": float(np.median(main)),
+               "value": px / (float(np.median(tot)) * 1e-3) / 1e6}
+        if renderer is not None:
+            color = np.empty((scene.height, scene.width), np.uint32); z = np.empty((scene.height, scene.width), np.float32)
+            g = []
+            for i in range(reps + 1):
+                color.fill(scene.clear_color); z.fill(scene.clear_depth)
+                t0 = time.perf_counter()
+                renderer.render_scene_host(scene, color, z, phong=True, object_ps=ps)
+                if i:
+                    g.append((time.perf_counter() - t0) * 1e3)
+            rec["gpu_e2e_ms_median"] = float(np.median(g))
+            rec["gpu_e2e_value"] = px / (float(np.median(g)) * 1e-3) / 1e6
+            rec["gpu_covered_pixels"] = int((z != np.float32(scene.clear_depth)).sum())
+        out["scenes"][name] = rec
+    return out
 
 
 def time_cpu(ol, s, threads, steps, warmup, kind, phong=False):
@@ -691,7 +753,15 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
             units = sample if unit == "Mtriangles/s" else W * H * (sample / ntri)
             rec["cpu_baseline"] = {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit,
                                    "cores": threads, "kind": kind, "sample": res["sample"],
-                                   "host": cpu_model()}
+                                   "host": cpu_model(),
+                                   "scalar_mt": {"value": units / (res["ms_per_step"] * 1e-3) / 1e6, "unit": unit, "cores": threads,
+                                                 "whole_frame": sample == ntri,
+                                                 "path": "verbatim FillEdgeTable + DrawModel per triangle, object-parallel over the host threads"}}
+            try:
+                r.set_stream(0); r.set_tile(64, 32)
+                rec["cpu_baseline"]["avx_mt"] = avx_baseline(r)
+            except Exception as e:
+                rec["cpu_baseline"]["avx_mt"] = {"error": repr(e)}
             if cfgname in ("c1", "c2", "c3"):              # c4 / c5 frames are too large to count on one core here
                 try:
                     rec["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)

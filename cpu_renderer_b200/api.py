@@ -223,16 +223,21 @@ class Renderer:
 
     # ---- host-pointer drop-in (FillEdgeTable + DrawModel pair, projekt.cpp:3882 + 162) ----
     def render_scene_host(self, scene, color: np.ndarray, depth: np.ndarray, splits=None, flags=0, phong=False,
-                          textured=None):
+                          textured=None, object_ps=None):
         """Render ``scene`` into host arrays color[H,W] u32 / depth[H,W] f32 in place.
         ``splits``: optional list of vertex counts to submit the scene as several objects.
         ``phong``: bool, or one bool per split (render_entry_3d_object::PhongShading).
         ``textured``: bool, or one bool per split: the object carries scene.texture as its Bitmap
-        (default: every object, when the scene has a texture)."""
+        (default: every object, when the scene has a texture).
+        ``object_ps``: optional list of Object->P; the whole scene is then submitted once per entry
+        (the same vertex arrays as several objects at different positions)."""
         assert color.dtype == np.uint32 and depth.dtype == np.float32
         nv = scene.positions.shape[0]
         splits = splits or [nv]
         assert sum(splits) == nv
+        if object_ps is not None:
+            assert splits == [nv]
+            splits = [nv] * len(object_ps)
         objs = (render_entry_3d_object * len(splits))()
         tex = getattr(scene, "texture", None)
         if textured is None:
@@ -244,7 +249,9 @@ class Renderer:
         at = 0
         for i, cnt in enumerate(splits):
             o = objs[i]
-            o.P = v3(*scene.object_p)
+            o.P = v3(*(object_ps[i] if object_ps is not None else scene.object_p))
+            if object_ps is not None:
+                at = 0
             o.VertexCount = cnt
             o.PhongShading = int(phong[i] if isinstance(phong, (list, tuple)) else phong)
             o.VertexData = scene.positions.ctypes.data + at * 12

@@ -449,6 +449,90 @@ def ref_render_triangles(scene, skip=None, use_fallback=False, threads=1, target
     return dict(color=color, z=z, status=status)
 
 
+# ------------------------------------------------------------------ the reference's AVX thread-pool path
+_avx = None
+
+
+def avx_available() -> bool:
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libprojekt_avx.so")) or os.path.isdir(REFERENCE_DIR)
+
+
+def avx():
+    global _avx
+    if _avx is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libprojekt_avx.so")
+        if not os.path.exists(path):
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.avx_render_objects.argtypes = [C.POINTER(RefObject), C.c_uint32, C.POINTER(RefCommands),
+                                           C.POINTER(RefLoadedBitmap), C.c_uint32, C.POINTER(C.c_double)]
+        lib.avx_render_objects.restype = C.c_int32
+        lib.avx_sizeof_row_header.restype = C.c_uint32
+        _avx = lib
+    return _avx
+
+
+def _aligned(shape, dtype, align=64):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.zeros(n + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+class AvxFrame:
+    """Everything one call of the reference's multithreaded AVX path needs:
+    DrawModelOptimizedLines + FillLinesOptimized (projekt.cpp:3362-3613, 629-1490) for a list of objects that
+    share one mesh and differ in Object->P.  That path handles textured + Phong objects only, loads depth with
+    aligned 8-float loads (rows must be 32-byte aligned: the width is padded to 8) and fetches texels at
+    trunc(u*Width) without a range check (UVs are clamped to [0, 1] and the bitmap carries one texel of padding)."""
+
+    def __init__(self, scene, object_ps, threads):
+        assert scene.texture is not None
+        self.scene, self.threads = scene, int(threads)
+        self.s = OracleScene(scene)
+        self.uv = np.ascontiguousarray(np.clip(scene.uvs, 0.0, 1.0), np.float32)
+        th, tw = scene.texture.shape
+        self.tex = np.zeros((th + 1, tw + 1), np.uint32)
+        self.tex[:th, :tw] = scene.texture
+        self.tex[th, :tw] = scene.texture[th - 1]; self.tex[:th, tw] = scene.texture[:, tw - 1]
+        self.tex_bmp = RefLoadedBitmap(tw, th, self.tex.strides[0], self.tex.ctypes.data)
+        self.wpad = (scene.width + 7) // 8 * 8
+        self.color = _aligned((scene.height, self.wpad), np.uint32)
+        self.z = _aligned((scene.height, self.wpad), np.float32)
+        self.zmask = np.zeros(scene.height * self.wpad // 8 + 64, np.uint8)
+        nv = scene.positions.shape[0]
+        self.edges = [np.zeros(nv, dtype=REF_EDGE_DTYPE) for _ in object_ps]
+        self.sort = np.zeros(nv, dtype=REF_EDGE_DTYPE)
+        self.arena = np.zeros((256 << 20) if len(object_ps) > 4 else (32 << 20), np.uint8)   # row-work arena (:2322)
+        self.cmd = self.s.ref_commands(self.z, self.sort)
+        self.cmd.ZMask = self.zmask.ctypes.data
+        self.cmd.ThreadMemory = self.arena.ctypes.data
+        self.cmd.ThreadMemorySize = self.arena.nbytes
+        self.bmp = RefLoadedBitmap(scene.width, scene.height, self.color.strides[0], self.color.ctypes.data)
+        self.objs = (RefObject * len(object_ps))()
+        for o, P, e in zip(self.objs, object_ps, self.edges):
+            o.P[:] = P
+            o.VertexCount = nv
+            o.Optimized, o.PhongShading = 1, 1
+            o.VertexData, o.ColorData = self.s.pos.ctypes.data, self.s.col.ctypes.data
+            o.NormalData, o.UVData = self.s.nrm.ctypes.data, self.uv.ctypes.data
+            o.EdgeMemory = e.ctypes.data
+            o.Bitmap = C.addressof(self.tex_bmp)
+        self.seconds = (C.c_double * 2)()
+
+    def clear(self):
+        self.color.fill(self.scene.clear_color); self.z.fill(self.scene.clear_depth)
+
+    def render(self):
+        """-> (objects drawn or -2, seconds on the submitting thread, seconds in total)"""
+        rc = avx().avx_render_objects(self.objs, len(self.objs), C.byref(self.cmd), C.byref(self.bmp), self.threads,
+                                      self.seconds)
+        return rc, self.seconds[0], self.seconds[1]
+
+    def covered(self):
+        return int((self.z[:, :self.scene.width] != np.float32(self.scene.clear_depth)).sum())
+
+
 def ref_sphere():
     """Verbatim ConstructSphere (projekt.cpp:4123): 6 624 vertices."""
     lib = ref()
