@@ -335,6 +335,7 @@ static int issue_frame(b200r_context *c)
     sp.seg_capacity = seg_cap;
     sp.tiles_x = v.tiles_x;
     sp.tile_offset = tile_offset; sp.tile_fill = tile_fill; sp.pair_list = (unsigned *)c->pairs.ptr;
+    sp.pair_capacity = pair_cap;
     launch_scatter(sp, c->stream);
     if(c->total_tris || c->object_mode) c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[3], c->stream));

@@ -82,6 +82,7 @@ scatter_kernel(const ScatterParams p)
         {
             const unsigned tile = (trow*(unsigned)p.tiles_x + (unsigned)tx)*kDepthBuckets + bucket;
             const unsigned slot = p.tile_offset[tile] + atomicAdd(&p.tile_fill[tile], si.nrows);
+            B200R_ASSERT(slot + si.nrows <= p.tile_offset[tile + 1] && slot + si.nrows <= p.pair_capacity);
             for(unsigned r = 0; r < si.nrows; ++r) p.pair_list[slot + r] = si.span_base + r;
         }
     }

@@ -11,6 +11,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// -DB200R_CHECKED builds the kernels with bounds checks on every list index and shared-memory address they
+// compute (device assert: the kernel traps, the next API call returns B200R_E_CUDA).  compute-sanitizer is
+// not available on every pool; tools/build_variant.sh checked -DB200R_CHECKED + the GPU test suite under
+// B200R_LIB is the substitute (profiles/r02_checked_build.txt).
+#if defined(B200R_CHECKED)
+#include <assert.h>
+#define B200R_ASSERT(x) assert(x)
+#else
+#define B200R_ASSERT(x) ((void)0)
+#endif
+
 namespace b200r {
 
 constexpr int kMaxLights = 8;
@@ -303,6 +314,7 @@ struct ScatterParams
     const unsigned *tile_offset;
     unsigned *tile_fill;
     unsigned *pair_list;        // per tile: span indices
+    unsigned pair_capacity;
 };
 void launch_scatter(const ScatterParams &p, cudaStream_t s);
 // After the scan: one word that tells scatter and raster whether every list fitted.

@@ -341,6 +341,8 @@ raster_kernel(const __grid_constant__ RasterParams p)
                     {
                         const uint32_t pa = tile_addr + (zaddr - plane_addr)*4u;
                         const int x = x0 + ((int)(zaddr - zrow) >> 2);
+                        B200R_ASSERT(zaddr >= zrow && zaddr < zrow + (uint32_t)cols*4u && zrow >= plane_addr &&
+                                     zrow < plane_addr + (uint32_t)(rows*TW*4) && n_left > 0);
                         Pixel mine;
                         mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
                         if(PHONG && tex_id >= 0)
@@ -395,7 +397,9 @@ raster_kernel(const __grid_constant__ RasterParams p)
                         const unsigned idx = base + (unsigned)__popc(need_mask & ((1u << lane) - 1u));
                         if(idx < cnt)
                         {
+                            B200R_ASSERT(off + idx < p.pair_capacity);
                             const unsigned sp = __ldg(p.pair_list + off + idx);
+                            B200R_ASSERT(sp < p.span_capacity);
                             const float4 *S = reinterpret_cast<const float4 *>(p.spans + (size_t)sp*(PHONG ? kSpanWordsPhong : kSpanWords));
                             const float4 q0 = __ldg(S), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
                             prim = __float_as_int(q0.x);
@@ -423,6 +427,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
                                 }
                             }
                             const int xe = min(maxx, xlast);
+                            B200R_ASSERT(y >= ys0 && y < ys0 + rows && minx >= 0);
                             n_left = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
                             if(q3.w < s_rowmin[y - ys0]) n_left = 0;          // cannot win or tie anywhere in its row
                             zrow = plane_addr + (uint32_t)((y - ys0)*TW*4);
@@ -446,7 +451,10 @@ raster_kernel(const __grid_constant__ RasterParams p)
                     float zo[kRound];
 #pragma unroll
                     for(int k = 0; k < kRound; ++k)
+                    {
+                        B200R_ASSERT(!(k < m && 4*k >= lo) || (zaddr + 4u*k >= zrow && zaddr + 4u*k < zrow + (uint32_t)cols*4u));
                         zo[k] = lds_depth_if(zaddr + 4u*k, k < m && 4*k >= lo);   // NaN when not loaded: never >= anything
+                    }
                     const int before = n_left;
 #pragma unroll
                     for(int k = 0; k < kRound; ++k)

@@ -666,6 +666,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             si.tx = (unsigned)tx0 | ((unsigned)tx1 << 16);
             si.span_base = seg_span0;
             si.nrows = span - seg_span0;
+            B200R_ASSERT(seg < seg_at + (unsigned)my_segs && seg < out.seg_capacity);
             out.segs[seg] = si;
             for(int tx = tx0; tx <= tx1; ++tx)
                 atomicAdd(&out.tile_count[(seg_band*v.tiles_x + tx)*kDepthBuckets + bucket], si.nrows);
@@ -768,6 +769,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         }
                         if(in_band)
                         {
+                            B200R_ASSERT(span < span_at + (unsigned)my_spans && span < out.span_capacity);
                             float4 *Q = reinterpret_cast<float4 *>(out.spans + (size_t)span*sw);
                             Q[0] = make_float4(__uint_as_float(prim), __int_as_float(y), __int_as_float(minx), __int_as_float(maxx));
                             Q[1] = make_float4(z, c0, c1, c2);
