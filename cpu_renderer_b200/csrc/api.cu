@@ -203,6 +203,8 @@ static int fill_view(b200r_context *c, const game_render_commands *cmd, const b2
     // layout, not of the mirror's
     if(c->host_alias_rows >= 0) v.alias_rows = c->host_alias_rows;
     if(v.tiles_x > 65535 || v.tiles_y > 65535) return fail(c, B200R_E_UNSUPPORTED, "more than 65535 tiles per axis");
+    // the raster kernel's stash packs (column - tile column) into 19 signed bits
+    if(t->Width > 262143) return fail(c, B200R_E_UNSUPPORTED, "target wider than 262143 pixels");
     return B200R_OK;
 }
 
@@ -536,8 +538,8 @@ int b200r_set_tile(b200r_context *c, int w, int h)
 {
     if(!c) return B200R_E_INVALID;
     if(!((w == 64 && h == 32) || (w == 32 && h == 32) || (w == 128 && h == 16) || (w == 64 && h == 16) ||
-         (w == 128 && h == 32) || (w == 256 && h == 8)))
-        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16, 64x16, 128x32 or 256x8");
+         (w == 128 && h == 32) || (w == 256 && h == 8) || (w == 128 && h == 8) || (w == 256 && h == 4)))
+        return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16, 64x16, 128x32, 256x8, 128x8 or 256x4");
     int rc = b200r_sync(c);
     if(rc != B200R_OK) return rc;
     c->tile_w = w; c->tile_h = h;
@@ -927,7 +929,7 @@ static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     // a 1x1 dummy band keeps the tile bookkeeping trivial.
     b200r_device_target t;
     memset(&t, 0, sizeof(t));
-    t.Width = 1 << 20; t.Height = 1 << 20; t.BandFirstRow = 0; t.BandRows = 1;
+    t.Width = 1 << 17; t.Height = 1 << 20; t.BandFirstRow = 0; t.BandRows = 1;
     t.ColorPitch = t.Width*4; t.DepthStride = t.Width;
     t.Color = (u32 *)16; t.Depth = (r32 *)16;    // never dereferenced: raster is not launched
     ViewParams v;

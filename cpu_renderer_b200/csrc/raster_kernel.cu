@@ -35,6 +35,23 @@ namespace b200r {
 
 struct __align__(16) Pixel { unsigned z, prim, color, pad; };
 
+// -DB200R_STATS: developer build that counts what the lanes do (tools/raster_stats.py); never shipped
+#if defined(B200R_STATS)
+__device__ unsigned long long g_raster_stats[32];
+#define STAT_CLK_ADD(i, v) atomicAdd(&g_raster_stats[i], (unsigned long long)(v))
+#if B200R_STATS == 2                       // clocks only: the counters' atomics distort them
+#define STAT_ADD(i, v) ((void)0)
+#else
+#define STAT_ADD(i, v) atomicAdd(&g_raster_stats[i], (unsigned long long)(v))
+#endif
+#define STAT_WARP(i, v) do { if((threadIdx.x & 31) == 0) STAT_ADD(i, v); } while(0)
+#define STAT_CLOCK(var) const long long var = clock64()
+#else
+#define STAT_ADD(i, v) ((void)0)
+#define STAT_WARP(i, v) ((void)0)
+#define STAT_CLOCK(var) ((void)0)
+#endif
+
 // shared-state-space (32-bit) addressing: no generic-address conversion in the pixel loop
 __device__ __forceinline__ Pixel lds_pixel(uint32_t addr)
 {
@@ -177,6 +194,24 @@ __device__ __noinline__ uint32_t tex_pixel(const ViewParams &v, const TexDesc *t
 #define B200R_ROUND 4
 #endif
 constexpr int kRound = B200R_ROUND;
+// Pixels a parked lane may update in one visit of the update path while its run of passing pixels lasts.
+#ifndef B200R_HOT
+#define B200R_HOT 4
+#endif
+constexpr int kHot = B200R_HOT;
+// Spans a lane may take (and cull) in one visit of the refill path.
+#ifndef B200R_CULL_TRIES
+#define B200R_CULL_TRIES 3
+#endif
+constexpr int kCullTries = B200R_CULL_TRIES;
+// queue entries between two recomputations of a tile's depth floors
+#ifndef B200R_FLOOR_EVERY
+#define B200R_FLOOR_EVERY 256
+#endif
+// resident CTAs per SM the register allocation is held to (a 40 KB tile allows 5)
+#ifndef B200R_MINB
+#define B200R_MINB 5
+#endif
 
 template<int TW, int TH>
 struct TileLayout
@@ -196,7 +231,7 @@ struct TileLayout
 // __grid_constant__: the shaders below take p.v by reference; without it the parameter struct is
 // copied to local memory first (440 bytes of stack in the general kernel).
 template<int TW, int TH, int WARPS, int MODE>
-__global__ void __launch_bounds__(WARPS*32)
+__global__ void __launch_bounds__(WARPS*32, (MODE == kRasterGeneral ? 3 : B200R_MINB)*8/WARPS)
 raster_kernel(const __grid_constant__ RasterParams p)
 {
     constexpr bool PHONG = MODE == kRasterGeneral;         // normals, lighting, 24-word records
@@ -207,10 +242,15 @@ raster_kernel(const __grid_constant__ RasterParams p)
     constexpr int NT = WARPS*32;
     constexpr int PPT = NPIX/NT;                           // pixels per thread when (un)packing
     static_assert(NPIX % NT == 0, "tile must divide evenly over the CTA");
+    static_assert(TW <= 256 && TH <= 32, "stash entries hold 8 bits of tile column and 5 bits of tile row");
     using Layout = TileLayout<TW, TH>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned s_tile, s_ticket;
-    __shared__ float s_rowmin[TH];                        // lower bound of the depth of each tile row
+    constexpr int kBlocks = TW/32;                         // depth floors are kept per tile row and 32-pixel block
+    __shared__ float s_floor[TH][kBlocks];                 // lower bound of the depths of a block
+    // per warp: the spans of its last queue chunk that survived the cull
+    // { span, tile row | (last column - tile's first column) << 5 | (first column - tile's first column) << 13 }
+    __shared__ uint2 s_stash[WARPS][32];
 
     if(*p.overflow) return;                                // host grows the lists and re-issues the frame
 
@@ -244,7 +284,8 @@ raster_kernel(const __grid_constant__ RasterParams p)
         const int ys0 = p.v.band_y0 + yb;                  // screen row of the tile's first row
         const int cols = min(TW, p.v.width - x0);
         const int rows = min(TH, band_rows - yb);
-        if(cnt == 0) { __syncthreads(); continue; }
+        if(cnt == 0) { if(tid == 0) STAT_ADD(18, 1); __syncthreads(); continue; }
+        STAT_CLOCK(t0);
 
         // ---------------- stage the tile: depth -> plane, colour -> cstage ------------------
         bulk_wait_read();                                  // the previous tile's stores have read the plane and [0, 4N)
@@ -272,6 +313,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
             }
             __syncthreads();
         }
+        STAT_CLOCK(t1);
         // expand to { z, owner = -1, colour, 0 }: owner -1 is "already in the target", wins ties
         {
             float zr[PPT]; uint32_t cr[PPT];
@@ -287,29 +329,43 @@ raster_kernel(const __grid_constant__ RasterParams p)
         }
         __syncthreads();
 
-        // Conservative per-row depth floor for span culling.  Depth only ever rises, so a value
-        // read while other warps update pixels is at worst too low; recomputed now and every
-        // kFloorEvery spans.  A span whose depth upper bound (set-up kernel) is strictly below its
-        // row's floor cannot win or tie any pixel and is skipped without walking it.
-        constexpr unsigned kFloorEvery = 256;
+        // Conservative depth floors for span culling, one per tile row and 32-pixel block.  Depth only
+        // ever rises, so a value read while other warps update pixels is at worst too low; recomputed
+        // now and every kFloorEvery queue entries.  A span whose depth upper bound (set-up kernel) is
+        // strictly below the floor of every block it touches cannot win or tie any pixel and is
+        // skipped without walking it.
+        constexpr unsigned kFloorEvery = B200R_FLOOR_EVERY;
         const int warp_id = tid >> 5;
         auto refresh_row_floor = [&](int first_row, int row_step)
         {
+            const float inf = __int_as_float(0x7f800000);
             for(int r = first_row; r < TH; r += row_step)
             {
-                float m = __int_as_float(0x7f800000);
-                for(int c = lane; c < TW; c += 32)
-                {
-                    const float zz = lds_depth(smem_addr(zplane + r*TW + c));
-                    if(c < cols && zz < m) m = zz;                // a NaN depth never lets anything pass: no constraint
-                }
 #pragma unroll
-                for(int d = 16; d >= 1; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
-                if(lane == 0) s_rowmin[r] = (r < rows) ? m : __int_as_float(0x7f800000);
+                for(int c4 = lane; c4 < (TW/4 + 31)/32*32; c4 += 32)
+                {
+                    float m = inf;                                   // a NaN depth never lets anything pass: no constraint
+                    if(c4 < TW/4 && r < rows)
+                    {
+                        float4 q;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                                     : "r"(smem_addr(zplane + r*TW + 4*c4)) : "memory");
+                        const int c = 4*c4;
+                        if(c + 0 < cols) m = fminf(m, q.x);
+                        if(c + 1 < cols) m = fminf(m, q.y);
+                        if(c + 2 < cols) m = fminf(m, q.z);
+                        if(c + 3 < cols) m = fminf(m, q.w);
+                    }
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    if((lane & 7) == 0 && c4 < TW/4) s_floor[r][c4 >> 3] = m;
+                }
             }
         };
         refresh_row_floor(warp_id, WARPS);
         __syncthreads();
+        STAT_CLOCK(t2);
 
         // ---------------- rasterise the tile's span queue: persistent lanes --------------------
         {
@@ -327,84 +383,155 @@ raster_kernel(const __grid_constant__ RasterParams p)
             uint32_t zrow = plane_addr;                    // shared address of the depth of the row's first pixel IN the tile
             uint32_t zaddr = plane_addr;                   // ... of the lane's current pixel; below zrow: left of the tile
             bool guarded = false, exhausted = false, pending = false;
+            // the warp's stash (warp-uniform): entries [stash_pos, stash_n) are still to hand out
+            unsigned stash_n = 0, stash_pos = 0;
+            bool queue_done = false;
+            unsigned retired_mask = 0;
             while(true)
             {
+                // every lane is parked, walking, idle or retired; retired_mask only changes in the refill path
                 const unsigned pend_mask = __ballot_sync(FULL, pending);
                 const unsigned busy_mask = __ballot_sync(FULL, n_left > 0 && !pending);
-                const unsigned need_mask = __ballot_sync(FULL, n_left == 0 && !exhausted);
+                const unsigned need_mask = ~(pend_mask | busy_mask | retired_mask);
                 if((need_mask | busy_mask | pend_mask) == 0) break;
+                STAT_WARP(22, 1);
 
                 if(pend_mask && (busy_mask == 0 || __popc(pend_mask) >= kPend))
                 {
                     // ---- depth-test passes, projekt.cpp:520-529: pack + one 128-bit compare-and-swap ----
-                    if(pending)
+                    // Visible pixels come in runs: a lane whose NEXT pixel passes the early test as well
+                    // stays here ("hot") for up to kHot pixels instead of going back through a pixel round
+                    // to be parked again one pixel later.
+                    STAT_WARP(6, 1); STAT_WARP(7, __popc(pend_mask));
+                    for(int h = 0; ; )
                     {
-                        const uint32_t pa = tile_addr + (zaddr - plane_addr)*4u;
-                        const int x = x0 + ((int)(zaddr - zrow) >> 2);
-                        B200R_ASSERT(zaddr >= zrow && zaddr < zrow + (uint32_t)cols*4u && zrow >= plane_addr &&
-                                     zrow < plane_addr + (uint32_t)(rows*TW*4) && n_left > 0);
-                        Pixel mine;
-                        mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
-                        if(PHONG && tex_id >= 0)
-                            mine.color = tex_pixel(p.v, p.textures, tex_id, c0, c1, c2, phong_span, n0, n1, n2,
-                                                   fadd((float)x, shade_dx), shade_row, z);
-                        else if(MODE == kRasterTextured && tex_id >= 0)
+                        if(pending)
                         {
-                            // projekt.cpp:427-446, unlit: the texel word itself (see tex_pixel)
-                            const TexDesc td = (tex_id < kMaxSharedTex) ? s_tex[tex_id] : p.textures[tex_id];
-                            const float inv = fdiv(1.0f, c2);
-                            const float tx = fmul(fmul(inv, c0), (float)(td.w - 1)), ty = fmul(fmul(inv, c1), (float)(td.h - 1));
-                            const int ix = min(max(round_s32(tx), 0), td.w - 1), iy = min(max(round_s32(ty), 0), td.h - 1);
-                            mine.color = __ldg(reinterpret_cast<const uint32_t *>(
-                                reinterpret_cast<const unsigned char *>(td.mem) + (size_t)iy*(size_t)td.pitch) + ix);
+                            const uint32_t pa = tile_addr + (zaddr - plane_addr)*4u;
+                            const int x = x0 + ((int)(zaddr - zrow) >> 2);
+                            B200R_ASSERT(zaddr >= zrow && zaddr < zrow + (uint32_t)cols*4u && zrow >= plane_addr &&
+                                         zrow < plane_addr + (uint32_t)(rows*TW*4) && n_left > 0);
+                            Pixel old = lds_pixel(pa);
+                            Pixel mine;
+                            mine.z = __float_as_uint(z); mine.prim = (unsigned)prim;
+                            if(PHONG && tex_id >= 0)
+                                mine.color = tex_pixel(p.v, p.textures, tex_id, c0, c1, c2, phong_span, n0, n1, n2,
+                                                       fadd((float)x, shade_dx), shade_row, z);
+                            else if(MODE == kRasterTextured && tex_id >= 0)
+                            {
+                                // projekt.cpp:427-446, unlit: the texel word itself (see tex_pixel)
+                                const TexDesc td = (tex_id < kMaxSharedTex) ? s_tex[tex_id] : p.textures[tex_id];
+                                const float inv = fdiv(1.0f, c2);
+                                const float tx = fmul(fmul(inv, c0), (float)(td.w - 1)), ty = fmul(fmul(inv, c1), (float)(td.h - 1));
+                                const int ix = min(max(round_s32(tx), 0), td.w - 1), iy = min(max(round_s32(ty), 0), td.h - 1);
+                                mine.color = __ldg(reinterpret_cast<const uint32_t *>(
+                                    reinterpret_cast<const unsigned char *>(td.mem) + (size_t)iy*(size_t)td.pitch) + ix);
+                            }
+                            else
+                                mine.color = (PHONG && phong_span)
+                                             ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
+                                             : pack_argb(c0, c1, c2, c3, guarded);
+                            mine.pad = 0;
+                            float now = z;                                              // the word's depth when we leave
+                            while(true)
+                            {
+                                const float oz = __uint_as_float(old.z);
+                                const int op = (int)old.prim;
+                                if(!(z > oz || (z == oz && prim < op))) { now = oz; STAT_ADD(10, 1); break; }   // :525 + tie rule
+                                const Pixel prev = cas_pixel(pa, old, mine);
+                                STAT_ADD(8, 1);
+                                // (depth, owner) identify a pixel's contents: no need to compare the colour
+                                if(prev.z == old.z && prev.prim == old.prim) break;
+                                STAT_ADD(9, 1);
+                                old = prev;
+                            }
+                            sts_depth(zaddr, now);                                      // never above the word's depth
+                            if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
+                            c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
+                            z = fadd(z, zi);                                                              // :535
+                            zaddr += 4u; --n_left;
+                            // the next pixel lies in the tile (n_left counts pixels up to the tile's last column)
+                            pending = kHot > 1 && n_left > 0 && z >= lds_depth(zaddr);
                         }
-                        else
-                            mine.color = (PHONG && phong_span)
-                                         ? phong_pixel(p.v, c0, c1, c2, c3, n0, n1, n2, fadd((float)x, shade_dx), shade_row, z, true)
-                                         : pack_argb(c0, c1, c2, c3, guarded);
-                        mine.pad = 0;
-                        Pixel old = lds_pixel(pa);
-                        float now = z;                                              // the word's depth when we leave
-                        while(true)
-                        {
-                            const float oz = __uint_as_float(old.z);
-                            const int op = (int)old.prim;
-                            if(!(z > oz || (z == oz && prim < op))) { now = oz; break; }   // :525 + tie rule
-                            const Pixel prev = cas_pixel(pa, old, mine);
-                            if(prev.z == old.z && prev.prim == old.prim && prev.color == old.color) break;
-                            old = prev;
-                        }
-                        sts_depth(zaddr, now);                                      // never above the word's depth
-                        if(PHONG && phong_span) { n0 = fadd(n0, ni0); n1 = fadd(n1, ni1); n2 = fadd(n2, ni2); normalize3r(n0, n1, n2); }   // :504
-                        c0 = fadd(c0, i0); c1 = fadd(c1, i1); c2 = fadd(c2, i2); c3 = fadd(c3, i3);   // :534
-                        z = fadd(z, zi);                                                              // :535
-                        zaddr += 4u; --n_left;
-                        pending = false;
+                        if(++h >= kHot) break;
+                        const unsigned hot_mask = __ballot_sync(FULL, pending);
+                        if(hot_mask == 0 || (busy_mask != 0 && __popc(hot_mask) < kPend)) break;
+                        STAT_WARP(26, 1); STAT_WARP(27, __popc(hot_mask));
                     }
                 }
                 else if(need_mask && (busy_mask == 0 || __popc(need_mask) >= kRefill))
                 {
-                    // ---- idle lanes take the next spans of the queue: one ticket per warp ----
-                    const bool need = n_left == 0 && !exhausted;
-                    const int leader = __ffs(need_mask) - 1;
-                    unsigned base = 0;
-                    const unsigned take = (unsigned)__popc(need_mask);
-                    if(lane == leader) base = atomicAdd(&s_ticket, take);
-                    base = __shfl_sync(FULL, base, leader);
-                    if(base/kFloorEvery != (base + take)/kFloorEvery && base < cnt) refresh_row_floor(0, 1);
-                    if(need)
+                    // ---- idle lanes take the next spans of the queue ----
+                    // The WARP takes a chunk of 32 queue entries with one ticket on the tile's counter: all 32
+                    // lanes load one entry's column range and depth bound each and cull it against the depth
+                    // floors of the blocks it touches (more than half of C3's entries die here; doing it at
+                    // full lane width costs a third of per-lane culling).  The survivors are compacted into the
+                    // warp's stash in shared memory; idle lanes pop them, a few at a time, without a global
+                    // ticket.  A chunk whose entries are all culled is replaced at once.
+                    STAT_WARP(11, 1); STAT_WARP(12, __popc(need_mask));
+                    for(int tries = 0; stash_pos >= stash_n && !queue_done && tries < kCullTries; ++tries)
                     {
-                        const unsigned idx = base + (unsigned)__popc(need_mask & ((1u << lane) - 1u));
-                        if(idx < cnt)
+                        unsigned b = 0;
+                        if(lane == 0) b = atomicAdd(&s_ticket, 32u);
+                        b = __shfl_sync(FULL, b, 0);
+                        if(b >= cnt) { queue_done = true; break; }
+                        const unsigned chunk_n = min(32u, cnt - b);
+                        B200R_ASSERT(off + b + chunk_n <= p.pair_capacity);
+                        if(b/kFloorEvery != (b + 32u)/kFloorEvery) refresh_row_floor(0, 1);
+                        bool live = false;
+                        uint2 e = make_uint2(0u, 0u);
+                        if((unsigned)lane < chunk_n)
                         {
-                            B200R_ASSERT(off + idx < p.pair_capacity);
-                            const unsigned sp = __ldg(p.pair_list + off + idx);
+                            const unsigned sp = __ldg(p.pair_list + off + b + lane);
                             B200R_ASSERT(sp < p.span_capacity);
                             const float4 *S = reinterpret_cast<const float4 *>(p.spans + (size_t)sp*(PHONG ? kSpanWordsPhong : kSpanWords));
-                            const float4 q0 = __ldg(S), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
-                            prim = __float_as_int(q0.x);
+                            const float4 q0 = __ldg(S), q3 = __ldg(S + 3);
                             const int y = __float_as_int(q0.y);
                             const int minx = __float_as_int(q0.z), maxx = __float_as_int(q0.w);
+                            const int xe = min(maxx, xlast), xs = max(minx, x0);
+                            B200R_ASSERT(y >= ys0 && y < ys0 + rows && minx >= 0);
+                            const int n = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
+                            STAT_ADD(3, 1); if(n == 0) STAT_ADD(5, 1);
+                            if(n > 0)
+                            {
+                                const int b0 = (xs - x0) >> 5, b1 = (xe - x0) >> 5;
+                                float fl = __int_as_float(0x7f800000);
+#pragma unroll
+                                for(int k = 0; k < kBlocks; ++k)
+                                    if(k >= b0 && k <= b1) fl = fminf(fl, s_floor[y - ys0][k]);
+                                live = !(q3.w < fl);                          // below every floor: cannot win or tie anywhere
+                                if(!live) STAT_ADD(4, 1);
+                                e = make_uint2(sp, (unsigned)(y - ys0) | ((unsigned)(xe - x0) << 5) | ((unsigned)(minx - x0) << 13));
+                                if(live) { STAT_ADD(2, max(x0 - minx, 0)); STAT_ADD(1, n - max(x0 - minx, 0)); }
+                            }
+                        }
+                        const unsigned lm = __ballot_sync(FULL, live);
+                        if(live) s_stash[warp_id][__popc(lm & ((1u << lane) - 1u))] = e;
+                        stash_n = (unsigned)__popc(lm); stash_pos = 0;
+                        __syncwarp();
+                    }
+                    const bool need = n_left == 0 && !exhausted;
+                    const unsigned avail = stash_n - stash_pos;
+                    if(avail == 0)
+                    {
+                        // nothing to hand out: the queue is finished (lanes retire), or kCullTries chunks in a
+                        // row were culled completely (the lanes ask again)
+                        if(need && queue_done) exhausted = true;
+                        retired_mask = __ballot_sync(FULL, exhausted);
+                    }
+                    else
+                    {
+                        const unsigned rank = (unsigned)__popc(need_mask & ((1u << lane) - 1u));
+                        if(need && rank < avail)
+                        {
+                            const uint2 e = s_stash[warp_id][stash_pos + rank];
+                            const float4 *S = reinterpret_cast<const float4 *>(p.spans + (size_t)e.x*(PHONG ? kSpanWordsPhong : kSpanWords));
+                            const float4 q0 = __ldg(S), q1 = __ldg(S + 1), q2 = __ldg(S + 2), q3 = __ldg(S + 3);
+                            const int first = (int)e.y >> 13;                        // first column - x0: negative left of the tile
+                            n_left = (int)((e.y >> 5) & 255u) - first + 1;
+                            zrow = plane_addr + (e.y & 31u)*(uint32_t)(TW*4);
+                            zaddr = zrow + (uint32_t)(first*4);                       // wraps below zrow left of the tile
+                            prim = __float_as_int(q0.x);
                             z = q1.x; c0 = q1.y; c1 = q1.z; c2 = q1.w;
                             c3 = q2.x; zi = q2.y; i0 = q2.z; i1 = q2.w;
                             i2 = q3.x; i3 = q3.y;
@@ -418,7 +545,7 @@ raster_kernel(const __grid_constant__ RasterParams p)
                             {
                                 const unsigned fl = __float_as_uint(q3.z);
                                 phong_span = (fl & kSpanPhong) != 0;
-                                shade_dx = 0.0f; shade_row = (float)y;
+                                shade_dx = 0.0f; shade_row = (float)__float_as_int(q0.y);
                                 if(phong_span)
                                 {
                                     const float4 q4 = __ldg(S + 4), q5 = __ldg(S + 5);
@@ -426,17 +553,9 @@ raster_kernel(const __grid_constant__ RasterParams p)
                                     if(fl & kSpanAlias) { shade_dx = q4.w; shade_row = q5.x; ni0 = ni1 = ni2 = 0.0f; }
                                 }
                             }
-                            const int xe = min(maxx, xlast);
-                            B200R_ASSERT(y >= ys0 && y < ys0 + rows && minx >= 0);
-                            n_left = (minx <= xe && maxx >= x0) ? (xe - minx + 1) : 0;
-                            if(q3.w < s_rowmin[y - ys0]) n_left = 0;          // cannot win or tie anywhere in its row
-                            zrow = plane_addr + (uint32_t)((y - ys0)*TW*4);
-                            zaddr = zrow + (uint32_t)((minx - x0)*4);         // wraps below zrow for pixels left of the tile
                         }
-                        else
-                        {
-                            exhausted = true;
-                        }
+                        stash_pos += min((unsigned)__popc(need_mask), avail);
+                        __syncwarp();
                     }
                     continue;
                 }
@@ -447,6 +566,8 @@ raster_kernel(const __grid_constant__ RasterParams p)
                 // nearly every pixel, high-overdraw scenes rarely: both stay converged).
                 {
                     const int m = pending ? 0 : n_left;                       // pixels this lane may visit in this round
+                    STAT_WARP(0, 1); STAT_WARP(19, __popc(busy_mask)); STAT_WARP(20, __popc(pend_mask)); STAT_WARP(21, __popc(need_mask));
+                    STAT_ADD(23, min(m, kRound));
                     const int lo = max((int)(zrow - zaddr), 0);               // bytes until the lane's first pixel IN the tile
                     float zo[kRound];
 #pragma unroll
@@ -472,7 +593,9 @@ raster_kernel(const __grid_constant__ RasterParams p)
                 }
             }
         }
+        STAT_CLOCK(t3);
         __syncthreads();
+        STAT_CLOCK(t4);
 
         // ---------------- write the tile back: depth into the plane, colour packed to [0, 4N) ------
         {
@@ -505,9 +628,31 @@ raster_kernel(const __grid_constant__ RasterParams p)
                 }
             }
         }
+#if defined(B200R_STATS)
+        {
+            const long long t5 = clock64();
+            if(lane == 0)
+            {
+                STAT_CLK_ADD(13, t1 - t0); STAT_CLK_ADD(14, t2 - t1); STAT_CLK_ADD(15, t3 - t2); STAT_CLK_ADD(16, t4 - t3); STAT_CLK_ADD(24, t5 - t4);
+                STAT_CLK_ADD(25, 1);
+            }
+            if(tid == 0) STAT_ADD(17, 1);
+        }
+#endif
     }
     bulk_wait_read();
 }
+
+#if defined(B200R_STATS)
+extern "C" int b200r_debug_raster_stats(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_raster_stats, sizeof(g_raster_stats));
+    if(e != cudaSuccess) return -2;
+    if(reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(g_raster_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // cudaFuncSetAttribute and the occupancy answer are per DEVICE: keep them per device ordinal
 // (a process may hold contexts on several GPUs).
@@ -554,6 +699,8 @@ static cudaError_t launch_mode(const RasterParams &p, int sm_count, cudaStream_t
     if(tw == 64 && th == 16) return launch_one<64, 16, 8, MODE>(p, sm_count, s);     // 20 KB
     if(tw == 128 && th == 32) return launch_one<128, 32, 8, MODE>(p, sm_count, s);   // 80 KB
     if(tw == 256 && th == 8) return launch_one<256, 8, 8, MODE>(p, sm_count, s);     // 40 KB
+    if(tw == 128 && th == 8) return launch_one<128, 8, 4, MODE>(p, sm_count, s);     // 20 KB, 4 warps
+    if(tw == 256 && th == 4) return launch_one<256, 4, 4, MODE>(p, sm_count, s);     // 20 KB, 4 warps
     return cudaErrorInvalidValue;
 }
 
