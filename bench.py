@@ -427,10 +427,11 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
         scene = sc.textured(scene, TEX_SIZE, TEX_SIZE, lo=0.05, hi=0.95)
     ntri, W, H = scene.triangle_count, scene.width, scene.height
     wpad = (W + 63) // 64 * 64
-    tile = tile or {"c3": "128x16", "c4": "64x32"}.get(cfgname, "64x32")
+    tile = tile or "0x0"                        # 0x0: the library picks (64x16 for small triangles, 128x8 otherwise)
     tw, th = (int(x) for x in tile.split("x"))
     r.set_stream(stream.cuda_stream)
     r.set_tile(tw, th)
+    th = th or 32                               # row bands are split in multiples of this (any tile height divides it)
     flags = api.DEFER_VERDICT if args.defer_verdict else 0
 
     d_pos = torch.from_numpy(scene.positions).to(dev)
@@ -712,7 +713,8 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
                    "parallelism": ({"c4": f"screen-space row bands x{world}", "c5": f"{C5_VIEWS} views over {world} ranks"}
                                    .get(cfgname, f"frame-parallel x{world}") if world > 1 else "1 GPU"),
                    "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": scale,
-                   "tile": tile,
+                   "tile": (tile if tile != "0x0" else
+                            "auto:" + ("64x16" if W * band_rows / max(ntri, 1) < 4.0 else "128x8")),
                    "timing": f"median of {passes} passes of exactly {K} steps, per pass the max over ranks (CUDA events)",
                    "l2": "each timed frame streams >126 MB (vertices + records + pair lists + its own "
                          "pre-cleared target), i.e. inputs larger than L2; no explicit flush",

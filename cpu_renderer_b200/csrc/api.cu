@@ -15,6 +15,7 @@
 #include "raster_device.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,6 +63,9 @@ struct FrameWords
     unsigned long long counters[4];     // binned triangles, queue entries, segments, spans
     unsigned seg_fill[kSubAllocators];
     unsigned span_fill[kSubAllocators];
+    unsigned scan_ticket;               // look-back scan of the bin counts: chunk numbers
+    unsigned pad_;
+    unsigned long long scan_state[kScanMaxChunks];   // ... and the published chunk sums / prefixes
 };
 
 } // namespace
@@ -75,6 +79,7 @@ struct b200r_context
     cudaEvent_t total_ready = nullptr;
     std::string error;
     int tile_w = 64, tile_h = 32;
+    bool tile_auto = true;              // b200r_set_tile(0, 0): the render call picks the tile from the triangle density
     int span_words = kSpanWords;        // of the last issued frame (kSpanWordsPhong if it had a Phong mesh)
     int refill_lanes = 12, pend_lanes = 4;   // raster_kernel thresholds (env B200R_REFILL / B200R_PEND)
 
@@ -208,12 +213,25 @@ static int fill_view(b200r_context *c, const game_render_commands *cmd, const b2
     return B200R_OK;
 }
 
+// Automatic tile shape (b200r_set_tile(0, 0), the default).  Small triangles (a few pixels of target per
+// triangle) bin and rasterise best in 64x16 tiles: short spans, little replay, many tiles in flight.
+// Larger ones take 128x8: spans cross fewer tile columns.  Both are 20 KB tiles, run by 8 and 4 warps
+// (measured on C2 / C3 / C4, profiles/README.md).
+static void choose_tile(b200r_context *c, uint64_t triangles, int width, int rows)
+{
+    if(!c->tile_auto) return;
+    const double px_per_tri = (double)width*(double)(rows > 0 ? rows : 0)/(double)(triangles ? triangles : 1);
+    if(px_per_tri < 4.0) { c->tile_w = 64; c->tile_h = 16; } else { c->tile_w = 128; c->tile_h = 8; }
+}
+
 // Enqueue every kernel of the frame described by c->view / c->meshes / c->target.
 static int issue_frame(b200r_context *c)
 {
     const ViewParams &v = c->view;
     const unsigned ntiles = c->ntiles;
     const unsigned nbins = ntiles*kDepthBuckets;        // one sub-queue per tile and depth bucket
+    if((unsigned long long)ntiles*kDepthBuckets > (unsigned long long)kScanMaxChunks*8192ull)
+        return fail(c, B200R_E_UNSUPPORTED, "more than 16 M (tile, depth bucket) bins in one band");
     unsigned *tile_count = (unsigned *)c->tiles.ptr;
     unsigned *tile_fill = tile_count + nbins;
     unsigned *tile_offset = tile_fill + nbins;          // nbins + 1 entries
@@ -316,7 +334,7 @@ static int issue_frame(b200r_context *c)
     }
     }
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[1], c->stream));
-    launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, tile_offset + nbins + 1, c->stream);
+    launch_tile_scan(tile_count, tile_offset, nbins, &words->pair_total, words->scan_state, &words->scan_ticket, c->stream);
     c->stats.KernelLaunches += 1;
     const unsigned pair_cap_f = (unsigned)(c->pairs.bytes/sizeof(unsigned));
     FinalizeParams fp;
@@ -327,7 +345,7 @@ static int issue_frame(b200r_context *c)
     launch_finalize(fp, c->stream);
     c->stats.KernelLaunches += 1;
     if(c->profiling) CU(cudaEventRecord(c->stage_ev[2], c->stream));
-    CU(cudaMemcpyAsync(c->h_words, words, sizeof(FrameWords), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_words, words, offsetof(FrameWords, scan_ticket), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaEventRecord(c->total_ready, c->stream));
 
     const unsigned pair_cap = (unsigned)(c->pairs.bytes/sizeof(unsigned));
@@ -537,12 +555,13 @@ int b200r_sync(b200r_context *c)
 int b200r_set_tile(b200r_context *c, int w, int h)
 {
     if(!c) return B200R_E_INVALID;
+    if(w == 0 && h == 0) { c->tile_auto = true; return B200R_OK; }
     if(!((w == 64 && h == 32) || (w == 32 && h == 32) || (w == 128 && h == 16) || (w == 64 && h == 16) ||
          (w == 128 && h == 32) || (w == 256 && h == 8) || (w == 128 && h == 8) || (w == 256 && h == 4)))
         return fail(c, B200R_E_INVALID, "tile must be 64x32, 32x32, 128x16, 64x16, 128x32, 256x8, 128x8 or 256x4");
     int rc = b200r_sync(c);
     if(rc != B200R_OK) return rc;
-    c->tile_w = w; c->tile_h = h;
+    c->tile_w = w; c->tile_h = h; c->tile_auto = false;
     return B200R_OK;
 }
 
@@ -563,6 +582,12 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
         const bool ph = (meshes[i].Flags & B200R_MESH_PHONG) != 0;
         any_phong |= ph; all_phong &= ph;
         any_tex |= meshes[i].Texture != nullptr;
+    }
+    if(target)
+    {
+        uint64_t tris = 0;
+        for(u32 i = 0; i < mesh_count; ++i) tris += meshes[i].TriangleCount;
+        choose_tile(c, tris, target->Width, target->BandRows);
     }
     ViewParams v;
     rc = fill_view(c, cmd, target, v, all_phong);
@@ -828,6 +853,11 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     CU(c->d_depth.reserve((size_t)wpad*H*4));
     // 3. the targets, last: only the raster kernel reads them -- band by band of tile rows, so that
     //    the first band can be rastered and read back while the others are still being uploaded
+    {
+        uint64_t tris = 0;
+        for(const b200r_device_mesh &m : meshes) tris += m.TriangleCount;
+        choose_tile(c, tris, W, H);             // the same answer b200r_render_device gets below
+    }
     const int tiles_y = (H + c->tile_h - 1)/c->tile_h;
     c->host_bands = (tiles_y >= 2*kHostBands) ? kHostBands : 1;
     c->host_out.color = out->Memory; c->host_out.color_pitch = (size_t)out->Pitch;

@@ -109,20 +109,36 @@ __global__ void finalize_kernel(const FinalizeParams p)
     }
 }
 
-// Large bin counts (16K^2 targets: 1 M bins) use a three-step scan: per-CTA scans of 8192-element
-// chunks, the single-CTA scan over the chunk totals, then a uniform add.
+// More than one chunk of bins: ONE launch, a chained scan with decoupled look-back.  CTAs take chunk
+// numbers from a ticket (so every chunk's predecessors are running or done), scan their 8192 bins
+// locally, publish their sum, and add up the published sums / prefixes of the chunks before them.
+// state[c] = flag << 32 | value, flag 1: the chunk's own sum, flag 2: the inclusive prefix up to it.
 constexpr unsigned kChunk = kScanThreads*8;
 
 __global__ void __launch_bounds__(kScanThreads)
-chunk_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offset, unsigned n,
-                  unsigned *__restrict__ chunk_sums)
+lookback_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ offset, unsigned n,
+                     unsigned *__restrict__ total, unsigned long long *state, unsigned *ticket)
 {
     __shared__ unsigned warp_sums[kScanThreads/32];
+    __shared__ unsigned s_chunk, s_prefix;
     const unsigned t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const unsigned lo = min(blockIdx.x*kChunk + t*8, n), hi = min(lo + 8, n);
+    if(t == 0) s_chunk = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned chunk = s_chunk;
+    const unsigned lo = min(chunk*kChunk + t*8, n), hi = min(lo + 8, n);
     unsigned v[8], sum = 0;
+    if(hi - lo == 8 && (lo & 3u) == 0)
+    {
+        const uint4 a = *reinterpret_cast<const uint4 *>(count + lo), b = *reinterpret_cast<const uint4 *>(count + lo + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    else
+    {
 #pragma unroll
-    for(int i = 0; i < 8; ++i) { v[i] = (lo + i < hi) ? count[lo + i] : 0u; sum += v[i]; }
+        for(int i = 0; i < 8; ++i) v[i] = (lo + i < hi) ? count[lo + i] : 0u;
+    }
+#pragma unroll
+    for(int i = 0; i < 8; ++i) sum += v[i];
     unsigned incl = sum;
 #pragma unroll
     for(int d = 1; d < 32; d <<= 1)
@@ -142,38 +158,49 @@ chunk_scan_kernel(const unsigned *__restrict__ count, unsigned *__restrict__ off
             if(lane >= (unsigned)d) wi += up;
         }
         warp_sums[lane] = wi - w;
-        if(lane == 31) chunk_sums[blockIdx.x] = wi;
+        if(lane == 31)
+        {
+            // publish, then look back
+            const unsigned aggregate = wi;
+            volatile unsigned long long *st = state;
+            unsigned prefix = 0;
+            if(chunk > 0)
+            {
+                st[chunk] = (1ull << 32) | aggregate;
+                __threadfence();
+                for(int j = (int)chunk - 1; j >= 0; )
+                {
+                    const unsigned long long sv = st[j];
+                    const unsigned flag = (unsigned)(sv >> 32);
+                    if(flag == 0u) continue;                     // not published yet
+                    prefix += (unsigned)sv;
+                    if(flag == 2u) break;
+                    --j;
+                }
+            }
+            __threadfence();
+            st[chunk] = (2ull << 32) | (prefix + aggregate);
+            s_prefix = prefix;
+            if(chunk == gridDim.x - 1) { *total = prefix + aggregate; offset[n] = prefix + aggregate; }
+        }
     }
     __syncthreads();
-    unsigned run = warp_sums[warp] + (incl - sum);
+    unsigned run = s_prefix + warp_sums[warp] + (incl - sum);
 #pragma unroll
     for(int i = 0; i < 8; ++i) { if(lo + i < hi) offset[lo + i] = run; run += v[i]; }
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-chunk_add_kernel(unsigned *__restrict__ offset, unsigned n, const unsigned *__restrict__ chunk_offsets,
-                 const unsigned *__restrict__ total)
-{
-    const unsigned add = chunk_offsets[blockIdx.x];
-    const unsigned lo = blockIdx.x*kChunk;
-    for(unsigned i = lo + threadIdx.x; i < min(lo + kChunk, n); i += kScanThreads) offset[i] += add;
-    if(blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) offset[n] = *total;
-}
-
-// scratch: 2*ceil(n/8192) + 1 words
+// state: ceil(n/8192) zeroed 64-bit words, ticket: one zeroed word (both part of the frame's control words)
 void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
-                      unsigned *pair_total, unsigned *scratch, cudaStream_t s)
+                      unsigned *pair_total, unsigned long long *state, unsigned *ticket, cudaStream_t s)
 {
-    if(ntiles <= 4*kChunk)
+    if(ntiles <= kChunk)
     {
         tile_scan_kernel<<<1, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, pair_total);
         return;
     }
     const unsigned chunks = (ntiles + kChunk - 1)/kChunk;
-    unsigned *chunk_sums = scratch, *chunk_offsets = scratch + chunks;
-    chunk_scan_kernel<<<chunks, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, chunk_sums);
-    tile_scan_kernel<<<1, kScanThreads, 0, s>>>(chunk_sums, chunk_offsets, chunks, pair_total);
-    chunk_add_kernel<<<chunks, kScanThreads, 0, s>>>(tile_offset, ntiles, chunk_offsets, pair_total);
+    lookback_scan_kernel<<<chunks, kScanThreads, 0, s>>>(tile_count, tile_offset, ntiles, pair_total, state, ticket);
 }
 
 void launch_scatter(const ScatterParams &p, cudaStream_t s)

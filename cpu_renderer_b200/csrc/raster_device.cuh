@@ -301,8 +301,9 @@ cudaError_t launch_object_walk(const ViewParams &v, const ObjectWalkParams &p, c
 // {zmax, 1/(zmax - zmin)}
 void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s);
 void launch_zrange_finish(unsigned *zkeys, cudaStream_t s);
+constexpr unsigned kScanMaxChunks = 2048;   // look-back scan: 8192 bins per chunk -> 16 M bins per frame
 void launch_tile_scan(const unsigned *tile_count, unsigned *tile_offset, unsigned ntiles,
-                      unsigned *pair_total, unsigned *scratch, cudaStream_t s);
+                      unsigned *pair_total, unsigned long long *state, unsigned *ticket, cudaStream_t s);
 struct ScatterParams
 {
     const SegInfo *segs;

@@ -167,8 +167,10 @@ const char *b200r_last_error(const b200r_context *Context);
 int b200r_set_stream(b200r_context *Context, void *CudaStream);
 int b200r_sync(b200r_context *Context);
 
-/* Screen tile staged in shared memory by the raster kernel: 64x32 (default), 32x32, 128x16,
- * 64x16, 128x32 or 256x8 pixels. */
+/* Screen tile staged in shared memory by the raster kernel: 64x32, 32x32, 128x16, 64x16, 128x32,
+ * 256x8, 128x8 or 256x4 pixels.  0x0 (the default) lets every render call choose: 64x16 for frames of
+ * small triangles (fewer than 4 target pixels per submitted triangle), 128x8 otherwise.  Targets wider
+ * than 262143 pixels are not supported. */
 int b200r_set_tile(b200r_context *Context, int TileWidth, int TileHeight);
 
 /* ------------------------------------------------------------------------------------------
