@@ -538,39 +538,84 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
     stage_ms = {k: float(np.median(v)) for k, v in stage.items()}
     dominant = max(stage_ms, key=stage_ms.get)
 
-    # ---- NCCL gather of the finished colour images to rank 0 (the path's only exchange step) ----
+    # ---- the path's only exchange step: the finished colour images end up on rank 0 -------------
+    # (a) fused: the raster kernel stores every finished tile a second time, straight into rank 0's
+    #     peer-mapped image (b200r_set_gather_target, NVLink); only a stream-ordered barrier follows the frame
+    # (b) for comparison: a torch.distributed gather (NCCL send/recv) behind every frame
     with_gather = None
+    gather_nccl = None
     if world > 1:
-        clear_all()
+        kg = min(K, 10)
+
+        def timed_gather(after_step, passes_g):
+            out = []
+            for _ in range(passes_g):
+                clear_all()
+                ctx.barrier(); torch.cuda.synchronize()
+                with torch.cuda.stream(stream):
+                    ev0.record(stream)
+                    for i in range(kg):
+                        step(i)
+                        after_step(i)                  # stream-ordered after this step's kernels
+                    ev1.record(stream)
+                    r.sync()
+                torch.cuda.synchronize(); ctx.barrier()
+                out.append(ev0.elapsed_time(ev1) / kg)
+            return ctx.max_over_ranks(out)
+
+        fused_ok = cfgname != "c5"                     # c5 renders 32 views per step into one target pair
+        if fused_ok:
+            slots = 1 if cfgname == "c4" else world
+            fg = shard.FusedGather(r, api, H, W, wpad, slots, world, rank, dev, dst=0)
+            fg.select(0 if cfgname == "c4" else rank)
+            clear_all()
+            with torch.cuda.stream(stream):
+                for _ in range(2):                         # warm-up (peer mappings, communicator), untimed
+                    step(0)
+                    fg.finish()
+                r.sync()
+            torch.cuda.synchronize(); ctx.barrier()
+            # what rank 0 now holds must be what the ranks rendered
+            mine = imagehash.image_fnv_torch(colors[0], W) if cfgname != "c4" else None
+            hashes = [None] * world
+            dist.all_gather_object(hashes, mine)
+            gather_ok = None
+            if rank == 0:
+                if cfgname == "c4":
+                    image_fnv = imagehash.image_fnv_torch(fg.color[0], W)      # the image the bands assemble to
+                else:
+                    gather_ok = all(imagehash.image_fnv_torch(fg.color[q], W) == hashes[q] for q in range(world))
+            g_ms = timed_gather(lambda i: fg.finish(), 3)
+            fg.close()
+            with_gather = {"ms_per_step": float(np.median(g_ms)), "ms_per_step_best": float(min(g_ms)),
+                           "what": "fused: raster_kernel stores every finished tile into rank 0's peer-mapped image over NVLink "
+                                   "(b200r_set_gather_target + CUDA IPC); a stream-ordered 4-byte all_reduce as the barrier",
+                           "gather_bytes_per_step": int(H * wpad * 4 * (world - 1) // (world if cfgname == "c4" else 1)),
+                           **({"images_match_the_ranks_frames": gather_ok} if gather_ok is not None else {})}
         if cfgname == "c4":
             gather = lambda t: shard.gather_bands(t, H, world, rank, th, dst=0)      # noqa: E731
         else:
             gl = [torch.empty_like(colors[0]) for _ in range(world)] if rank == 0 else None
             gather = lambda t: dist.gather(t, gl, dst=0)                             # noqa: E731
         gathered = None
+        clear_all()
         with torch.cuda.stream(stream):
             for _ in range(2):                         # communicator set-up and warm-up, untimed
                 step(0)
                 gathered = gather(colors[0])
+            r.sync()
         ctx.barrier(); torch.cuda.synchronize()
-        if cfgname == "c4" and rank == 0:
-            image_fnv = imagehash.image_fnv_torch(gathered, W)      # the image the bands reassemble to
+        if cfgname == "c4" and rank == 0 and not fused_ok:
+            image_fnv = imagehash.image_fnv_torch(gathered, W)
+        nccl_fnv = imagehash.image_fnv_torch(gathered, W) if (cfgname == "c4" and rank == 0) else None
         del gathered
-        kg = min(K, 10)
-        g_ms = []
-        for _ in range(3):
-            with torch.cuda.stream(stream):
-                ev0.record(stream)
-                for i in range(kg):
-                    step(i)
-                    gather(colors[i % nsets])          # stream-ordered after this step's kernels
-                ev1.record(stream)
-            torch.cuda.synchronize(); ctx.barrier()
-            g_ms.append(ev0.elapsed_time(ev1) / kg)
-        g_ms = ctx.max_over_ranks(g_ms)
-        with_gather = {"ms_per_step": float(np.median(g_ms)), "ms_per_step_best": float(min(g_ms)),
-                       "what": "NCCL gather of the finished colour image(s) to rank 0 after every step (torch.distributed.gather)",
-                       "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1))}
+        n_ms = timed_gather(lambda i: gather(colors[i % nsets]), 3 if not fused_ok else 1)
+        gather_nccl = {"ms_per_step": float(np.median(n_ms)), "ms_per_step_best": float(min(n_ms)),
+                       "what": "torch.distributed.gather (NCCL) of the finished colour image(s) to rank 0 after every step",
+                       "gather_bytes_per_step": int(colors[0].numel() * 4 * (world - 1)),
+                       **({"image_fnv": nccl_fnv} if nccl_fnv is not None else {})}
+        if not fused_ok:
+            with_gather, gather_nccl = gather_nccl, None
 
     whole_object = None
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region ---------
@@ -745,6 +790,9 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
     if with_gather:
         with_gather["value"] = to_value(with_gather["ms_per_step"], world)
         rec["with_gather"] = with_gather
+    if gather_nccl:
+        gather_nccl["value"] = to_value(gather_nccl["ms_per_step"], world)
+        rec["with_gather_nccl"] = gather_nccl
     if cpu_baseline and world == 1 and rank == 0:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -781,7 +829,7 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
 def leg_summary(rec):
     """The sub-record of a secondary leg inside the one JSON line."""
     keep = ("metric", "value", "unit", "ms_per_step", "ms_per_step_best", "passes", "steps", "scaling", "stage_ms",
-            "gpu_launches", "image_fnv", "image_fnv_oracle", "image_ok", "with_gather", "binner")
+            "gpu_launches", "image_fnv", "image_fnv_oracle", "image_ok", "with_gather", "with_gather_nccl", "binner")
     out = {k: rec[k] for k in keep if k in rec}
     out["config"] = {k: rec["config"][k] for k in ("workload", "triangles", "width", "height", "parallelism", "band_rows", "tile")}
     out["roofline"] = {k: rec["roofline"][k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",

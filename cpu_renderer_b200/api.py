@@ -24,6 +24,7 @@ EXPORTS = [
     "b200r_create", "b200r_destroy", "b200r_last_error", "b200r_set_stream", "b200r_sync",
     "b200r_set_tile", "b200r_render_objects", "b200r_fill_edge_table", "b200r_render_device",
     "b200r_clear_device", "b200r_get_stats", "b200r_set_profiling", "b200r_get_stage_ms",
+    "b200r_set_gather_target", "b200r_peer_alloc", "b200r_peer_open", "b200r_peer_release",
 ]
 STAGES = ("setup_kernel", "tile_scan_kernel", "scatter_kernel", "raster_kernel")
 
@@ -109,6 +110,11 @@ EDGE_INFO_DTYPE = np.dtype({
     "itemsize": 120})
 
 
+class peer_handle(C.Structure):
+    """b200r_peer_handle: a CUDA IPC memory handle, 64 opaque bytes any transport can carry."""
+    _fields_ = [("Bytes", C.c_ubyte * 64)]
+
+
 class B200RasterError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"b200r status {code}: {message}")
@@ -148,6 +154,10 @@ def load_library():
         lib.b200r_get_stats.argtypes = [ctx, C.POINTER(frame_stats)]
         lib.b200r_set_profiling.argtypes = [ctx, C.c_int]
         lib.b200r_get_stage_ms.argtypes = [ctx, C.POINTER(C.c_float)]
+        lib.b200r_set_gather_target.argtypes = [ctx, C.POINTER(device_target)]
+        lib.b200r_peer_alloc.argtypes = [ctx, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(peer_handle)]
+        lib.b200r_peer_open.argtypes = [ctx, C.POINTER(peer_handle), C.POINTER(C.c_void_p)]
+        lib.b200r_peer_release.argtypes = [ctx, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -299,3 +309,24 @@ class Renderer:
 
     def clear_device(self, target: device_target, color: int, depth: float):
         self._check(self.lib.b200r_clear_device(self.ctx, C.byref(target), color, depth))
+
+    # ---- fused gather: bands / frames mirrored into one (peer-mapped) image of the whole screen ----
+    def set_gather_target(self, target):
+        """b200r_set_gather_target; ``None`` switches the mirror off."""
+        self._check(self.lib.b200r_set_gather_target(self.ctx, C.byref(target) if target is not None else None))
+
+    def peer_alloc(self, nbytes: int):
+        """Device memory other processes can map: returns (device pointer, 64-byte handle)."""
+        ptr, h = C.c_void_p(), peer_handle()
+        self._check(self.lib.b200r_peer_alloc(self.ctx, nbytes, C.byref(ptr), C.byref(h)))
+        return ptr.value, bytes(h.Bytes)
+
+    def peer_open(self, handle: bytes) -> int:
+        h = peer_handle()
+        C.memmove(h.Bytes, handle, 64)
+        ptr = C.c_void_p()
+        self._check(self.lib.b200r_peer_open(self.ctx, C.byref(h), C.byref(ptr)))
+        return ptr.value
+
+    def peer_release(self, ptr: int):
+        self._check(self.lib.b200r_peer_release(self.ctx, C.c_void_p(ptr)))

@@ -111,6 +111,11 @@ struct b200r_context
     unsigned total_tris = 0;
     unsigned ntiles = 0;
 
+    // fused gather (b200r_set_gather_target): an image of the whole screen every band is mirrored into
+    bool has_gather = false;
+    b200r_device_target gather = {};
+    std::vector<void *> peer_owned, peer_opened;    // b200r_peer_alloc / b200r_peer_open
+
     b200r_frame_stats stats = {};
     bool profiling = false;
     cudaEvent_t stage_ev[B200R_STAGES + 1] = {};
@@ -381,6 +386,16 @@ static int issue_frame(b200r_context *c)
     rp.bulk_ok = ((((uintptr_t)c->target.Color) & 15) == 0 && (((uintptr_t)c->target.Depth) & 15) == 0 &&
                   (c->target.ColorPitch & 15) == 0 && ((c->target.DepthStride*4) & 15) == 0 &&
                   (c->target.Width & 3) == 0) ? 1 : 0;
+    rp.gather_color = nullptr; rp.gather_depth = nullptr;
+    rp.gather_pitch_words = 0; rp.gather_depth_stride = 0; rp.gather_bulk_ok = 0;
+    if(c->has_gather && !c->host_path)
+    {
+        const b200r_device_target &g = c->gather;
+        rp.gather_color = g.Color; rp.gather_depth = g.Depth;
+        rp.gather_pitch_words = g.ColorPitch/4; rp.gather_depth_stride = g.DepthStride;
+        rp.gather_bulk_ok = ((((uintptr_t)g.Color) & 15) == 0 && (g.ColorPitch & 15) == 0 &&
+                             (!g.Depth || ((((uintptr_t)g.Depth) & 15) == 0 && ((g.DepthStride*4) & 15) == 0))) ? 1 : 0;
+    }
     rp.textures = nullptr;
     rp.texture_count = (unsigned)c->tex_host.size();
     rp.mode = (c->span_words == kSpanWordsPhong) ? kRasterGeneral : (c->tex_host.empty() ? kRasterPlain : kRasterTextured);
@@ -515,6 +530,8 @@ void b200r_destroy(b200r_context *c)
     c->sel_list.release(); c->sel_counts.release();
     c->obj_chain_base.release(); c->obj_chains.release(); c->obj_pairs.release(); c->obj_flags.release();
     for(b200r_context::HostTexture &ht : c->host_textures) ht.pixels.release();
+    for(void *q : c->peer_opened) cudaIpcCloseMemHandle(q);
+    for(void *q : c->peer_owned) cudaFree(q);
     for(cudaEvent_t e : c->stage_ev) if(e) cudaEventDestroy(e);
     if(c->h_words) cudaFreeHost(c->h_words);
     if(c->total_ready) cudaEventDestroy(c->total_ready);
@@ -592,6 +609,9 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     ViewParams v;
     rc = fill_view(c, cmd, target, v, all_phong);
     if(rc != B200R_OK) return rc;
+
+    if(c->has_gather && (c->gather.Width != target->Width || c->gather.Height != target->Height))
+        return fail(c, B200R_E_INVALID, "gather target and render target describe different screens");
 
     uint64_t total = 0;
     std::vector<MeshParams> ms;
@@ -672,6 +692,75 @@ int b200r_clear_device(b200r_context *c, const b200r_device_target *t, u32 color
     c->stats.KernelLaunches += 1;
     CU(cudaGetLastError());
     return B200R_OK;
+}
+
+int b200r_set_gather_target(b200r_context *c, const b200r_device_target *g)
+{
+    if(!c) return B200R_E_INVALID;
+    ENTER(c);
+    int rc = b200r_sync(c);                      // the last frame may still be writing the old one
+    if(rc != B200R_OK) return rc;
+    if(!g) { c->has_gather = false; return B200R_OK; }
+    if(!g->Color || g->Width <= 0 || g->Height <= 0 || g->ColorPitch < g->Width*4 || (g->ColorPitch & 3) ||
+       (g->Depth && g->DepthStride < g->Width))
+        return fail(c, B200R_E_INVALID, "bad gather target geometry");
+    c->gather = *g;
+    c->has_gather = true;
+    return B200R_OK;
+}
+
+static_assert(sizeof(b200r_peer_handle) == sizeof(cudaIpcMemHandle_t), "b200r_peer_handle carries a cudaIpcMemHandle_t");
+
+int b200r_peer_alloc(b200r_context *c, uint64_t bytes, void **ptr, b200r_peer_handle *handle)
+{
+    if(!c || !ptr || !handle || bytes == 0) return fail(c, B200R_E_INVALID, "b200r_peer_alloc: null argument");
+    ENTER(c);
+    void *q = nullptr;
+    CU(cudaMalloc(&q, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, q);
+    if(e != cudaSuccess) { cudaFree(q); return fail(c, B200R_E_CUDA, "cudaIpcGetMemHandle", e); }
+    memcpy(handle->Bytes, &h, sizeof(h));
+    c->peer_owned.push_back(q);
+    *ptr = q;
+    return B200R_OK;
+}
+
+int b200r_peer_open(b200r_context *c, const b200r_peer_handle *handle, void **ptr)
+{
+    if(!c || !ptr || !handle) return fail(c, B200R_E_INVALID, "b200r_peer_open: null argument");
+    ENTER(c);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle->Bytes, sizeof(h));
+    void *q = nullptr;
+    CU(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_opened.push_back(q);
+    *ptr = q;
+    return B200R_OK;
+}
+
+int b200r_peer_release(b200r_context *c, void *ptr)
+{
+    if(!c || !ptr) return B200R_E_INVALID;
+    ENTER(c);
+    int rc = b200r_sync(c);
+    if(rc != B200R_OK) return rc;
+    if(c->has_gather && (c->gather.Color == ptr || (void *)c->gather.Depth == ptr)) c->has_gather = false;
+    for(size_t i = 0; i < c->peer_opened.size(); ++i)
+        if(c->peer_opened[i] == ptr)
+        {
+            c->peer_opened.erase(c->peer_opened.begin() + (long)i);
+            CU(cudaIpcCloseMemHandle(ptr));
+            return B200R_OK;
+        }
+    for(size_t i = 0; i < c->peer_owned.size(); ++i)
+        if(c->peer_owned[i] == ptr)
+        {
+            c->peer_owned.erase(c->peer_owned.begin() + (long)i);
+            CU(cudaFree(ptr));
+            return B200R_OK;
+        }
+    return fail(c, B200R_E_INVALID, "b200r_peer_release: not a pointer of this context");
 }
 
 int b200r_set_profiling(b200r_context *c, int enable)

@@ -138,6 +138,12 @@ struct RasterParams
     int color_pitch_words;      // u32 per row
     int depth_stride;           // floats per row
     int bulk_ok;                // rows may be moved with cp.async.bulk (16-byte aligned)
+    // Fused gather (b200r_set_gather_target): every tile of the band is ALSO stored into this image of the
+    // whole screen, typically peer memory of the GPU that assembles the frame (NVLink); null: off.
+    uint32_t *gather_color;     // row 0 of the whole screen
+    float *gather_depth;        // optional
+    int gather_pitch_words, gather_depth_stride;
+    int gather_bulk_ok;
     const TexDesc *textures;    // device: the frame's texture table (null without textured meshes)
     unsigned texture_count;
     int mode;                   // kRasterPlain / kRasterGeneral / kRasterTextured (raster_kernel.cu)

@@ -2,8 +2,10 @@
 
 The path shards without any data-path collective: rows of the reference's row loop are
 independent (projekt.cpp:198), so a GPU can own a band of screen rows (config C4), and frames are
-independent (config C5).  The only exchange is the gather of finished band / frame images
-(torch.distributed: NCCL over NVLink on the GPU box, gloo in the CPU tests).
+independent (config C5).  The only exchange is the gather of finished band / frame images: either a collective after the frame
+(torch.distributed: NCCL over NVLink on the GPU box, gloo in the CPU tests), or fused into the raster
+kernel's tile write-back (FusedGather below: the kernel stores every finished tile a second time,
+straight into the assembling GPU's memory over NVLink, and only a barrier follows the frame).
 """
 from __future__ import annotations
 
@@ -61,3 +63,74 @@ def gather_frames(local: torch.Tensor, world: int, rank: int, dst: int = 0):
     parts = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
     dist.gather(local.contiguous(), parts, dst=dst)
     return torch.cat(parts, dim=0) if rank == dst else None
+
+
+class _DevicePointer:
+    """Lets torch.as_tensor view raw device memory (a b200r_peer_alloc allocation) without copying."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class FusedGather:
+    """The gather of the finished images fused into the raster kernel (b200r_set_gather_target).
+
+    ``dst`` allocates ONE image of ``slots`` whole screens ([slots, height, wpad] u32 colour, optionally
+    f32 depth) with b200r_peer_alloc and sends its CUDA IPC handles to the other ranks, which map it
+    (b200r_peer_open).  Every rank then points its renderer's gather target at the screen it
+    contributes to -- the same slot for row bands of one frame, slot = rank for frame-parallel work --
+    and from then on each b200r_render_device call also stores its tiles there.  ``finish()`` is the
+    stream-ordered barrier after which ``dst`` may read the assembled image(s)."""
+
+    def __init__(self, renderer, api, height: int, width: int, wpad: int, slots: int, world: int, rank: int,
+                 device, dst: int = 0, with_depth: bool = False):
+        self.r, self.api, self.rank, self.dst, self.world = renderer, api, rank, dst, world
+        self.h, self.w, self.wpad, self.slots = height, width, wpad, slots
+        nbytes = slots * height * wpad * 4
+        handles = [None, None]
+        self._owned, self._opened = [], []
+        if rank == dst:
+            self.color_ptr, hc = renderer.peer_alloc(nbytes)
+            self._owned.append(self.color_ptr)
+            handles[0] = hc
+            if with_depth:
+                self.depth_ptr, hd = renderer.peer_alloc(nbytes)
+                self._owned.append(self.depth_ptr)
+                handles[1] = hd
+        if world > 1:
+            dist.broadcast_object_list(handles, src=dst)
+        if rank != dst:
+            self.color_ptr = renderer.peer_open(handles[0])
+            self._opened.append(self.color_ptr)
+            if handles[1] is not None:
+                self.depth_ptr = renderer.peer_open(handles[1])
+                self._opened.append(self.depth_ptr)
+        if not with_depth:
+            self.depth_ptr = 0
+        self.color = self.depth = None
+        if rank == dst:
+            self.color = torch.as_tensor(_DevicePointer(self.color_ptr, (slots, height, wpad), "<i4"), device=device)
+            if with_depth:
+                self.depth = torch.as_tensor(_DevicePointer(self.depth_ptr, (slots, height, wpad), "<f4"), device=device)
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def select(self, slot: int):
+        """Mirror this rank's frames into screen ``slot`` of the assembled image."""
+        off = slot * self.h * self.wpad * 4
+        t = self.api.device_target(self.color_ptr + off, (self.depth_ptr + off) if self.depth_ptr else None,
+                                   self.w, self.h, self.wpad * 4, self.wpad, 0, self.h)
+        self.r.set_gather_target(t)
+
+    def finish(self):
+        """Stream-ordered barrier: enqueued behind this rank's frame on the current stream; when it has
+        completed on ``dst``, every rank's kernels -- and with them their stores into the image -- have."""
+        if self.world > 1:
+            dist.all_reduce(self._token)
+
+    def close(self):
+        self.r.set_gather_target(None)
+        self.color = self.depth = None
+        for p in self._opened + self._owned:
+            self.r.peer_release(p)
+        self._opened, self._owned = [], []

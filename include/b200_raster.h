@@ -246,6 +246,31 @@ int b200r_render_device(b200r_context *Context, const b200r_device_mesh *Meshes,
 int b200r_clear_device(b200r_context *Context, const b200r_device_target *Target, u32 Color,
                        r32 Depth);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused gather for multi-GPU frames (the path's only exchange step is the gather
+ * of the finished band / frame images).  With a gather target set, the raster kernel stores every
+ * tile of the band it renders a second time: into GatherTarget, an image of the WHOLE screen
+ * (Width x Height as in the render target; BandFirstRow / BandRows ignored; Depth may be 0) --
+ * typically memory of the GPU that assembles the frame, mapped into this process with
+ * b200r_peer_open, so that the band travels over NVLink tile by tile while the kernel is still
+ * rasterising and no separate gather pass follows.  Tiles nothing was drawn into are copied
+ * through, so after the frame the band's rows of GatherTarget equal the band exactly.  The writes
+ * are complete when the frame's kernels are (stream order on the rendering GPU); the assembling
+ * rank must order its reads after that (e.g. a stream-ordered barrier across the ranks).
+ * Applies to b200r_render_device only.  0 switches it off.
+ * ------------------------------------------------------------------------------------------ */
+int b200r_set_gather_target(b200r_context *Context, const b200r_device_target *GatherTarget);
+
+/* Device memory other processes on the same machine can map (CUDA IPC).  b200r_peer_alloc
+ * allocates Bytes on the context's device and returns the handle to send to the peers (any byte
+ * transport); b200r_peer_open maps a peer's allocation into this process (peer access over
+ * NVLink / PCIe is enabled on first use); b200r_peer_release unmaps / frees either kind.
+ * Whatever is left is released by b200r_destroy. */
+typedef struct b200r_peer_handle { unsigned char Bytes[64]; } b200r_peer_handle;
+int b200r_peer_alloc(b200r_context *Context, uint64_t Bytes, void **DevicePointer, b200r_peer_handle *Handle);
+int b200r_peer_open(b200r_context *Context, const b200r_peer_handle *Handle, void **DevicePointer);
+int b200r_peer_release(b200r_context *Context, void *DevicePointer);
+
 typedef struct b200r_frame_stats
 {
     uint64_t Triangles;        /* submitted in the last render call                             */

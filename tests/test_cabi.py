@@ -44,6 +44,7 @@ MIRRORS = {
     "projective_transform": api.projective_transform,
     "b200r_device_mesh": api.device_mesh, "b200r_device_texture": api.device_texture,
     "b200r_device_target": api.device_target, "b200r_frame_stats": api.frame_stats,
+    "b200r_peer_handle": api.peer_handle,
 }
 
 
@@ -99,6 +100,10 @@ def test_null_context_is_rejected_not_dereferenced():
     assert lib.b200r_fill_edge_table(None, None, None, 0) == api.E_INVALID
     assert lib.b200r_render_device(None, None, 0, None, None, 0) == api.E_INVALID
     assert lib.b200r_get_stats(None, None) == api.E_INVALID
+    assert lib.b200r_set_gather_target(None, None) == api.E_INVALID
+    assert lib.b200r_peer_alloc(None, 16, None, None) == api.E_INVALID
+    assert lib.b200r_peer_open(None, None, None) == api.E_INVALID
+    assert lib.b200r_peer_release(None, None) == api.E_INVALID
     assert lib.b200r_last_error(None) == b"null context"
     lib.b200r_destroy(None)
 
