@@ -76,6 +76,13 @@ struct MeshParams
     // able to reach this GPU's band.  Owners stay prim_base + original index.
     const unsigned *tri_list;   // device, or null: all ntri triangles in order
     const unsigned *tri_count;  // device: number of listed triangles
+    // Row-parallel walks (setup_kernel<..., SPLIT>): a CTA stages tris_per_cta (8..64) triangles and cuts
+    // tall ones into walkers of part_rows screen rows (a multiple of the tile height); 0: off.
+    int tris_per_cta, part_rows;
+    // Frames of tall triangles (the host decides from target pixels per triangle): walkers are sorted by
+    // height >> sort_shift, and the lock-step row loop runs at most row_chunk rows between two looks at
+    // the lanes' list events (INT_MAX: up to the next event, right for triangles of a few rows).
+    int sort_shift, row_chunk;
     const float *uv;            // v2 x 3 per triangle, or null
     int tex;                    // index into the frame's texture table, -1: untextured
     int white;                  // b200r_fill_edge_table of a textured Gouraud object: light white vertices (:4034-4060)

@@ -178,7 +178,17 @@ select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count)
 // kernel is instruction-cache bound; the branches cost 6 % of its time when they were run-time).
 // LISTED: the kernel processes the triangles of MeshParams::tri_list (row-band pre-selection) and
 // gathers their attributes; a template parameter for the same reason.
-template<bool PHONG, bool TEX, bool LISTED>
+// SPLIT: row-parallel walks for frames of FEW, TALL triangles (the host picks it from the triangle count).
+// A triangle's rows are sequential state (an edge's value at row r is r rounded adds from its start), so
+// a thread that walks a 150-row triangle alone is a 150-row latency chain, and 50 000 such threads leave
+// most of the machine idle (C3: set-up 0.30 ms at 16 % of the resident warps; a 500-triangle 4K frame
+// still took 0.2 ms).  With SPLIT a CTA stages only MeshParams::tris_per_cta (<= 64) triangles and a
+// triangle taller than kSplitMinRows is cut into WALKERS of MeshParams::part_rows screen rows (slabs
+// aligned to tile rows, so no segment straddles two walkers).  Every walker replays the edge stepping
+// from the triangle's first row -- 14 adds and the crossing test per row, no span set-up -- and emits
+// the spans of its own slab only, at offsets it derives from the same closed-form row counts that sized
+// the triangle's allocation.  A template parameter: the small-triangle kernels must not pay for it.
+template<bool PHONG, bool TEX, bool LISTED, bool SPLIT>
 __global__ void __launch_bounds__(kSetupThreads, 5)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
@@ -196,11 +206,14 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     __shared__ unsigned s_warp_sum[kSetupThreads/32], s_warp_sum2[kSetupThreads/32];
 
     __shared__ unsigned s_id[kSetupThreads];             // list mode: original index of each staged triangle
+    __shared__ unsigned s_wmap[SPLIT ? kSetupThreads : 1];   // SPLIT: the batch's walkers, triangle slot | part << 8
+    __shared__ unsigned s_wtotal;
     constexpr bool listed = LISTED;
     const unsigned total = listed ? *m.tri_count : m.ntri;
-    const unsigned base = blockIdx.x*kSetupThreads;
+    const unsigned tpc = SPLIT ? (unsigned)m.tris_per_cta : (unsigned)kSetupThreads;   // triangles per CTA
+    const unsigned base = blockIdx.x*tpc;
     if(base >= total) return;                              // list mode launches for ntri; the tail has nothing to do
-    const unsigned n = min((unsigned)kSetupThreads, total - base);
+    const unsigned n = min(tpc, total - base);
     const int t = threadIdx.x;
     if(t == 0) { s_binned = 0; s_pairs = 0; }
     int my_segs = 0, my_spans = 0, walk_end = 0, first_row = 0, max_y = 0, nedges = 0, nonfinite = 0;
@@ -301,6 +314,40 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             cam[k].y = fadd(s_pos[tri_*9 + 3*k + 1], m.py);
             cam[k].z = fadd(s_pos[tri_*9 + 3*k + 2], m.pz);
             prj[k] = project_vertex(cam[k], v);                // :3907
+        }
+    };
+    // Spans and segments of the rows [first, limit) of a triangle, without walking: between consecutive
+    // list-change rows the set of active edges {e : YMin <= row < YMax} is constant; a stretch with >= 2 of
+    // them yields one span per row.  A segment is the run of a triangle's spans inside one tile-row band.
+    auto count_rows = [&](const uint32_t *rec_, int nedges_, int first, int limit, int &segs, int &spans)
+    {
+        int y = first, last_band = -1;
+        segs = 0; spans = 0;
+        while(y < limit)
+        {
+            int nxt = limit, act = 0;
+#pragma unroll
+            for(int e = 0; e < 3; ++e)
+            {
+                if(e >= nedges_) break;
+                const int ymn = (int)rec_[R_EDGE0 + e*kEdgeWords + E_YMIN];
+                const int ymx = (int)rec_[R_EDGE0 + e*kEdgeWords + E_YMAX];
+                if(ymn <= y && y < ymx) ++act;
+                if(ymn > y && ymn < nxt) nxt = ymn;
+                if(ymx > ymn && ymx > y && ymx < nxt) nxt = ymx;
+            }
+            if(act >= 2)
+            {
+                const int a = max(y, v.band_y0);
+                if(a < nxt)
+                {
+                    const int b0 = (a - v.band_y0) >> v.tile_h_shift, b1 = (nxt - 1 - v.band_y0) >> v.tile_h_shift;
+                    segs += b1 - b0 + ((b0 == last_band) ? 0 : 1);
+                    last_band = b1;
+                    spans += nxt - a;
+                }
+            }
+            y = nxt;
         }
     };
     bool alive = false;
@@ -509,36 +556,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
         // yields one span per row.  A segment is the run of a triangle's spans inside one tile-row
         // band (its span records are consecutive), so the segment count is the number of distinct
         // bands those rows fall into.  The walk below opens segments by exactly the same rule.
-        if(have_walk)
-        {
-            int y = first_row, last_band = -1;
-            while(y < walk_end)
-            {
-                int nxt = walk_end, act = 0;
-#pragma unroll
-                for(int e = 0; e < 3; ++e)
-                {
-                    if(e >= nedges) break;
-                    const int ymn = (int)rec[R_EDGE0 + e*kEdgeWords + E_YMIN];
-                    const int ymx = (int)rec[R_EDGE0 + e*kEdgeWords + E_YMAX];
-                    if(ymn <= y && y < ymx) ++act;
-                    if(ymn > y && ymn < nxt) nxt = ymn;
-                    if(ymx > ymn && ymx > y && ymx < nxt) nxt = ymx;
-                }
-                if(act >= 2)
-                {
-                    const int a = max(y, v.band_y0);
-                    if(a < nxt)
-                    {
-                        const int b0 = (a - v.band_y0) >> v.tile_h_shift, b1 = (nxt - 1 - v.band_y0) >> v.tile_h_shift;
-                        my_segs += b1 - b0 + ((b0 == last_band) ? 0 : 1);
-                        last_band = b1;
-                        my_spans += nxt - a;
-                    }
-                }
-                y = nxt;
-            }
-        }
+        if(have_walk) count_rows(rec, nedges, first_row, walk_end, my_segs, my_spans);
     }
 
     // ---- CTA-wide exclusive scans of segment and span counts: warp shuffles, then ONE pair of
@@ -580,18 +598,90 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     // ---- hand the walks out again: compact the triangles that have rows to walk and sort them by
     //      row count (counting sort in shared memory), so that warps are dense and hold triangles of
     //      similar height.  Lanes of a warp walk in lock step, so a warp costs its tallest triangle;
-    //      without this, culled / off-band / short triangles leave most lanes idle. ----
+    //      without this, culled / off-band / short triangles leave most lanes idle.
+    //      SPLIT: the units are walkers (triangle, slab of part_rows rows), handed out in batches of one
+    //      per thread. ----
+    const bool mine_walks = tri >= 0 && have_walk && s_fits != 0u;
+    s_w_first[t] = first_row; s_w_end[t] = walk_end;
+    s_w_info[t] = (unsigned)nedges | ((unsigned)nonfinite << 8) | (mine_walks ? 0x8000u : 0u) | ((unsigned)my_segs << 16);
+    s_w_spans[t] = (unsigned)my_spans;
+    s_w_seg_at[t] = seg_at; s_w_span_at[t] = span_at; s_w_tri[t] = tri;
+    // SPLIT: slab s covers the band-relative rows [s*part_rows, (s+1)*part_rows); rows above the band are
+    // replayed by every walker and emitted by none
+    constexpr int kSplitMinRows = 40;                     // shorter triangles stay one walker
+    if(SPLIT) s_alive[t] = 0u;                             // reused: "this triangle has been counted as binned"
+    const int part_rows = SPLIT ? m.part_rows : 1;
+    int my_parts = mine_walks ? 1 : 0, my_slab0 = 0;
+    unsigned my_woff = 0;
+    if(SPLIT)
     {
-        const bool mine_walks = tri >= 0 && have_walk && s_fits != 0u;
-        const int my_rows = mine_walks ? (walk_end - first_row) : 0;
-        const int key = mine_walks ? (kSortBins - 1 - min(my_rows, kSortBins - 1)) : kSortBins;   // tall first, idle last
+        if(mine_walks && walk_end - first_row > kSplitMinRows)
+        {
+            my_slab0 = (max(first_row, v.band_y0) - v.band_y0)/part_rows;
+            my_parts = (walk_end - 1 - v.band_y0)/part_rows - my_slab0 + 1;
+        }
+        // exclusive scan of the walker counts over the CTA
+        const unsigned lane = t & 31, warp = t >> 5;
+        unsigned incl = (unsigned)my_parts;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned up = __shfl_up_sync(0xffffffffu, incl, d);
+            if(lane >= (unsigned)d) incl += up;
+        }
+        __syncthreads();                                    // s_warp_sum was read by the allocation scan
+        if(lane == 31) s_warp_sum[warp] = incl;
+        __syncthreads();
+        unsigned before = 0, all = 0;
+        for(unsigned w = 0; w < kSetupThreads/32; ++w) { if(w < warp) before += s_warp_sum[w]; all += s_warp_sum[w]; }
+        my_woff = before + incl - (unsigned)my_parts;
+        if(t == 0) s_wtotal = all;
+    }
+    for(unsigned wb = 0; ; wb += kSetupThreads)
+    {
+    unsigned wmine = (unsigned)t;                          // this thread's unit before sorting: triangle slot | part << 8
+    bool unit = mine_walks;
+    if(SPLIT)
+    {
+        __syncthreads();                                    // s_wtotal written / the previous batch has been read
+        if(wb >= s_wtotal) break;
+        s_wmap[t] = 0xffffffffu;
+        __syncthreads();
+        for(int q = 0; q < my_parts; ++q)
+        {
+            const unsigned w = my_woff + (unsigned)q;
+            if(w >= wb && w < wb + kSetupThreads) s_wmap[w - wb] = (unsigned)t | ((unsigned)q << 8);
+        }
+        __syncthreads();
+        wmine = s_wmap[t];
+        unit = wmine != 0xffffffffu;
+    }
+    else if(wb > 0) break;                                // one unit per thread: a single batch
+    // a unit's rows: where it starts to walk, where it starts and stops to emit
+    auto unit_rows = [&](unsigned wm, int &u_first, int &u_emit, int &u_end)
+    {
+        const int slot_ = (int)(wm & 0xffu), part_ = (int)(wm >> 8);
+        u_first = s_w_first[slot_]; u_emit = v.band_y0; u_end = s_w_end[slot_];
+        if(SPLIT && u_end - u_first > kSplitMinRows)
+        {
+            const int slab = (max(u_first, v.band_y0) - v.band_y0)/part_rows + part_;
+            u_emit = max(v.band_y0 + slab*part_rows, v.band_y0);
+            u_end = min(u_end, v.band_y0 + (slab + 1)*part_rows);
+        }
+    };
+    {
+        int u_first = 0, u_emit = 0, u_end = 0;
+        if(unit) unit_rows(wmine, u_first, u_emit, u_end);
+        // SPLIT: lanes walk in lock step, so a row costs the warp a span set-up as soon as ONE lane emits it;
+        // walkers are therefore grouped by how many rows they replay first (their emitting rows are at most
+        // part_rows each): a warp replays together, then emits together
+        // (not SPLIT: by height; MeshParams::sort_shift scales heights into the kSortBins bins for frames of
+        // tall triangles, which would otherwise all share the last bin)
+        const int my_rows = unit ? (SPLIT ? ((u_emit - u_first) >> 2) : ((u_end - u_first) >> m.sort_shift)) : 0;
+        const int key = unit ? (kSortBins - 1 - max(min(my_rows, kSortBins - 1), 0)) : kSortBins;   // tall first, idle last
         if(t <= kSortBins) s_hist[t] = 0;
         __syncthreads();
         const unsigned rank = atomicAdd(&s_hist[key], 1u);
-        s_w_first[t] = first_row; s_w_end[t] = walk_end;
-        s_w_info[t] = (unsigned)nedges | ((unsigned)nonfinite << 8) | (mine_walks ? 0x8000u : 0u) | ((unsigned)my_segs << 16);
-        s_w_spans[t] = (unsigned)my_spans;
-        s_w_seg_at[t] = seg_at; s_w_span_at[t] = span_at; s_w_tri[t] = tri;
         __syncthreads();
         if(t < 32)
         {
@@ -610,7 +700,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             if(3*t + 2 <= kSortBins) { s_hist[3*t + 2] = run; }
         }
         __syncthreads();
-        s_order[s_hist[key] + rank] = (unsigned)t;          // order inside a bin is irrelevant
+        s_order[s_hist[key] + rank] = unit ? wmine : 0xffffffffu;          // order inside a bin is irrelevant
         __syncthreads();
     }
 
@@ -618,16 +708,29 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     //      predicated bodies): list events are handled for all lanes that have one at the same
     //      time, then the rows up to each lane's next event run in lock step. ----
     {
-        const int slot = (int)s_order[t];                   // whose phase-2 results this thread walks
+        const unsigned wm = s_order[t];                     // the unit this thread walks
+        const bool have_unit = wm != 0xffffffffu;
+        const int slot = have_unit ? (int)(wm & 0xffu) : 0; // whose phase-2 results
         const int tri = max(s_w_tri[slot], 0);              // that triangle's index inside the CTA
         const unsigned info = s_w_info[slot];
         const int nedges = (int)(info & 0xffu);
         const int nonfinite = (int)((info >> 8) & 0x7fu);
-        const int my_segs = (int)(info >> 16), my_spans = (int)s_w_spans[slot];
-        const int first_row = s_w_first[slot], walk_end = s_w_end[slot];
-        const unsigned seg_at = s_w_seg_at[slot], span_at = s_w_span_at[slot];
-        const bool walking = (info & 0x8000u) != 0;
+        int my_segs = (int)(info >> 16), my_spans = (int)s_w_spans[slot];
+        int first_row = 0, emit_from = 0, walk_end = 0;
+        if(have_unit) unit_rows(wm, first_row, emit_from, walk_end);
+        unsigned seg_at = s_w_seg_at[slot], span_at = s_w_span_at[slot];
+        const bool walking = have_unit && (info & 0x8000u) != 0;
         const uint32_t *rec = s_edge + tri*kEdgeRec - R_EDGE0;
+        if(SPLIT && walking && s_w_end[slot] - s_w_first[slot] > kSplitMinRows)
+        {
+            // this walker's share of the triangle's allocation: what the rows before its slab produce, and
+            // what the rows up to its end produce
+            int sb, pb, se, pe;
+            count_rows(rec, nedges, first_row, emit_from, sb, pb);
+            count_rows(rec, nedges, first_row, walk_end, se, pe);
+            seg_at += (unsigned)sb; span_at += (unsigned)pb;
+            my_segs = se - sb; my_spans = pe - pb;
+        }
         const float *nrm = PHONG ? (s_nrm + tri*9) : nullptr;
         const int sw = out.span_words;
         const uint32_t span_flags = (nonfinite ? kSpanNonFinite : 0u) | (PHONG ? kSpanPhong : 0u) |
@@ -676,18 +779,31 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 
         while(__any_sync(0xffffffffu, walking && y < walk_end))
         {
+            // SPLIT: a row costs the whole warp a span set-up as soon as ONE lane emits it, so the lanes of a
+            // warp are kept in phase: while any lane still replays rows in front of its slab (stepping only),
+            // the lanes that have reached theirs wait; then all emit together
+            bool go = walking && y < walk_end;
+            int stop = walk_end;
+            if(SPLIT)
+            {
+                const bool replaying = go && y < emit_from;
+                if(__any_sync(0xffffffffu, replaying)) { go = replaying; stop = min(emit_from, walk_end); }
+            }
             // (a) list events (projekt.cpp:202-296), together
-            if(walking && y < walk_end && y == next_ev) active_list_event(y, rec, nedges, L, R, nact, next_ev, nrm);
+            if(go && y == next_ev) active_list_event(y, rec, nedges, L, R, nact, next_ev, nrm);
             // (b) rows up to the next event
-            const int nrow = (walking && y < walk_end) ? (min(next_ev, walk_end) - y) : 0;
+            // (MeshParams::row_chunk caps the stretch for frames of tall triangles: with stretches of ~50 rows a
+            // lane whose stretch ends early would idle until the warp's longest one has finished; with the
+            // cap it goes through its list event a few rows later and carries on)
+            const int nrow = go ? min(min(next_ev, stop) - y, m.row_chunk) : 0;
             const int nrow_max = __reduce_max_sync(0xffffffffu, nrow);
             for(int k = 0; k < nrow_max; ++k)
             {
                 if(k >= nrow) continue;
                 if(nact == 2)
                 {
-                    const bool in_band = y >= v.band_y0;
-                    if(in_band || (v.alias_rows && y == v.band_y0 - 1))
+                    const bool in_band = y >= emit_from;           // rows before: state only (above the band / another walker's)
+                    if(in_band || (v.alias_rows && y == v.band_y0 - 1 && emit_from == v.band_y0))
                     {
                         if(in_band)
                         {
@@ -805,9 +921,15 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                 SegInfo si; si.tile_row = 0; si.tx = 1u; si.span_base = 0; si.nrows = 0;
                 out.segs[seg] = si;
             }
-            if(pairs) { atomicAdd(&s_binned, 1u); atomicAdd(&s_pairs, pairs); }
+            if(pairs)
+            {
+                // SPLIT: a triangle counts as binned once, whichever of its walkers produced pairs
+                if(!SPLIT || atomicExch(&s_alive[slot], 1u) == 0u) atomicAdd(&s_binned, 1u);
+                atomicAdd(&s_pairs, pairs);
+            }
         }
     }
+    }   // batches of walkers
     __syncthreads();
 
     if(t == 0 && s_binned)
@@ -838,9 +960,11 @@ void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, uns
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s)
 {
     if(m.ntri == 0) return;
-    unsigned blocks = (m.ntri + kSetupThreads - 1)/kSetupThreads;
-    const bool tex = m.uv != nullptr, listed = m.tri_list != nullptr;
-#define B200R_LAUNCH_SETUP(P, T, L) setup_kernel<P, T, L><<<blocks, kSetupThreads, 0, s>>>(v, m, out)
+    const bool tex = m.uv != nullptr, listed = m.tri_list != nullptr, split = m.tris_per_cta > 0;
+    const unsigned tpc = split ? (unsigned)m.tris_per_cta : (unsigned)kSetupThreads;
+    const unsigned blocks = (m.ntri + tpc - 1)/tpc;
+#define B200R_LAUNCH_SETUP(P, T, L) do { if(split) setup_kernel<P, T, L, true><<<blocks, kSetupThreads, 0, s>>>(v, m, out); \
+                                         else setup_kernel<P, T, L, false><<<blocks, kSetupThreads, 0, s>>>(v, m, out); } while(0)
     if(listed)
     {
         if(m.phong) { if(tex) B200R_LAUNCH_SETUP(true, true, true); else B200R_LAUNCH_SETUP(true, false, true); }

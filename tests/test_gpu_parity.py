@@ -935,3 +935,43 @@ def test_idempotence_and_order_independence_properties(renderer):
     c2, z2, _ = ol.new_targets(s)
     renderer.render_scene_host(s, c2, z2, splits=[nv // 6 * 3, nv - nv // 6 * 3])
     assert np.array_equal(c1, c2) and np.array_equal(z1.view(np.uint32), z2.view(np.uint32))
+
+
+@pytest.mark.parametrize("tpc,rows,chunk", [(8, 8, 1), (8, 16, 4), (16, 32, 2), (32, 64, 1000000), (64, 128, 3), (0, 0, 1)])
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_row_parallel_setup_with_forced_parameters(monkeypatch, tpc, rows, chunk, seed):
+    """setup_kernel<..., SPLIT> (tall triangles cut into walkers of `rows` screen rows, `tpc` triangles per
+    CTA) and the row-chunk cap of the lock-step walk, forced through their environment switches on random
+    scenes of tall triangles -- every shading mode, whole frames and row bands at arbitrary rows (walkers
+    replay rows above their band AND above their slab) -- against the oracle.  (0, 0, 1): no split."""
+    monkeypatch.setenv("B200R_SPLIT", "2" if tpc else "0")
+    if tpc:
+        monkeypatch.setenv("B200R_SPLIT_TPC", str(tpc)); monkeypatch.setenv("B200R_SPLIT_ROWS", str(rows))
+    monkeypatch.setenv("B200R_TALL_CHUNK", str(chunk))
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(300, 900)), int(rng.integers(250, 700))
+    s = sc.triangle_soup(f"tall{seed}", seed, int(rng.integers(40, 900)), w, h, 10.0, float(rng.uniform(60.0, 220.0)),
+                         jitter=float(rng.uniform(0.3, 2.0)))
+    mode = ("gouraud", "phong", "textured")[seed % 3]
+    phong = mode == "phong"
+    if mode == "textured":
+        s = sc.textured(s, 64, 48, seed=seed, lo=0.05, hi=0.9)
+    wpad = (s.width + 63) // 64 * 64
+    wc = np.full((s.height, wpad), s.clear_color, np.uint32)[:, :s.width]
+    wz = np.full((s.height, wpad), s.clear_depth, np.float32)[:, :s.width]
+    want = ol.oracle_render(s, phong=phong, targets=(wc, wz, None))
+    r = Renderer(0)
+    try:
+        for cuts in ([0, s.height], [0] + sorted(set(int(x) for x in rng.integers(1, s.height, size=3))) + [s.height]):
+            colors, depths = [], []
+            for a, b in zip(cuts, cuts[1:]):
+                c, z = _device_render(r, s, (128, 8) if seed % 2 else (64, 32), a, b - a, phong=phong)
+                colors.append(c); depths.append(z)
+            color, z = np.concatenate(colors), np.concatenate(depths)
+            assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)), (seed, mode, cuts)
+            ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+            assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (seed, mode, int(ch.max()))
+        st = r.stats()
+        assert st["Spans"] > 0 and st["Binned"] <= st["Triangles"]
+    finally:
+        r.close()
