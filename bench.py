@@ -258,6 +258,32 @@ def equivalent_zbuffer(ol, scene, tri_bytes, frame_ms, peak_gbs):
             "what": "z-buffer traffic of the reference's own algorithm for this frame / our frame time (not HBM traffic)"}
 
 
+def issue_roofline(config, fragments, raster_ms, sm_mhz):
+    """The raster kernel's second roofline: instruction issue.  With tiles resident in shared memory the
+    kernel moves few HBM bytes per fragment but executes instructions for every one of them, so the bound
+    that matters is (thread-instructions executed) / (148 SMs x 4 schedulers x 32 lanes x SM clock).  The
+    instruction counts come from the committed ncu capture of the same kernel on the same config
+    (profiles/traffic.json: smsp__inst_executed.sum and the active threads per instruction); the duration is
+    this run's own event-timed one."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        inst = json.load(open(p)).get(config, {}).get("raster_kernel_inst")
+    except Exception:
+        inst = None
+    if not inst or not fragments:
+        return None
+    mhz = float(sm_mhz or 1965.0)
+    thread_inst = inst["warp_instructions"] * inst["threads_per_instruction"]
+    lane_slots = 148 * 4 * 32 * mhz * 1e6 * raster_ms * 1e-3
+    return {"kernel": "raster_kernel", "warp_instructions": inst["warp_instructions"],
+            "warp_instructions_per_fragment": inst["warp_instructions"] / fragments,
+            "thread_instructions_per_fragment": thread_inst / fragments,
+            "issue_slots_used": inst["warp_instructions"] / (148 * 4 * mhz * 1e6 * raster_ms * 1e-3),
+            "lane_slots_used": thread_inst / lane_slots, "sm_mhz": mhz,
+            "what": "ncu instruction counts of the committed capture over this run's raster_kernel time; fragments = "
+                    "depth-tested fragments of the reference's algorithm (oracle count)"}
+
+
 def avx_scenes(sc):
     """The two inputs the reference's multithreaded AVX path is timed on (it only
     handles textured + Phong convex objects that do not overlap on screen): the demo sphere at 1080p (config C1)
@@ -815,6 +841,10 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
             if cfgname in ("c1", "c2", "c3"):              # c4 / c5 frames are too large to count on one core here
                 try:
                     rec["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)
+                    issue = issue_roofline(cfgname, rec["roofline"]["equivalent_zbuffer"]["fragments"], stage_ms["raster_kernel"],
+                                           (rec.get("clocks") or {}).get("sm_mhz"))
+                    if issue:
+                        rec["roofline"]["issue"] = issue
                 except Exception as e:
                     rec["roofline"]["equivalent_zbuffer"] = {"error": repr(e)}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the line

@@ -18,6 +18,8 @@ LIB_PATH = os.environ.get("B200R_LIB") or os.path.join(_HERE, "libb200raster.so"
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED, E_NOMEM, E_NO_DEVICE = 0, -1, -2, -3, -4, -5
 WHOLE_OBJECT_AEL = 1
 DEFER_VERDICT = 2
+AVX_RIGHT_END_EXCLUSIVE = 4      # spans cover [MinX, MaxX) (projekt.cpp:782-794)
+AVX_DEPTH_GE = 8                 # depth test >= (projekt.cpp:3205): last submitted wins ties
 MESH_PHONG = 1
 
 EXPORTS = [

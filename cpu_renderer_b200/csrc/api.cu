@@ -209,6 +209,7 @@ static int fill_view(b200r_context *c, const game_render_commands *cmd, const b2
     v.tile_h_shift = 0; while((1 << v.tile_h_shift) < v.tile_h) ++v.tile_h_shift;
     v.tiles_x = (t->Width + c->tile_w - 1)/c->tile_w;
     v.tiles_y = (t->BandRows + c->tile_h - 1)/c->tile_h;
+    v.right_end_exclusive = 0; v.depth_ge = 0;             // set from the call's flags by b200r_render_device
     v.alias_rows = (t->ColorPitch == t->Width*4 && t->DepthStride == t->Width) ? 1 : 0;
     // host-pointer calls render into a device mirror whose rows are padded to 64 pixels; whether a
     // column == Width write lands in the next row (projekt.cpp:414-419) is a property of the CALLER's
@@ -306,15 +307,10 @@ static int issue_frame(b200r_context *c)
     else
     {
     if(c->host_path) CU(cudaStreamWaitEvent(c->stream, c->pos_ready, 0));
-    for(const MeshParams &m : c->meshes)
-    {
-        launch_zrange(m, words->zkeys, c->stream);
-        if(m.ntri) c->stats.KernelLaunches += 1;
-    }
-    launch_zrange_finish(words->zkeys, c->stream);
-    c->stats.KernelLaunches += 1;
     // A partial band of a big mesh (multi-GPU row bands): pre-select the triangles that can reach it
-    // from their positions alone, so that the set-up kernel's front end runs on those only.
+    // from their positions alone, so that the set-up kernel's front end runs on those only.  The
+    // selection pass reads every position anyway and folds the z range in; the other meshes take
+    // zrange_kernel.  Every set-up launch needs the z range of ALL meshes, so these passes come first.
     const bool partial_band = v.band_y0 > 0 || v.band_y1 < v.height;
     bool selecting = false;
     if(partial_band && !c->host_path)
@@ -327,15 +323,23 @@ static int issue_frame(b200r_context *c)
     }
     for(size_t i = 0; i < c->meshes.size(); ++i)
     {
-        MeshParams m = c->meshes[i];
-        if(c->host_path && i < c->chunk_ready.size()) CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
+        MeshParams &m = c->meshes[i];
+        m.tri_list = nullptr; m.tri_count = nullptr;
         if(selecting && m.ntri >= kSelectMinTriangles)
         {
             unsigned *list = (unsigned *)c->sel_list.ptr + m.prim_base, *count = (unsigned *)c->sel_counts.ptr + i;
-            launch_select(v, m, list, count, c->stream);
-            c->stats.KernelLaunches += 1;
+            launch_select(v, m, list, count, words->zkeys, c->stream);
             m.tri_list = list; m.tri_count = count;
         }
+        else launch_zrange(m, words->zkeys, c->stream);
+        if(m.ntri) c->stats.KernelLaunches += 1;
+    }
+    launch_zrange_finish(words->zkeys, c->stream);
+    c->stats.KernelLaunches += 1;
+    for(size_t i = 0; i < c->meshes.size(); ++i)
+    {
+        const MeshParams &m = c->meshes[i];
+        if(c->host_path && i < c->chunk_ready.size()) CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[i], 0));
         launch_setup(v, m, so, c->stream);
         if(m.ntri) c->stats.KernelLaunches += 1;
     }
@@ -626,6 +630,8 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     rc = fill_view(c, cmd, target, v, all_phong);
     if(rc != B200R_OK) return rc;
 
+    v.right_end_exclusive = (flags & B200R_AVX_RIGHT_END_EXCLUSIVE) ? 1 : 0;
+    v.depth_ge = (flags & B200R_AVX_DEPTH_GE) ? 1 : 0;
     if(c->has_gather && (c->gather.Width != target->Width || c->gather.Height != target->Height))
         return fail(c, B200R_E_INVALID, "gather target and render target describe different screens");
 
@@ -960,6 +966,8 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     ENTER(c);
     int rc = settle_pending(c);
     if(rc != B200R_OK) return rc;
+    if((flags & B200R_WHOLE_OBJECT_AEL) && (flags & (B200R_AVX_RIGHT_END_EXCLUSIVE | B200R_AVX_DEPTH_GE)))
+        return fail(c, B200R_E_UNSUPPORTED, "the AVX compatibility switches apply to the per-triangle mode only");
     if(flags & B200R_WHOLE_OBJECT_AEL) return render_objects_whole(c, objs, n, cmd, out);
 
     std::vector<b200r_device_mesh> meshes;

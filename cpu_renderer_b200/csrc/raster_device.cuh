@@ -53,6 +53,8 @@ struct ViewParams
     int tile_w, tile_h;         // powers of two
     int tile_w_shift, tile_h_shift;
     int tiles_x, tiles_y;
+    int right_end_exclusive;    // B200R_AVX_RIGHT_END_EXCLUSIVE: spans cover [MinX, MaxX)
+    int depth_ge;               // B200R_AVX_DEPTH_GE: equal depth goes to the LAST submitted fragment
     int alias_rows;             // rows are contiguous (Pitch == Width*4, depth stride == Width): a pixel the
                                 // reference writes at column == Width lands in column 0 of the next row
 };
@@ -269,8 +271,9 @@ struct SetupOutputs
 };
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
-// positions only: indices of the triangles whose projected rows can reach the band -> list, *count
-void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, cudaStream_t s);
+// positions only: indices of the triangles whose projected rows can reach the band -> list, *count; the same
+// pass folds the mesh's camera z into zkeys (replaces launch_zrange for that mesh)
+void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, cudaStream_t s);
 
 // ---- whole-object mode (object_walk_kernel.cu) ----
 struct ObjectDesc

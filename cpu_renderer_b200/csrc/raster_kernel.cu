@@ -467,7 +467,8 @@ raster_kernel(const __grid_constant__ RasterParams p)
                             {
                                 const float oz = __uint_as_float(old.z);
                                 const int op = (int)old.prim;
-                                if(!(z > oz || (z == oz && prim < op))) { now = oz; STAT_ADD(10, 1); break; }   // :525 + tie rule
+                                // :525 + tie rule (first submitted wins; with B200R_AVX_DEPTH_GE, :3205, the last one)
+                                if(!(z > oz || (z == oz && (p.v.depth_ge ? prim > op : prim < op)))) { now = oz; STAT_ADD(10, 1); break; }
                                 const Pixel prev = cas_pixel(pa, old, mine);
                                 STAT_ADD(8, 1);
                                 // (depth, owner) identify a pixel's contents: no need to compare the colour

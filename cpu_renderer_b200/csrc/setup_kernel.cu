@@ -146,11 +146,15 @@ __device__ __forceinline__ bool off_band_rows(float y0, float y1, float y2, cons
 // test) on every triangle although about 1/G of them can reach its band: C4's set-up scaled 1.65x
 // on 8 GPUs.  This pass reads the positions only (36 B), applies the same band test to the same
 // projected rows, and compacts the surviving indices; the set-up kernel then gathers just those.
+// The positions are read ONCE: the same pass accumulates the frame's z range (what zrange_kernel does
+// for meshes that are not pre-selected) -- both kernels read every position, and at 8 bands that
+// read is a fifth of a GPU's whole frame.
 __global__ void __launch_bounds__(256)
-select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count)
+select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count, unsigned *zkeys)
 {
     const unsigned tri = blockIdx.x*blockDim.x + threadIdx.x;
     bool keep = false;
+    unsigned kmax = 0u, kmin = 0xffffffffu;
     if(tri < m.ntri)
     {
         const float *gp = m.pos + (size_t)tri*9;
@@ -158,8 +162,11 @@ select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count)
 #pragma unroll
         for(int k = 0; k < 3; ++k)
         {
-            V3 cam = { fadd(__ldg(gp + 3*k + 0), m.px), fadd(__ldg(gp + 3*k + 1), m.py), fadd(__ldg(gp + 3*k + 2), m.pz) };
+            const float pz = __ldg(gp + 3*k + 2);
+            V3 cam = { fadd(__ldg(gp + 3*k + 0), m.px), fadd(__ldg(gp + 3*k + 1), m.py), fadd(pz, m.pz) };
             y[k] = project_vertex(cam, v).y;
+            const float z = pz + m.pz;                      // as zrange_kernel
+            if(fabsf(z) < 3.0e38f) { const unsigned kk = float_key(z); kmax = max(kmax, kk); kmin = min(kmin, kk); }
         }
         keep = !off_band_rows(y[0], y[1], y[2], v);
     }
@@ -169,6 +176,9 @@ select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count)
     if(lane == 0 && bal) at = atomicAdd(count, (unsigned)__popc(bal));
     at = __shfl_sync(0xffffffffu, at, 0);
     if(keep) list[at + __popc(bal & ((1u << lane) - 1u))] = tri;
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    if(lane == 0 && kmax != 0u) { atomicMax(&zkeys[0], kmax); atomicMax(&zkeys[1], ~kmin); }
 }
 
 // PHONG: the mesh is drawn with per-pixel Phong shading (render_entry_3d_object::PhongShading,
@@ -837,6 +847,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
                         else if(rightx >= wf) { rightx = wf_m1; }
                         const int minx = round_s32(leftx);                            // :402-406
                         int maxx = round_s32(rightx);
+                        if(v.right_end_exclusive) maxx -= 1;                          // AVX fillers: [MinX, MaxX), projekt.cpp:782-794
                         const float z = fadd(L.z, fmul(xoff, zi));                    // :375, :408
                         const float c0 = fadd(L.c0, fmul(xoff, i0)), c1 = fadd(L.c1, fmul(xoff, i1));   // :379, :412
                         const float c2 = fadd(L.c2, fmul(xoff, i2)), c3 = fadd(L.c3, fmul(xoff, i3));
@@ -951,10 +962,10 @@ void launch_zrange_finish(unsigned *zkeys, cudaStream_t s)
     zrange_finish_kernel<<<1, 1, 0, s>>>(zkeys);
 }
 
-void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, cudaStream_t s)
+void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, cudaStream_t s)
 {
     if(m.ntri == 0) return;
-    select_kernel<<<(m.ntri + 255)/256, 256, 0, s>>>(v, m, list, count);
+    select_kernel<<<(m.ntri + 255)/256, 256, 0, s>>>(v, m, list, count, zkeys);
 }
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s)

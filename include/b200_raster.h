@@ -156,6 +156,17 @@ typedef struct edge_info                   /* projekt.h:17-37, 120 bytes */
                                       the frame is re-issued at that later point, reading the mesh and target
                                       pointers again.  For pipelines that re-submit frames of known size.       */
 
+/* Compatibility switches, for hosts that compare against images of the reference's AVX
+ * fillers.  Those differ from the scalar path in more than can be switched (lane-wise start + k*inc
+ * arithmetic, truncated texel coordinates -- SURVEY.md section 0); these are the two rules that can be stated
+ * on top of the scalar arithmetic.  Per-triangle mode only (with B200R_WHOLE_OBJECT_AEL: B200R_E_UNSUPPORTED). */
+#define B200R_AVX_RIGHT_END_EXCLUSIVE 4u   /* a span covers [MinX, MaxX) instead of [MinX, MaxX]: the end-clip masks of
+                                              FillLinesOptimized (projekt.cpp:782-794); no pixel is ever written at
+                                              column == Width                                                          */
+#define B200R_AVX_DEPTH_GE 8u              /* the depth test is CurrentZ >= *Z (DrawModelOptimized, projekt.cpp:3205)
+                                              instead of > (:525): equal depth goes to the LAST submitted fragment, and
+                                              pre-existing target contents lose ties                                    */
+
 typedef struct b200r_context b200r_context;
 
 /* One context per GPU.  Device < 0 keeps the calling thread's current device. */

@@ -302,6 +302,13 @@ static void sample_texture(const orc_texture *Tex, float U, float V, float W, fl
     Out[2] = (float)((Texel >> 0) & 0xFF)/255.0f;
 }
 
+/* Compatibility switches: the two rules in which the reference's AVX fillers differ
+ * from its scalar path and that can be stated on top of the scalar arithmetic -- the right end of a span is
+ * exclusive (projekt.cpp:782-794, the end-clip masks) and the depth test is >= (projekt.cpp:3205).  Test
+ * infrastructure state, set before a render and not thread safe. */
+static int g_compat = 0;
+void orc_set_compat(int32_t Flags) { g_compat = Flags; }
+
 static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Row,
                           int32_t PrimIndex, orc_target *T, orc_stats *Stats,
                           const orc_scene *Scene, int32_t Phong, const orc_texture *Tex)
@@ -335,6 +342,7 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
     else if(RightX >= (float)T->Width) { RightX = (float)T->Width - 1; }
     int32_t MinX = (int32_t)(float)round_s32(LeftX);             /* :402-406 */
     int32_t MaxX = (int32_t)(float)round_s32(RightX);
+    if(g_compat & ORC_COMPAT_RIGHT_END_EXCLUSIVE) MaxX -= 1;     /* AVX fillers: [MinX, MaxX) */
     Z += XOffset*ZInc;                                           /* :408 */
     W += XOffset*WInc;                                           /* :409 */
     U += XOffset*UInc; V += XOffset*VInc;                        /* :410 */
@@ -369,7 +377,7 @@ static void orc_fill_span(const active_edge *L, const active_edge *R, int32_t Ro
         uint32_t Color32 = (round_u32(F[3]*255.0f) << 24) | (round_u32(F[0]*255.0f) << 16) |
                            (round_u32(F[1]*255.0f) << 8) | (round_u32(F[2]*255.0f) << 0);
         if(Stats) Stats->Fragments += 1;
-        if(Z > *ZPixel)                                          /* :525 */
+        if((g_compat & ORC_COMPAT_DEPTH_GE) ? (Z >= *ZPixel) : (Z > *ZPixel))     /* :525 (AVX single-thread variant: >=, :3205) */
         {
             *ZPixel = Z;
             *Pixel = Color32;

@@ -88,6 +88,11 @@ typedef struct orc_stats {
     uint64_t TexelClamps;               /* textured pixels whose texel coordinates left the bitmap */
 } orc_stats;
 
+/* Compatibility switches of the span fill (mirror B200R_AVX_RIGHT_END_EXCLUSIVE / B200R_AVX_DEPTH_GE). */
+#define ORC_COMPAT_RIGHT_END_EXCLUSIVE 4
+#define ORC_COMPAT_DEPTH_GE 8
+void orc_set_compat(int32_t Flags);
+
 void orc_project_vertex(const float Cam[3], const orc_transform *T, float Out[3]);
 
 /* Whole object (VertexCount/3 triangles) -> sorted edge records.  Edges/Temp need room for

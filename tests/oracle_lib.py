@@ -308,9 +308,18 @@ def _orc_target(color, z, prim):
     return t
 
 
-def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0, phong=False):
-    """Level-1 (one triangle = one object) render.  Returns dict(color, z, prim, stats, would_crash)."""
+def oracle_render(scene, with_prim=False, threads=1, targets=None, prim_base=0, phong=False, compat=0):
+    """Level-1 (one triangle = one object) render.  Returns dict(color, z, prim, stats, would_crash).
+    ``compat``: ORC_COMPAT_* switches of the span fill (= the B200R_AVX_* flag values)."""
     lib = oracle()
+    lib.orc_set_compat(int(compat))
+    try:
+        return _oracle_render(lib, scene, with_prim, threads, targets, prim_base, phong)
+    finally:
+        lib.orc_set_compat(0)
+
+
+def _oracle_render(lib, scene, with_prim, threads, targets, prim_base, phong):
     s = OracleScene(scene)
     color, z, prim = targets if targets is not None else new_targets(scene, with_prim)
     t = _orc_target(color, z, prim)

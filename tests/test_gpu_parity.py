@@ -767,7 +767,8 @@ def test_row_band_preselection_of_a_large_mesh(renderer, mode):
     for a, b in zip(cuts, cuts[1:]):
         c, z = _device_render(renderer, s, (64, 32), a, b - a, phong=phong)
         colors.append(c); depths.append(z)
-    assert renderer.stats()["KernelLaunches"] - launches == 3 * 8      # 7 kernels per frame + select_kernel
+    # 7 kernels per frame: select_kernel (which folds the z range in) takes the place of zrange_kernel
+    assert renderer.stats()["KernelLaunches"] - launches == 3 * 7
     color, z = np.concatenate(colors), np.concatenate(depths)
     assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32))
     ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
@@ -975,3 +976,34 @@ def test_row_parallel_setup_with_forced_parameters(monkeypatch, tpc, rows, chunk
         assert st["Spans"] > 0 and st["Binned"] <= st["Triangles"]
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("flags", [api.AVX_RIGHT_END_EXCLUSIVE, api.AVX_DEPTH_GE, api.AVX_RIGHT_END_EXCLUSIVE | api.AVX_DEPTH_GE])
+@pytest.mark.parametrize("seed", range(600, 606))
+def test_avx_compatibility_switches_against_the_oracle(renderer, flags, seed):
+    """exclusive right span end (projekt.cpp:782-794) and >= depth test (:3205) on top of
+    the scalar arithmetic.  Every triangle is submitted twice with different colours, so every pixel has an
+    equal-depth tie: > keeps the first submission, >= takes the last; half of the target is pre-filled with
+    depths that tie-break against the new fragments too."""
+    s, phong, tex, tile, _ = _random_case(seed)
+    rng = np.random.default_rng(seed)
+    dup = lambda a: np.ascontiguousarray(np.concatenate([a, a]))             # noqa: E731
+    col2 = s.colors.copy(); col2[:, :3] = 1.0 - col2[:, :3]
+    s = replace(s, positions=dup(s.positions), normals=dup(s.normals), uvs=dup(s.uvs),
+                colors=np.ascontiguousarray(np.concatenate([s.colors, col2])))
+    plain = ol.oracle_render(s, phong=phong)
+    pre_c = rng.integers(0, 2**32, size=(s.height, s.width), dtype=np.uint64).astype(np.uint32)
+    pre_z = np.where(rng.random((s.height, s.width)) < 0.5, plain["z"], np.float32(s.clear_depth)).astype(np.float32)
+    want = ol.oracle_render(s, phong=phong, targets=(pre_c.copy(), pre_z.copy(), None), compat=flags)
+    color, z = pre_c.copy(), pre_z.copy()
+    renderer.set_tile(*tile)
+    renderer.render_scene_host(s, color, z, phong=phong, flags=flags)
+    assert np.array_equal(z.view(np.uint32), want["z"].view(np.uint32)), (seed, flags, phong, tex)
+    ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    assert int(ch.max()) <= (PHONG_TOLERANCE_LSB if phong else 0), (seed, flags, int(ch.max()))
+    # the switches change the image (otherwise this test proves nothing)
+    base = ol.oracle_render(s, phong=phong, targets=(pre_c.copy(), pre_z.copy(), None))
+    assert not np.array_equal(base["color"], want["color"])
+    # and they are refused where they are not implemented
+    with pytest.raises(api.B200RasterError):
+        renderer.render_scene_host(s, color.copy(), z.copy(), phong=phong, flags=flags | api.WHOLE_OBJECT_AEL)
