@@ -785,7 +785,7 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
                                    .get(cfgname, f"frame-parallel x{world}") if world > 1 else "1 GPU"),
                    "frames_per_step_per_rank": nframes, "band_rows": band_rows, "scale": scale,
                    "tile": (tile if tile != "0x0" else
-                            "auto:" + ("64x16" if W * band_rows / max(ntri, 1) < 4.0 else "128x8")),
+                            "auto:" + ("64x16" if W * H / max(ntri, 1) < 4.0 else "128x8")),
                    "timing": f"median of {passes} passes of exactly {K} steps, per pass the max over ranks (CUDA events)",
                    "l2": "each timed frame streams >126 MB (vertices + records + pair lists + its own "
                          "pre-cleared target), i.e. inputs larger than L2; no explicit flush",

@@ -624,7 +624,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     {
         uint64_t tris = 0;
         for(u32 i = 0; i < mesh_count; ++i) tris += meshes[i].TriangleCount;
-        choose_tile(c, tris, target->Width, target->BandRows);
+        choose_tile(c, tris, target->Width, target->Height);    // triangle density of the SCREEN: a band sees the same triangles
     }
     ViewParams v;
     rc = fill_view(c, cmd, target, v, all_phong);
@@ -681,7 +681,7 @@ int b200r_render_device(b200r_context *c, const b200r_device_mesh *meshes, u32 m
     // CTAs cost a frame of 100 000 ten-pixel triangles a quarter of its set-up time)
     // Measured (C3 scaled, 4K): 500 / 2 500 / 10 000 triangles 0.19 / 0.20 / 0.20 -> 0.08 / 0.08 / 0.12 ms; from
     // 25 000 triangles on a thread per triangle is faster again (0.23 against 0.26 ms).
-    const bool tall = total > 0 && (uint64_t)target->Width*(uint64_t)target->BandRows >= total*64;
+    const bool tall = total > 0 && (uint64_t)target->Width*(uint64_t)target->Height >= total*64;
     if(tall && c->tall_mode != 0)
         for(MeshParams &mp : ms) { mp.sort_shift = c->tall_shift; mp.row_chunk = c->tall_chunk; }
     if(total > 0 && c->split_mode != 0 && (c->split_mode == 2 || (tall && total <= 16384)))

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--phong", action="store_true")
     ap.add_argument("--textured", action="store_true")
+    ap.add_argument("--band", default="0/1", help="i/n: render only band i of n row bands (what rank i of n GPUs does)")
     args = ap.parse_args()
     import torch
     import bench
@@ -46,9 +47,12 @@ def main():
         d_tex = torch.from_numpy(scene.texture.view(np.int32)).to(dev)
         dtex = api.device_texture(d_tex.data_ptr(), scene.texture.shape[1], scene.texture.shape[0], scene.texture.shape[1] * 4)
         uv, tex = d_uv.data_ptr(), C.pointer(dtex)
-    color = torch.empty((H, wpad), dtype=torch.int32, device=dev)
-    depth = torch.empty((H, wpad), dtype=torch.float32, device=dev)
-    target = api.device_target(color.data_ptr(), depth.data_ptr(), W, H, wpad * 4, wpad, 0, H)
+    from cpu_renderer_b200 import shard
+    bi, bn = (int(x) for x in args.band.split("/"))
+    first, rows = shard.band_rows(H, bn, bi, 32)
+    color = torch.empty((rows, wpad), dtype=torch.int32, device=dev)
+    depth = torch.empty((rows, wpad), dtype=torch.float32, device=dev)
+    target = api.device_target(color.data_ptr(), depth.data_ptr(), W, H, wpad * 4, wpad, first, rows)
     cmd, keep = api.make_commands(scene)
     mesh = api.device_mesh(d_pos.data_ptr(), d_col.data_ptr(), d_nrm.data_ptr(), ntri, api.v3(*scene.object_p),
                            api.MESH_PHONG if args.phong else 0, uv, tex)
