@@ -86,6 +86,9 @@ struct b200r_context
     int split_mode = 1, split_tpc = 0, split_rows = 0;   // row-parallel set-up (env B200R_SPLIT=0 off, B200R_SPLIT_TPC / _ROWS force)
 
     DeviceBuffer recs, segs, spans, tiles, pairs, words;
+    // b200r_fill_edge_table: second set-up pass of a textured object, edge counts + offsets, sort keys / payloads
+    // (two buffers each), the assembled edge_info table
+    DeviceBuffer recs_uv, et_counts, et_keys, et_vals, et_out;
     FrameWords *h_words = nullptr;      // pinned
     // row-band pre-selection (select_kernel): one index list for the frame's meshes, one count per mesh
     DeviceBuffer sel_list, sel_counts;
@@ -546,6 +549,7 @@ void b200r_destroy(b200r_context *c)
     c->recs.release(); c->segs.release(); c->spans.release(); c->tiles.release(); c->pairs.release(); c->words.release();
     c->d_pos.release(); c->d_col.release(); c->d_nrm.release(); c->d_uv.release(); c->d_color.release(); c->d_depth.release();
     c->tex_dev.release();
+    c->recs_uv.release(); c->et_counts.release(); c->et_keys.release(); c->et_vals.release(); c->et_out.release();
     c->obj_dev.release(); c->edges_pristine.release(); c->edges_work.release();
     c->sel_list.release(); c->sel_counts.release();
     c->obj_chain_base.release(); c->obj_chains.release(); c->obj_pairs.release(); c->obj_flags.release();
@@ -1045,28 +1049,11 @@ int b200r_render_objects(b200r_context *c, const render_entry_3d_object *objs, u
     return B200R_OK;
 }
 
-// The reference's MergeSort (projekt.cpp:2-72) is not stable: on equal YMin the merge takes the
-// right half first (:51-58) while the two-element base case keeps the left one first (:13).  The
-// resulting order is a pure function of (YMin, position): walk the recursion from the root and
-// emit, per level, 0 for the side that wins ties.  Sorting by (YMin, that path) reproduces it.
-static uint32_t merge_tie_key(uint32_t i, uint32_t n)
-{
-    uint32_t key = 0, lo = 0, cnt = n;
-    int depth = 0;
-    while(cnt > 2)
-    {
-        uint32_t half0 = cnt/2;
-        uint32_t bit;
-        if(i - lo < half0) { bit = 1; cnt = half0; }
-        else { bit = 0; lo += half0; cnt -= half0; }
-        key = (key << 1) | bit; ++depth;
-    }
-    if(cnt == 2) { key = (key << 1) | (i - lo); ++depth; }
-    return key << (32 - depth);
-}
-
 // FillEdgeTable of one object (projekt.cpp:3882) into outp (room for VertexCount records), in the
-// reference's MergeSort order.  Returns the edge count or a negative status.
+// reference's MergeSort order (projekt.cpp:2-72; reproduced on the device, edge_table_kernels.cu).  Every
+// field of a record is written: the ones the reference leaves untouched for this kind of object (texture
+// fields of an untextured object, normals of a Gouraud object, Next) are zero.  Returns the edge count or a
+// negative status.
 static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
                             const game_render_commands *cmd, b32 phong, edge_info *outp)
 {
@@ -1085,8 +1072,10 @@ static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     if(rc != B200R_OK) return rc;
     CU(cudaStreamWaitEvent(c->stream, c->pos_ready, 0));
     CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[meshes.size() - 1], 0));
-    const u32 tris = meshes[0].TriangleCount;
+    // the upload is chunked (one mesh per 131 072 triangles) but contiguous: one set-up pass over the whole object
+    const u32 tris = obj->VertexCount/3;
     if(tris == 0) return 0;
+    if(tris > kScanMaxChunks*8192u) return fail(c, B200R_E_UNSUPPORTED, "b200r_fill_edge_table: more than 16 M triangles in one object");
 
     // Only the set-up kernel runs.  Height only clamps MaxY in the record header (unused here);
     // a 1x1 dummy band keeps the tile bookkeeping trivial.
@@ -1121,84 +1110,46 @@ static int build_edge_table(b200r_context *c, const render_entry_3d_object *obj,
     launch_setup(v, mp, so, c->stream);
     c->stats.KernelLaunches += 1;
     CU(cudaGetLastError());
-    std::vector<uint32_t> recs((size_t)tris*kRecWords), uvrecs;
-    CU(cudaMemcpyAsync(recs.data(), c->recs.ptr, recs.size()*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    // FillEdgeTable's tail on the device (edge_table_kernels.cu): the emission index of every edge (a scan
+    // of the per-triangle edge counts), MergeSort's order (projekt.cpp:2-72) as a sort on unique keys, and
+    // the edge_info records themselves; only the finished table crosses the bus.
+    const uint32_t *d_uvrecs = nullptr;
     if(textured)
     {
+        CU(c->recs_uv.reserve((size_t)tris*kRecWords*sizeof(uint32_t)));
         CU(c->d_uv.reserve((size_t)tris*3*8));
         CU(cudaMemcpyAsync(c->d_uv.ptr, obj->UVData, (size_t)tris*3*8, cudaMemcpyHostToDevice, c->stream));
         mp.uv = (const float *)c->d_uv.ptr; mp.tex = 0; mp.white = 0;
+        so.recs = (uint32_t *)c->recs_uv.ptr;
         launch_setup(v, mp, so, c->stream);
         c->stats.KernelLaunches += 1;
         CU(cudaGetLastError());
-        uvrecs.resize(recs.size());
-        CU(cudaMemcpyAsync(uvrecs.data(), c->recs.ptr, uvrecs.size()*sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        d_uvrecs = (const uint32_t *)c->recs_uv.ptr;
     }
+    CU(c->et_counts.reserve(((size_t)tris*2 + 2)*sizeof(unsigned)));
+    unsigned *counts = (unsigned *)c->et_counts.ptr, *offsets = counts + tris;      // tris + 1 offsets
+    launch_edge_counts((const uint32_t *)c->recs.ptr, tris, counts, c->stream);
+    launch_tile_scan(counts, offsets, tris, &words->pair_total, words->scan_state, &words->scan_ticket, c->stream);
+    c->stats.KernelLaunches += 2;
+    unsigned n = 0;
+    CU(cudaMemcpyAsync(&n, &words->pair_total, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-
-    // Host side of FillEdgeTable's tail: append each triangle's edges in the reference's
-    // emission order (edge 0-1, 1-2, 2-0; projekt.cpp:3947) and apply MergeSort's permutation.
-    struct Ref { uint64_t key; const uint32_t *edge; u32 tri; };
-    std::vector<Ref> order;
-    order.reserve((size_t)tris*3);
-    for(u32 tri = 0; tri < tris; ++tri)
-    {
-        const uint32_t *rec = recs.data() + (size_t)tri*kRecWords;
-        const int ne = (int)rec[R_NEDGES];
-        const uint32_t emit = rec[R_EDGE0 + 3*kEdgeWords];     // slot of the k-th emitted edge, 2 bits each
-        for(int k = 0; k < ne; ++k)
-        {
-            int slot = (emit >> (2*k)) & 3;
-            order.push_back({0, rec + R_EDGE0 + slot*kEdgeWords, tri});
-        }
-    }
-    const uint32_t n = (uint32_t)order.size();
-    for(uint32_t i = 0; i < n; ++i)
-    {
-        uint32_t ymin = order[i].edge[E_YMIN];
-        order[i].key = ((uint64_t)(ymin ^ 0x80000000u) << 32) | merge_tie_key(i, n);
-    }
-    std::sort(order.begin(), order.end(), [](const Ref &a, const Ref &b) { return a.key < b.key; });
-    for(uint32_t i = 0; i < n; ++i)
-    {
-        const uint32_t *E = order[i].edge;
-        edge_info &o = outp[i];
-        // NaN sign/payload is not part of the arithmetic contract: SSE's invalid-operation result
-        // is the default NaN 0xFFC00000 (and it propagates), the GPU's is 0x7FFFFFFF.  Such values
-        // only occur in edges that are never drawn (YMax == YMin: gradients 0/0); export them in
-        // the x86 encoding so that the table is byte-identical to the reference's.
-        auto f = [&](int w) { uint32_t u = E[w]; if((u & 0x7fffffffu) > 0x7f800000u) u = 0xffc00000u;
-                              float x; memcpy(&x, &u, 4); return x; };
-        o.YMin = (s32)E[E_YMIN]; o.YMax = (s32)E[E_YMAX];
-        o.XMin = f(E_X); o.Gradient = f(E_DX); o.ZMin = f(E_Z); o.ZGradient = f(E_DZ);
-        o.MinColor.x = f(E_C + 0); o.MinColor.y = f(E_C + 1); o.MinColor.z = f(E_C + 2); o.MinColor.w = f(E_C + 3);
-        o.ColorGradient.x = f(E_DC + 0); o.ColorGradient.y = f(E_DC + 1);
-        o.ColorGradient.z = f(E_DC + 2); o.ColorGradient.w = f(E_DC + 3);
-        o.Left = (b32)(E[E_LEFT] & 1u);
-        o.Next = nullptr;
-        if(textured)
-        {
-            // same triangle, same slot of the second pass: u/z, v/z, 1/z in the colour words
-            const uint32_t *U = uvrecs.data() + (E - recs.data());
-            auto g = [&](int w) { uint32_t u = U[w]; if((u & 0x7fffffffu) > 0x7f800000u) u = 0xffc00000u;
-                                  float x; memcpy(&x, &u, 4); return x; };
-            o.UMin = g(E_C + 0); o.VMin = g(E_C + 1); o.OneOverZMin = g(E_C + 2);
-            o.UGradient = g(E_DC + 0); o.VGradient = g(E_DC + 1); o.OneOverZGradient = g(E_DC + 2);
-        }
-        if(phong)
-        {
-            // projekt.cpp:4017-4018, 4104-4109: MinNormal = the upper vertex's normal (not advanced by
-            // the top clip), NormalGradient = (MaxNormal - MinNormal)/YDifference -- one IEEE
-            // subtraction and division each, done here on the host from the caller's NormalData
-            const float *N = (const float *)obj->NormalData + (size_t)order[i].tri*9;
-            const int mn = (int)((E[E_LEFT] >> 8) & 3u), mx = (int)((E[E_LEFT] >> 16) & 3u);
-            const volatile float ydiff = (float)o.YMax - (float)o.YMin;
-            const float *a = N + 3*mn, *b = N + 3*mx;
-            o.MinNormal.x = a[0]; o.MinNormal.y = a[1]; o.MinNormal.z = a[2];
-            volatile float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
-            o.NormalGradient.x = dx/ydiff; o.NormalGradient.y = dy/ydiff; o.NormalGradient.z = dz/ydiff;
-        }
-    }
+    if(n > obj->VertexCount) return fail(c, B200R_E_CUDA, "edge count exceeds VertexCount");    // cannot happen: <= 3 per triangle
+    if(n == 0) return 0;
+    CU(c->et_keys.reserve((size_t)n*2*sizeof(unsigned long long)));
+    CU(c->et_vals.reserve((size_t)n*2*sizeof(unsigned)));
+    CU(c->et_out.reserve((size_t)n*sizeof(edge_info)));
+    unsigned long long *keys[2] = { (unsigned long long *)c->et_keys.ptr, (unsigned long long *)c->et_keys.ptr + n };
+    unsigned *vals[2] = { (unsigned *)c->et_vals.ptr, (unsigned *)c->et_vals.ptr + n };
+    launch_edge_keys((const uint32_t *)c->recs.ptr, tris, offsets, &words->pair_total, keys[0], vals[0], c->stream);
+    const int at = launch_edge_sort(keys, vals, n, &words->pair_total, c->stream);
+    launch_edge_assemble((const uint32_t *)c->recs.ptr, d_uvrecs, phong ? (const float *)mp.nrm : nullptr, vals[at], n,
+                         &words->pair_total, c->et_out.ptr, c->stream);
+    c->stats.KernelLaunches += 3;
+    for(unsigned long long run = 2048; run < n; run <<= 1) c->stats.KernelLaunches += 1;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(outp, c->et_out.ptr, (size_t)n*sizeof(edge_info), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return (int)n;
 }
 

@@ -275,6 +275,14 @@ void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &
 // pass folds the mesh's camera z into zkeys (replaces launch_zrange for that mesh)
 void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, cudaStream_t s);
 
+// ---- FillEdgeTable's tail on the device (edge_table_kernels.cu): emission order, MergeSort order, edge_info ----
+void launch_edge_counts(const uint32_t *recs, unsigned ntri, unsigned *counts, cudaStream_t s);
+void launch_edge_keys(const uint32_t *recs, unsigned ntri, const unsigned *offsets, const unsigned *total,
+                      unsigned long long *keys, unsigned *vals, cudaStream_t s);
+int launch_edge_sort(unsigned long long *keys[2], unsigned *vals[2], unsigned n, const unsigned *total, cudaStream_t s);
+void launch_edge_assemble(const uint32_t *recs, const uint32_t *uvrecs, const float *normals, const unsigned *vals,
+                          unsigned n, const unsigned *total, void *out, cudaStream_t s);
+
 // ---- whole-object mode (object_walk_kernel.cu) ----
 struct ObjectDesc
 {

@@ -233,12 +233,18 @@ select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count, unsig
 // from the triangle's first row -- 14 adds and the crossing test per row, no span set-up -- and emits
 // the spans of its own slab only, at offsets it derives from the same closed-form row counts that sized
 // the triangle's allocation.  A template parameter: the small-triangle kernels must not pay for it.
+// DIRECT_COL: untextured meshes do not stage their vertex colours -- the thread that lights a triangle reads its
+// 48 bytes itself (three 128-bit loads issued at the top of phase 2, used by the lighting ~150 instructions
+// later) -- which takes the kernel's shared memory from 43.4 to 37.3 KB; held to 80 registers (16 bytes of
+// spill) six CTAs fit an SM instead of five.  Measured: C2 and C3 unchanged (the kernel is not occupancy
+// bound: 0.334 ms either way), a 1/8 row band of C4 (LISTED: the gather no longer stages colours) 1.85 -> 1.76 ms.
 template<bool PHONG, bool TEX, bool LISTED, bool SPLIT>
-__global__ void __launch_bounds__(kSetupThreads, 5)
+__global__ void __launch_bounds__(kSetupThreads, (!PHONG && !TEX) ? 6 : 5)
 setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 {
+    constexpr bool DIRECT_COL = !TEX;
     __shared__ __align__(16) float s_pos[kSetupThreads*9];
-    __shared__ __align__(16) float s_col[kSetupThreads*12];
+    __shared__ __align__(16) float s_col[DIRECT_COL ? 4 : kSetupThreads*12];
     __shared__ __align__(16) float s_nrm[kSetupThreads*9];
     // per triangle only the 3 x 15 edge words live in shared memory (odd stride: conflict-free);
     // `rec` pointers below are biased by -R_EDGE0 so that rec[R_EDGE0 + ...] addresses them.
@@ -295,7 +301,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 #pragma unroll
                     for(int i = 0; i < 6; ++i) s_col[t*12 + i] = ru[i];
                 }
-                else
+                else if(!DIRECT_COL)
                 {
                     const float *c12 = m.col + (size_t)id*12;
                     float rc[12];
@@ -328,7 +334,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             {
                 const int i = t + k*kSetupThreads;
                 rp[k] = (i < kPos4) ? __ldg(gp4 + i) : make_float4(0, 0, 0, 0);
-                rc[k] = (i < kCol4) ? __ldg(gc4 + i) : make_float4(0, 0, 0, 0);
+                if(!DIRECT_COL) rc[k] = (i < kCol4) ? __ldg(gc4 + i) : make_float4(0, 0, 0, 0);
                 rn[k] = (i < kPos4) ? __ldg(gn4 + i) : make_float4(0, 0, 0, 0);
             }
 #pragma unroll
@@ -336,13 +342,13 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
             {
                 const int i = t + k*kSetupThreads;
                 if(i < kPos4) { reinterpret_cast<float4 *>(s_pos)[i] = rp[k]; reinterpret_cast<float4 *>(s_nrm)[i] = rn[k]; }
-                if(i < kCol4) reinterpret_cast<float4 *>(s_col)[i] = rc[k];
+                if(!DIRECT_COL && i < kCol4) reinterpret_cast<float4 *>(s_col)[i] = rc[k];
             }
         }
         else
         {
             for(unsigned i = t; i < n*9; i += kSetupThreads) { s_pos[i] = __ldg(gp + i); s_nrm[i] = __ldg(gn + i); }
-            for(unsigned i = t; i < n*12; i += kSetupThreads) s_col[i] = __ldg(gc + i);
+            if(!DIRECT_COL) for(unsigned i = t; i < n*12; i += kSetupThreads) s_col[i] = __ldg(gc + i);
         }
     }
     __syncthreads();
@@ -440,6 +446,22 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
     if(tri >= 0)
     {
         uint32_t *rec = s_edge + tri*kEdgeRec - R_EDGE0;
+        // DIRECT_COL: the triangle's three vertex colours, requested now and used by the lighting below
+        float4 cq[3];
+        if(DIRECT_COL)
+        {
+            const float *c12 = m.col + (size_t)(listed ? s_id[tri] : base + (unsigned)tri)*12;
+            if((((uintptr_t)m.col) & 15) == 0)
+            {
+#pragma unroll
+                for(int q = 0; q < 3; ++q) cq[q] = __ldg(reinterpret_cast<const float4 *>(c12) + q);
+            }
+            else
+            {
+#pragma unroll
+                for(int q = 0; q < 3; ++q) cq[q] = make_float4(__ldg(c12 + 4*q), __ldg(c12 + 4*q + 1), __ldg(c12 + 4*q + 2), __ldg(c12 + 4*q + 3));
+            }
+        }
         V3 cam[3], prj[3];
         project_triangle(tri, cam, prj);
         uint32_t emit = 0;                                  // slot of the k-th edge FillEdgeTable emits, 2 bits each
@@ -490,7 +512,9 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 #pragma unroll 1
                 for(int q = 0; q < 3; ++q)
                 {
-                    float4 c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
+                    float4 c4;
+                    if(DIRECT_COL) c4 = (q == 0) ? cq[0] : (q == 1) ? cq[1] : cq[2];
+                    else c4 = *reinterpret_cast<const float4 *>(&s_col[tri*12 + 4*q]);
                     float col[4] = { c4.x, c4.y, c4.z, c4.w };
                     V3 nr = { s_nrm[tri*9 + 3*q + 0], s_nrm[tri*9 + 3*q + 1], s_nrm[tri*9 + 3*q + 2] };
                     if(TEX) { lit[q][0] = s_col[tri*12 + 2*q]; lit[q][1] = s_col[tri*12 + 2*q + 1]; lit[q][2] = 0.0f; lit[q][3] = 0.0f; }

@@ -116,6 +116,25 @@ def test_fill_edge_table_random_object(renderer):
                               np.ascontiguousarray(want[f]).view(np.uint32)), f
 
 
+@pytest.mark.parametrize("ntri,phong", [(1, False), (683, False), (2049, True), (300_001, False)])
+def test_fill_edge_table_device_merge_sort_order(renderer, ntri, phong):
+    """MergeSort's order (projekt.cpp:2-72) is reproduced on the device (edge_table_kernels.cu: unique
+    (YMin, tie path) keys, bitonic tiles of 2 048, rank-merge levels).  Sizes around the tile size, a
+    single edge pair, and an object of 300 001 triangles -- three upload chunks, ~9 merge levels, an odd
+    count at every level of the reference's recursion, and thousands of equal YMin keys per row."""
+    s = sc.triangle_soup("ms", 0x77 + ntri, ntri, 1280, 720, 1.0, 12.0, jitter=2.5)
+    e = renderer.fill_edge_table(s, phong=phong)
+    want, n = ol.oracle_edge_table(s, phong=phong)
+    assert len(e) == n
+    for f in (ol.PHONG_FIELDS if phong else ol.GOURAUD_FIELDS):
+        a, b = np.ascontiguousarray(e[f]), np.ascontiguousarray(want[f])
+        same = a.view(np.uint32) == b.view(np.uint32)
+        if a.dtype.kind == "f":
+            same |= (np.isnan(a) & np.isnan(b))
+        assert same.all(), (f, int((~same).sum()))
+    assert not e["Next"].any()
+
+
 def test_several_objects_and_split_submission(renderer):
     s = sc.triangle_soup("multi", 0x31, 30_000, 1280, 720, 2.0, 30.0)
     nv = s.positions.shape[0]

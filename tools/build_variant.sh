@@ -5,7 +5,7 @@ suffix=$1; shift
 src=/root/repo/cpu_renderer_b200/csrc
 out=/tmp/variant_$suffix; mkdir -p $out
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC"
-for f in setup_kernel object_walk_kernel bin_kernels raster_kernel api; do
+for f in setup_kernel object_walk_kernel bin_kernels edge_table_kernels raster_kernel api; do
   nvcc $FL "$@" -c $src/$f.cu -o $out/$f.o &
 done
 wait
