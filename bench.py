@@ -439,7 +439,7 @@ def expected_hashes():
 
 
 def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textured=False, tile=None,
-            e2e_steps=10, cpu_baseline=False, c1_whole_object=False):
+            e2e_steps=10, cpu_baseline=False, c1_whole_object=False, zbuffer_roofline=False):
     """One configuration, measured three ways: device-resident frames (CUDA events, `passes` passes of
     exactly K steps, max over ranks per pass), per-kernel durations, and end to end with host buffers."""
     torch, dist, api = ctx.torch, ctx.dist, ctx.api
@@ -838,18 +838,21 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
                 rec["cpu_baseline"]["avx_mt"] = avx_baseline(r)
             except Exception as e:
                 rec["cpu_baseline"]["avx_mt"] = {"error": repr(e)}
-            if cfgname in ("c1", "c2", "c3"):              # c4 / c5 frames are too large to count on one core here
-                try:
-                    rec["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)
-                    issue = issue_roofline(cfgname, rec["roofline"]["equivalent_zbuffer"]["fragments"], stage_ms["raster_kernel"],
-                                           (rec.get("clocks") or {}).get("sm_mhz"))
-                    if issue:
-                        rec["roofline"]["issue"] = issue
-                except Exception as e:
-                    rec["roofline"]["equivalent_zbuffer"] = {"error": repr(e)}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the line
             rec["cpu_baseline"] = {"value": None, "unit": unit, "cores": 0, "kind": "port",
                                    "sample": f"failed: {e!r}"}
+    if (cpu_baseline or zbuffer_roofline) and world == 1 and rank == 0 and cfgname in ("c1", "c2", "c3"):
+        # the reference algorithm's own z-buffer traffic and the raster kernel's issue roofline; both need the
+        # frame's fragment counts, which the oracle counts on one host thread (c4 / c5 frames are too large for that)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol
+            rec["roofline"]["equivalent_zbuffer"] = equivalent_zbuffer(ol, scene, tri_bytes, ms, peak)
+            issue = issue_roofline(cfgname, rec["roofline"]["equivalent_zbuffer"]["fragments"], stage_ms["raster_kernel"], None)
+            if issue:
+                rec["roofline"]["issue"] = issue
+        except Exception as e:
+            rec["roofline"]["equivalent_zbuffer"] = {"error": repr(e)}
     # release this leg's device memory before the next one
     del colors, depths, targets, frames, d_pos, d_col, d_nrm
     torch.cuda.empty_cache()
@@ -863,7 +866,8 @@ def leg_summary(rec):
     out = {k: rec[k] for k in keep if k in rec}
     out["config"] = {k: rec["config"][k] for k in ("workload", "triangles", "width", "height", "parallelism", "band_rows", "tile")}
     out["roofline"] = {k: rec["roofline"][k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic",
-                                                        "algorithmic_bytes_per_launch", "kernel_ms", "frame")}
+                                                        "algorithmic_bytes_per_launch", "kernel_ms", "frame",
+                                                        "equivalent_zbuffer", "issue") if k in rec["roofline"]}
     if "e2e" in rec:
         out["e2e"] = rec["e2e"]
     return out
@@ -882,7 +886,7 @@ def run_ours(args):
         # north_star's two numeric targets sit on C3 (4K fill, 1 GPU) and C4 (16K^2 row bands, every N):
         # short legs of both ride in the default line so that the driver's own runs carry them
         if ctx.world == 1:
-            legs["c3"] = leg_summary(run_leg(ctx, "c3", min(K, 10), 3, passes=3, e2e_steps=5))
+            legs["c3"] = leg_summary(run_leg(ctx, "c3", min(K, 10), 3, passes=3, e2e_steps=5, zbuffer_roofline=True))
         legs["c4_bands"] = leg_summary(run_leg(ctx, "c4", min(K, 3), 3, passes=3, e2e_steps=2))
     clocks = sampler.stop() if sampler else None
     if ctx.rank == 0:

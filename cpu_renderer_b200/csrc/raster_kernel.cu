@@ -208,6 +208,10 @@ constexpr int kCullTries = B200R_CULL_TRIES;
 #ifndef B200R_FLOOR_EVERY
 #define B200R_FLOOR_EVERY 256
 #endif
+// finished tiles are stored from registers (1) or packed into shared memory and bulk-copied row by row (0)
+#ifndef B200R_DIRECT_WB
+#define B200R_DIRECT_WB 1
+#endif
 // resident CTAs per SM the register allocation is held to (a 40 KB tile allows 5)
 #ifndef B200R_MINB
 #define B200R_MINB 5
@@ -628,7 +632,31 @@ raster_kernel(const __grid_constant__ RasterParams p)
         __syncthreads();
         STAT_CLOCK(t4);
 
-        // ---------------- write the tile back: depth into the plane, colour packed to [0, 4N) ------
+        // ---------------- write the tile back ------------------------------------------------------
+        // Straight from registers: thread t holds pixels t, t + NT, ... of the row-major tile, so consecutive
+        // threads write consecutive columns of a target row (128-byte stores per warp).  The first version
+        // packed depth and colour back into shared memory and issued two bulk copies per tile row; on frames
+        // whose tiles carry little work that write-back was 37 % of a tile's time (19 k of 52 k cycles per
+        // tile on a 500-triangle 4K frame, tools/raster_stats.py), the issue of 2 x rows small bulk copies
+        // behind three barriers and a proxy fence.  The shared-memory route remains for the fused gather,
+        // whose second copy of the tile goes to peer memory with bulk stores.
+        if(B200R_DIRECT_WB && p.gather_color == nullptr)
+        {
+            Pixel px[PPT];
+#pragma unroll
+            for(int k = 0; k < PPT; ++k) px[k] = tile[tid + k*NT];
+#pragma unroll
+            for(int k = 0; k < PPT; ++k)
+            {
+                const int idx = tid + k*NT, r = idx / TW, c = idx % TW;
+                if(r < rows && c < cols)
+                {
+                    p.depth[(size_t)(yb + r)*p.depth_stride + x0 + c] = __uint_as_float(px[k].z);
+                    p.color[(size_t)(yb + r)*p.color_pitch_words + x0 + c] = px[k].color;
+                }
+            }
+        }
+        else
         {
             Pixel px[PPT];
 #pragma unroll

@@ -198,10 +198,12 @@ int b200r_render_objects(b200r_context *Context, const render_entry_3d_object *O
 
 /* Replaces FillEdgeTable alone (projekt.cpp:3882): sorted edge_info records are written to
  * Object->EdgeMemory (host, room for VertexCount records) in the reference's MergeSort order
- * (projekt.cpp:2-72, ties included).  Only the fields the selected path defines are written
- * (YMin YMax XMin Gradient ZMin ZGradient MinColor ColorGradient Left, plus Next = 0; with
- * PhongShading also MinNormal and NormalGradient; with Object->Bitmap also UMin VMin OneOverZMin
- * and their gradients, and Gouraud colours are lit white as in projekt.cpp:4034-4060).
+ * (projekt.cpp:2-72, ties included; the order is produced on the device).  Every record is
+ * written whole: the fields the selected path defines (YMin YMax XMin Gradient ZMin ZGradient
+ * MinColor ColorGradient Left; with PhongShading also MinNormal and NormalGradient; with
+ * Object->Bitmap also UMin VMin OneOverZMin and their gradients, and Gouraud colours are lit white
+ * as in projekt.cpp:4034-4060), zero in the fields the reference leaves untouched for that kind
+ * of object, Next = 0.  At most 16 M triangles per object.
  * Returns the edge count (>= 0) or a negative status. */
 int b200r_fill_edge_table(b200r_context *Context, const render_entry_3d_object *Object,
                           const game_render_commands *Commands, b32 PhongShading);
