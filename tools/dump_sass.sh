@@ -3,7 +3,7 @@
 set -e
 cd /root/repo
 lib=cpu_renderer_b200/libb200raster.so
-dump() { cuobjdump -sass -fun "$1" $lib | sed -n '/Function :/,$p' > "profiles/$2"; echo "$2: $(grep -c '/\*[0-9a-f]\{4\}\*/' profiles/$2) instructions"; }
+dump() { cuobjdump -sass -fun "$1" $lib 2>/dev/null | sed -n '/Function :/,$p' > "profiles/$2"; echo "$2: $(grep -c '/\*[0-9a-f]\{4\}\*/' profiles/$2) instructions"; }
 dump _ZN5b200r12setup_kernelILb0ELb0ELb0ELb0EEEvNS_10ViewParamsENS_10MeshParamsENS_12SetupOutputsE r02_sass_setup_kernel_plain.txt
 dump _ZN5b200r12setup_kernelILb0ELb0ELb0ELb1EEEvNS_10ViewParamsENS_10MeshParamsENS_12SetupOutputsE r02_sass_setup_kernel_split.txt
 dump _ZN5b200r12setup_kernelILb0ELb0ELb1ELb0EEEvNS_10ViewParamsENS_10MeshParamsENS_12SetupOutputsE r02_sass_setup_kernel_listed.txt
