@@ -331,7 +331,7 @@ static int issue_frame(b200r_context *c)
         if(selecting && m.ntri >= kSelectMinTriangles)
         {
             unsigned *list = (unsigned *)c->sel_list.ptr + m.prim_base, *count = (unsigned *)c->sel_counts.ptr + i;
-            launch_select(v, m, list, count, words->zkeys, c->stream);
+            launch_select(v, m, list, count, words->zkeys, c->sm_count, c->stream);
             m.tri_list = list; m.tri_count = count;
         }
         else launch_zrange(m, words->zkeys, c->stream);

@@ -273,7 +273,7 @@ struct SetupOutputs
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s);
 // positions only: indices of the triangles whose projected rows can reach the band -> list, *count; the same
 // pass folds the mesh's camera z into zkeys (replaces launch_zrange for that mesh)
-void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, cudaStream_t s);
+void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, int sm_count, cudaStream_t s);
 
 // ---- FillEdgeTable's tail on the device (edge_table_kernels.cu): emission order, MergeSort order, edge_info ----
 void launch_edge_counts(const uint32_t *recs, unsigned ntri, unsigned *counts, cudaStream_t s);

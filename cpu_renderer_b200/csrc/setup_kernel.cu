@@ -149,66 +149,84 @@ __device__ __forceinline__ bool off_band_rows(float y0, float y1, float y2, cons
 // The positions are read ONCE: the same pass accumulates the frame's z range (what zrange_kernel does
 // for meshes that are not pre-selected) -- both kernels read every position, and at 8 bands that
 // read is a fifth of a GPU's whole frame.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count, unsigned *zkeys)
 {
-    // positions staged through shared memory with coalesced 128-bit loads (a thread's own nine floats are
-    // 36 bytes apart: read directly, the pass ran at 0.9 TB/s)
+    // Persistent CTAs over blocks of 256 triangles.  A block's positions (9 KB) are staged through shared memory
+    // with coalesced 128-bit loads (a thread's own nine floats are 36 bytes apart), and the NEXT block's loads are
+    // issued before this block's projections start, so that every CTA has a block in flight at all times.  (One
+    // block per CTA, load -> barrier -> compute -> atomic, read the positions at 2.3 TB/s: while a CTA computed it
+    // had nothing in flight, and that pass is a tenth of a GPU's whole frame on 8 row bands.)
     __shared__ __align__(16) float s_p[256*9];
-    const unsigned base = blockIdx.x*256u;
-    const unsigned tri = base + threadIdx.x;
-    {
-        const float *gp = m.pos + (size_t)base*9;
-        const unsigned nf = min(256u, m.ntri - base)*9u;             // floats of this block
-        if(nf == 256u*9u && (((uintptr_t)gp) & 15) == 0)
-        {
-            const float4 *g4 = reinterpret_cast<const float4 *>(gp);
-            float4 *s4 = reinterpret_cast<float4 *>(s_p);
-            float4 a = __ldg(g4 + threadIdx.x), b = __ldg(g4 + 256 + threadIdx.x);
-            float4 c4 = (threadIdx.x < 64) ? __ldg(g4 + 512 + threadIdx.x) : make_float4(0, 0, 0, 0);
-            s4[threadIdx.x] = a; s4[256 + threadIdx.x] = b;
-            if(threadIdx.x < 64) s4[512 + threadIdx.x] = c4;
-        }
-        else
-            for(unsigned i = threadIdx.x; i < nf; i += 256u) s_p[i] = __ldg(gp + i);
-    }
-    __syncthreads();
-    bool keep = false;
-    unsigned kmax = 0u, kmin = 0xffffffffu;
-    if(tri < m.ntri)
-    {
-        const float *sp = s_p + threadIdx.x*9;
-        float y[3];
-#pragma unroll
-        for(int k = 0; k < 3; ++k)
-        {
-            const float pz = sp[3*k + 2];
-            V3 cam = { fadd(sp[3*k + 0], m.px), fadd(sp[3*k + 1], m.py), fadd(pz, m.pz) };
-            y[k] = project_vertex(cam, v).y;
-            const float z = pz + m.pz;                      // as zrange_kernel
-            if(fabsf(z) < 3.0e38f) { const unsigned kk = float_key(z); kmax = max(kmax, kk); kmin = min(kmin, kk); }
-        }
-        keep = !off_band_rows(y[0], y[1], y[2], v);
-    }
-    // ONE returning atomic per block hands out the list slots: all blocks add to the same word, and
-    // same-address atomics are served one at a time (a per-warp atomic made this pass 0.6 ms on C4)
     __shared__ unsigned s_cnt[8], s_base;
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if(lane == 0) s_cnt[warp] = (unsigned)__popc(bal);
-    __syncthreads();
-    if(threadIdx.x == 0)
+    const unsigned nblocks = (m.ntri + 255u)/256u;
+    const bool aligned = (((uintptr_t)m.pos) & 15) == 0;      // a block starts 9216 bytes after the previous one
+    unsigned kmax = 0u, kmin = 0xffffffffu;
+    float4 ra = make_float4(0, 0, 0, 0), rb = ra, rc = ra;
+    auto full = [&](unsigned blk) { return aligned && blk*256u + 256u <= m.ntri; };
+    auto issue = [&](unsigned blk)
     {
-        unsigned tot = 0;
-        for(int w = 0; w < 8; ++w) { const unsigned c_ = s_cnt[w]; s_cnt[w] = tot; tot += c_; }
-        s_base = tot ? atomicAdd(count, tot) : 0u;
+        const float4 *g4 = reinterpret_cast<const float4 *>(m.pos + (size_t)blk*256u*9u);
+        ra = __ldg(g4 + threadIdx.x); rb = __ldg(g4 + 256 + threadIdx.x);
+        if(threadIdx.x < 64) rc = __ldg(g4 + 512 + threadIdx.x);
+    };
+    unsigned blk = blockIdx.x;
+    if(blk < nblocks && full(blk)) issue(blk);
+    for(; blk < nblocks; blk += gridDim.x)
+    {
+        const unsigned base = blk*256u;
+        const unsigned tri = base + threadIdx.x;
+        __syncthreads();                                    // the previous block's readers are done with s_p
+        if(full(blk))
+        {
+            float4 *s4 = reinterpret_cast<float4 *>(s_p);
+            s4[threadIdx.x] = ra; s4[256 + threadIdx.x] = rb;
+            if(threadIdx.x < 64) s4[512 + threadIdx.x] = rc;
+        }
+        else
+        {
+            const float *gp = m.pos + (size_t)base*9;
+            const unsigned nf = min(256u, m.ntri - base)*9u;
+            for(unsigned i = threadIdx.x; i < nf; i += 256u) s_p[i] = __ldg(gp + i);
+        }
+        __syncthreads();
+        const unsigned next = blk + gridDim.x;
+        if(next < nblocks && full(next)) issue(next);       // in flight while this block is projected
+        bool keep = false;
+        if(tri < m.ntri)
+        {
+            const float *sp = s_p + threadIdx.x*9;
+            float y[3];
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+            {
+                const float pz = sp[3*k + 2];
+                V3 cam = { fadd(sp[3*k + 0], m.px), fadd(sp[3*k + 1], m.py), fadd(pz, m.pz) };
+                y[k] = project_vertex(cam, v).y;
+                const float z = pz + m.pz;                      // as zrange_kernel
+                if(fabsf(z) < 3.0e38f) { const unsigned kk = float_key(z); kmax = max(kmax, kk); kmin = min(kmin, kk); }
+            }
+            keep = !off_band_rows(y[0], y[1], y[2], v);
+        }
+        // ONE returning atomic per block hands out the list slots: all blocks add to the same word, and
+        // same-address atomics are served one at a time (a per-warp atomic made this pass 0.6 ms on C4)
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if(lane == 0) s_cnt[warp] = (unsigned)__popc(bal);
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            unsigned tot = 0;
+            for(int w = 0; w < 8; ++w) { const unsigned c_ = s_cnt[w]; s_cnt[w] = tot; tot += c_; }
+            s_base = tot ? atomicAdd(count, tot) : 0u;
+        }
+        __syncthreads();
+        if(keep) list[s_base + s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = tri;
     }
-    __syncthreads();
-    if(keep) list[s_base + s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = tri;
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     kmin = __reduce_min_sync(0xffffffffu, kmin);
-    // every warp of a 20 M-triangle mesh ends here: only the few that still widen the range may touch the two
-    // words (one same-address atomic per warp serialises: 1.2 M of them cost C4 on 8 GPUs 0.3 ms)
+    // only the warps that still widen the range touch the two words (one same-address atomic per warp
+    // serialises: 1.2 M of them cost C4 on 8 GPUs 0.3 ms)
     if(lane == 0 && kmax != 0u)
     {
         if(kmax > __ldcg(&zkeys[0])) atomicMax(&zkeys[0], kmax);
@@ -1021,10 +1039,12 @@ void launch_zrange_finish(unsigned *zkeys, cudaStream_t s)
     zrange_finish_kernel<<<1, 1, 0, s>>>(zkeys);
 }
 
-void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, cudaStream_t s)
+void launch_select(const ViewParams &v, const MeshParams &m, unsigned *list, unsigned *count, unsigned *zkeys, int sm_count, cudaStream_t s)
 {
     if(m.ntri == 0) return;
-    select_kernel<<<(m.ntri + 255)/256, 256, 0, s>>>(v, m, list, count, zkeys);
+    // persistent: 8 CTAs of 256 threads per SM, fewer for small meshes
+    const unsigned nblocks = (m.ntri + 255u)/256u;
+    select_kernel<<<std::min(nblocks, (unsigned)std::max(sm_count, 1)*8u), 256, 0, s>>>(v, m, list, count, zkeys);
 }
 
 void launch_setup(const ViewParams &v, const MeshParams &m, const SetupOutputs &out, cudaStream_t s)
