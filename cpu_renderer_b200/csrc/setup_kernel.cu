@@ -102,17 +102,49 @@ __global__ void __launch_bounds__(256)
 zrange_kernel(MeshParams m, unsigned *zkeys)
 {
     // zkeys[0] = max key, zkeys[1] = max of ~key (i.e. ~min key) over camera z = vertex z + P.z
-    // (finite values only); both start at 0 so one memset initialises them
+    // (finite values only); both start at 0 so one memset initialises them.
+    // The positions are streamed with 128-bit loads, four in flight per thread, and the z components picked out
+    // of them (float 3j + 2 of the stream); one strided 4-byte load per vertex read the 36 MB of C2 at 2.1 TB/s.
     unsigned kmax = 0u, kmin = 0xffffffffu;
-    const size_t nv = (size_t)m.ntri*3;
-    for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x*blockDim.x)
+    const size_t nf = (size_t)m.ntri*9;                       // floats in the stream
+    const size_t tid = (size_t)blockIdx.x*blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x*blockDim.x;
+    auto take = [&](float zv)
     {
-        const float z = __ldg(m.pos + i*3 + 2) + m.pz;
+        const float z = zv + m.pz;
         if(fabsf(z) < 3.0e38f) { const unsigned k = float_key(z); kmax = max(kmax, k); kmin = min(kmin, k); }
+    };
+    size_t done = 0;                                          // floats covered by the vector part
+    if((((uintptr_t)m.pos) & 15) == 0)
+    {
+        const float4 *g4 = reinterpret_cast<const float4 *>(m.pos);
+        const size_t n4 = nf/4;
+        for(size_t i0 = tid; i0 < n4; i0 += 4*nthreads)
+        {
+            float4 q[4];
+#pragma unroll
+            for(int u = 0; u < 4; ++u) { const size_t i = i0 + u*nthreads; q[u] = (i < n4) ? __ldg(g4 + i) : make_float4(0, 0, 0, 0); }
+#pragma unroll
+            for(int u = 0; u < 4; ++u)
+            {
+                const size_t i = i0 + u*nthreads;
+                if(i >= n4) break;
+                const unsigned r = (unsigned)((4*i) % 3);     // component k of this vector is a z iff (r + k) % 3 == 2
+                if(r == 2) { take(q[u].x); take(q[u].w); }
+                else if(r == 1) take(q[u].y);
+                else take(q[u].z);
+            }
+        }
+        done = n4*4;
     }
+    for(size_t f = done + tid; f < nf; f += nthreads)
+        if(f % 3 == 2) take(__ldg(m.pos + f));
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     kmin = __reduce_min_sync(0xffffffffu, kmin);
-    if((threadIdx.x & 31) == 0 && kmax != 0u) { atomicMax(&zkeys[0], kmax); atomicMax(&zkeys[1], ~kmin); }
+    if((threadIdx.x & 31) == 0 && kmax != 0u)
+    {
+        if(kmax > __ldcg(&zkeys[0])) atomicMax(&zkeys[0], kmax);
+        if(~kmin > __ldcg(&zkeys[1])) atomicMax(&zkeys[1], ~kmin);
+    }
 }
 
 __global__ void zrange_finish_kernel(unsigned *zkeys)
@@ -1030,7 +1062,7 @@ setup_kernel(ViewParams v, MeshParams m, SetupOutputs out)
 void launch_zrange(const MeshParams &m, unsigned *zkeys, cudaStream_t s)
 {
     if(m.ntri == 0) return;
-    unsigned blocks = (unsigned)std::min<size_t>(((size_t)m.ntri*3 + 255)/256, 148*8);
+    unsigned blocks = (unsigned)std::min<size_t>(((size_t)m.ntri*9/16 + 255)/256 + 1, 148*8);
     zrange_kernel<<<blocks, 256, 0, s>>>(m, zkeys);
 }
 
