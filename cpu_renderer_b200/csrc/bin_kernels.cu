@@ -125,6 +125,7 @@ scatter_kernel(const ScatterParams p)
             if(has)
             {
                 const unsigned q = qn + (unsigned)__popc(bal & ((1u << lane) - 1u));
+                B200R_ASSERT(q < (unsigned)kRunQueue && si.nrows <= 255u);
                 s_slot[warp][q] = slot; s_base[warp][q] = si.span_base; s_rows[warp][q] = (unsigned char)si.nrows;
             }
             qn += (unsigned)__popc(bal);

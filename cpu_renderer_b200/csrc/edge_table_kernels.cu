@@ -2,14 +2,13 @@
 // (projekt.cpp:3947, 4113-4115) and put them into the order the reference's MergeSort leaves them in
 // (projekt.cpp:2-72, called at :4117), then assemble edge_info records (projekt.h:17-37).
 //
-// MergeSort is NOT stable: on equal YMin the merge takes the RIGHT half first (:51-58) while the
-// two-element base case keeps the left element first (:13).  The resulting order is nevertheless a pure
-// function of (YMin, position before the sort): follow the recursion from the root (Half0 = Count/2,
-// :21-22) down to an element and note, per level, whether it sits on the side that wins ties.  Those
-// bits, most significant first, are a key under which ANY correct sort reproduces the reference's
-// permutation -- keys are unique, so stability and the shape of the device sort do not matter:
+// MergeSort is NOT stable, but its order is a pure function of (YMin, position before the sort)
+// (merge_order.h): under the key
 //
-//   key(i) = (YMin(i) as ordered 32 bits) << 32 | tie_path(i, n)
+//   key(i) = (YMin(i) as ordered 32 bits) << 32 | b200r_merge_tie_path(i, n)
+//
+// ANY correct sort reproduces the reference's permutation -- keys are unique, so stability and the shape
+// of the device sort do not matter.
 //
 // Kernels: edge counts per triangle -> chained scan (bin_kernels.cu) -> keys and payloads ->
 // 2048-element bitonic tiles in shared memory -> log2(n / 2048) rank-merge passes (every element finds
@@ -17,6 +16,7 @@
 // assemble.  The first version did this on the host (D2H of the per-triangle records, std::sort, H2D
 // for the whole-object mode).
 #include "raster_device.cuh"
+#include "merge_order.h"
 
 namespace b200r {
 
@@ -34,23 +34,6 @@ struct EdgeOut
     long long Next;
 };
 static_assert(sizeof(EdgeOut) == 120, "edge_info is 120 bytes");
-
-// position of element i of n in MergeSort's tie order, as left-aligned path bits (0 = wins ties)
-__device__ __forceinline__ unsigned merge_tie_path(unsigned i, unsigned n)
-{
-    unsigned key = 0, lo = 0, cnt = n;
-    int depth = 0;
-    while(cnt > 2)
-    {
-        const unsigned half0 = cnt/2;                       // projekt.cpp:21
-        unsigned bit;
-        if(i - lo < half0) { bit = 1; cnt = half0; }        // left half: loses ties (:51-58)
-        else { bit = 0; lo += half0; cnt -= half0; }
-        key = (key << 1) | bit; ++depth;
-    }
-    if(cnt == 2) { key = (key << 1) | (i - lo); ++depth; }  // base case: left first (:13)
-    return depth ? key << (32 - depth) : 0u;
-}
 
 __global__ void __launch_bounds__(256)
 edge_count_kernel(const uint32_t *__restrict__ recs, unsigned ntri, unsigned *__restrict__ counts)
@@ -74,7 +57,8 @@ edge_key_kernel(const uint32_t *__restrict__ recs, unsigned ntri, const unsigned
         const unsigned slot = (emit >> (2*k)) & 3u;
         const uint32_t ymin = rec[R_EDGE0 + slot*kEdgeWords + E_YMIN];
         const unsigned i = at + k;
-        keys[i] = ((unsigned long long)(ymin ^ 0x80000000u) << 32) | merge_tie_path(i, n);
+        B200R_ASSERT(i < n);
+        keys[i] = ((unsigned long long)(ymin ^ 0x80000000u) << 32) | b200r_merge_tie_path(i, n);
         vals[i] = (tri << 2) | slot;
     }
 }
@@ -137,6 +121,7 @@ edge_merge_kernel(const unsigned long long *__restrict__ kin, const unsigned *__
         if(kin[sib + mid] < key) lo = mid + 1; else hi = mid;
     }
     const unsigned dst = pair0 + (i - mine) + lo;
+    B200R_ASSERT(dst < n);
     kout[dst] = key; vout[dst] = vin[i];
 }
 

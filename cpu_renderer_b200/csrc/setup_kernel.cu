@@ -253,6 +253,7 @@ select_kernel(ViewParams v, MeshParams m, unsigned *list, unsigned *count, unsig
             s_base = tot ? atomicAdd(count, tot) : 0u;
         }
         __syncthreads();
+        B200R_ASSERT(!keep || s_base + s_cnt[warp] + __popc(bal & ((1u << lane) - 1u)) < m.ntri);
         if(keep) list[s_base + s_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = tri;
     }
     kmax = __reduce_max_sync(0xffffffffu, kmax);
