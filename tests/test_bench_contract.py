@@ -51,3 +51,42 @@ def test_reference_arm_other_ranks_stay_silent():
 def test_reference_arm_textured_phong_variant():
     d = run_reference("--config", "c2", "--textured", "--phong")
     assert "Bitmap" in d["cpu_baseline"]["sample"] and "PhongShading" in d["cpu_baseline"]["sample"]
+
+
+def _archived(name):
+    p = os.path.join(ROOT, "profiles", name)
+    lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
+    assert len(lines) == 1, name
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("name,n", [("r02_bench_default.json", 1), ("r02_bench_default_n2.json", 2), ("r02_bench_default_n8.json", 8)])
+def test_archived_gpu_lines_carry_the_contract(name, n):
+    """The lines archived under profiles/ (what the README tables are printed from) are ONE JSON line each with
+    every key of the contract, consistent with each other, and every image hash equal to the oracle's."""
+    d = _archived(name)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "gpu_launches", "e2e", "roofline", "clocks", "stage_ms", "legs"):
+        assert key in d, key
+    assert d["n_gpus"] == n and d["metric"] == d["unit"] == "Mtriangles/s" and d["vs_baseline"] is None
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    # value = the units all ranks processed / the max-over-ranks time
+    assert abs(d["value"] - n * d["config"]["triangles"] / (d["ms_per_step"] * 1e-3) / 1e6) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["traffic"] and r["traffic"] > r["algorithmic_bytes_per_launch"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["image_ok"] is True and e["image_ok"] is True
+    c4 = d["legs"]["c4_bands"]
+    assert c4["image_ok"] is True and c4["scaling"] == "strong" and c4["config"]["band_rows"] * n >= 16384
+    if n == 1:
+        assert d["legs"]["c3"]["image_ok"] is True and "issue" in d["legs"]["c3"]["roofline"]
+        cb = d["cpu_baseline"]
+        assert cb["kind"] == "reference" and cb["scalar_mt"]["whole_frame"] is True and "avx_mt" in cb
+    else:
+        assert d["with_gather"]["images_match_the_ranks_frames"] is True
+        assert c4["with_gather"]["ms_per_step"] < c4["with_gather_nccl"]["ms_per_step"]
