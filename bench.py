@@ -834,6 +834,14 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
                                                  "whole_frame": sample == ntri,
                                                  "path": "verbatim FillEdgeTable + DrawModel per triangle, object-parallel over the host threads"}}
             try:
+                # SURVEY.md 8d, CPU baseline (1): the same scalar path on ONE host thread (one step, no warm-up)
+                one = time_cpu(ol, s, 1, 1, 0, kind, phong)
+                rec["cpu_baseline"]["scalar_1t"] = {"value": units / (one["ms_per_step"] * 1e-3) / 1e6, "unit": unit, "cores": 1,
+                                                    "ms_per_step": one["ms_per_step"], "whole_frame": sample == ntri,
+                                                    "path": "verbatim FillEdgeTable + DrawModel per triangle, one host thread"}
+            except Exception as e:
+                rec["cpu_baseline"]["scalar_1t"] = {"error": repr(e)}
+            try:
                 r.set_stream(0); r.set_tile(64, 32)
                 rec["cpu_baseline"]["avx_mt"] = avx_baseline(r)
             except Exception as e:
