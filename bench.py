@@ -258,6 +258,20 @@ def equivalent_zbuffer(ol, scene, tri_bytes, frame_ms, peak_gbs):
             "what": "z-buffer traffic of the reference's own algorithm for this frame / our frame time (not HBM traffic)"}
 
 
+def compare_with_oracle(ol, scene, color, depth, phong):
+    """The rendered frame against the CPU oracle's of the same scene: pixels whose depth bits differ, pixels whose
+    colour differs in any channel, the largest channel difference in LSB, and how many pixels took a clamped texel
+    (where the reference reads outside its bitmap; golden colour is defined by the clamp there)."""
+    want = ol.oracle_render(scene, phong=phong)
+    zdiff = int((want["z"].view(np.uint32) != depth.view(np.uint32)).sum())
+    ch = np.abs(want["color"].view(np.uint8).astype(np.int16) - color.view(np.uint8).astype(np.int16))
+    per_pixel = ch.reshape(color.shape[0], color.shape[1], 4).max(axis=2)
+    return {"pixels": int(color.size), "depth_pixels_differing": zdiff,
+            "colour_pixels_differing": int((per_pixel != 0).sum()), "colour_max_lsb": int(per_pixel.max()),
+            "texel_clamps": int(want["stats"].get("TexelClamps", 0)),
+            "what": "end-to-end frame vs the CPU oracle (oracle/raster_oracle.c) on the same scene"}
+
+
 def issue_roofline(config, fragments, raster_ms, sm_mhz):
     """The raster kernel's second roofline: instruction issue.  With tiles resident in shared memory the
     kernel moves few HBM bytes per fragment but executes instructions for every one of them, so the bound
@@ -644,6 +658,7 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
             with_gather, gather_nccl = gather_nccl, None
 
     whole_object = None
+    shaded_vs_oracle = None
     # ---- end to end: host buffers in, host buffers out, copies inside the timed region ---------
     pin = lambda a: torch.from_numpy(a).pin_memory()              # noqa: E731
     e2e = None
@@ -669,6 +684,16 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
         covered = int((hz[0] != np.float32(scene.clear_depth)).sum())
         e2e_fnv = imagehash.image_fnv_numpy(hcol[0])
         e2e_api = "b200r_render_objects (host pointers, pinned)"
+        shaded_vs_oracle = None
+        if (phong or textured) and rank == 0 and world == 1 and scale * ntri <= 2_000_000:
+            # the Phong / textured frames have no committed hash: compare the end-to-end frame with the CPU oracle's
+            # here and say how many pixels differ and by how much (the Phong bar is +-1 LSB per channel)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                import oracle_lib as ol
+                shaded_vs_oracle = compare_with_oracle(ol, scene, hcol[0], hz[0], phong)
+            except Exception as e:
+                shaded_vs_oracle = {"error": repr(e)}
         if c1_whole_object and rank == 0:
             # the same frame as ONE object through the whole-object mode, beside the
             # verbatim reference's own call pair on one host core (it is a single-threaded path)
@@ -794,6 +819,7 @@ def run_leg(ctx, cfgname, K, Wm, *, passes=PASSES, scale=1.0, phong=False, textu
         "frame_ms": ms / nframes,
         "gpu_launches": int(launches),
         **({"whole_object": whole_object} if whole_object else {}),
+        **({"shaded_vs_oracle": shaded_vs_oracle} if (e2e_steps > 0 and not clear_in_step and shaded_vs_oracle) else {}),
         "stage_ms": stage_ms,
         "binner": {"binned_triangles": stats["Binned"], "segments": stats["Segments"], "spans": stats["Spans"],
                    "queue_entries": stats["TilePairs"], "tiles": stats["Tiles"], "reruns": stats["Reruns"]},
